@@ -1,0 +1,157 @@
+/* magot_b200.h -- C ABI of libmagot_b200.so: the B200 (sm_100a) implementation of MAGOT's
+ * annotation-driven sequence path (FASTA + GFF3/GTF -> spliced CDS/transcript nucleotides ->
+ * reverse complement -> protein -> six-frame/ORF scan).
+ *
+ * The reference (pure Python 2.7, /root/reference/genome.py) has no FFI layer; its boundary is
+ * the Python API.  Every entry point below therefore cites the reference function(s) whose work
+ * it replaces; `magot_b200/genome.py` binds them with ctypes behind the unchanged Python API and
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * MG_E* code, with a thread-local message available from mg_last_error(); no exceptions, no
+ * callbacks.  The caller owns every buffer it passes; the library owns what sits behind a handle.
+ * `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  A handle is
+ * bound to one CUDA device; calls on one handle must be serialised by the caller, different
+ * handles/devices may be driven from different host threads.  There is NO CPU fallback: without
+ * a CUDA device every compute entry point fails with MG_ECUDA.
+ */
+#ifndef MAGOT_B200_H
+#define MAGOT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_VERSION 100            /* 0.1.0 */
+
+enum {
+    MG_OK = 0,
+    MG_EINVAL = -1,               /* bad argument */
+    MG_ECUDA = -2,                /* CUDA runtime error / no device */
+    MG_ENOMEM = -3,
+    MG_ESTATE = -4                /* call order violated (e.g. emit before prepare) */
+};
+
+typedef struct mg_genome mg_genome;   /* device-resident packed genome            */
+typedef struct mg_plan mg_plan;       /* device-resident interval/record tables   */
+
+/* ---- introspection ---------------------------------------------------------------------- */
+int mg_version(void);
+const char *mg_last_error(void);
+int mg_device_count(int *n_out);
+
+/* ---- K0: genome storage -- replaces GenomeSequence.__init__ (genome.py:856-877, storage only)
+ * The genome lives on the device as one nibble per base (0.5 B/base):
+ *   0-3 = A C G T, 4-7 = a c g t, 8 = N, 9 = n, 10 = '-', 11-14 = R Y K M, 15 = "exception":
+ * any other byte (the reference keeps every FASTA byte verbatim on '+' strand output,
+ * genome.py:606) is recorded in a sorted (position, byte) side list.                         */
+int mg_genome_create(int device, int64_t n_contigs, const int64_t *contig_len, mg_genome **out);
+/* Pack `n` ASCII bytes (newlines already removed) of contig `contig` starting at 0-based
+ * `offset` inside it.  `ascii` is a HOST pointer (pinned or pageable); `offset` must be a
+ * multiple of 32 unless it ends the contig.  Chunks may arrive in any order.                */
+int mg_genome_pack(mg_genome *g, int64_t contig, int64_t offset, const uint8_t *ascii, int64_t n, void *stream);
+/* Same, from a DEVICE pointer (used when the text is produced on the device).               */
+int mg_genome_pack_device(mg_genome *g, int64_t contig, int64_t offset, const uint8_t *ascii_dev, int64_t n, void *stream);
+/* Sort the exception list and make the genome usable by every call below.                   */
+int mg_genome_finalize(mg_genome *g, int64_t *n_exceptions_out);
+int mg_genome_destroy(mg_genome *g);
+int64_t mg_genome_bytes(const mg_genome *g);          /* device bytes held by the handle      */
+/* Decode contig[lo:hi) (0-based, half open, already clamped) back to the exact FASTA bytes;
+ * minus != 0 gives Sequence.reverse_compliment of it (genome.py:784-793).  Backs
+ * GenomeSequence.__getitem__/slicing, coords2fasta (genome_tools.py:656-661),
+ * get_scaffold_fasta (genome.py:907) and BaseAnnotation.get_seq (genome.py:603-608).        */
+int mg_genome_fetch(mg_genome *g, int64_t contig, int64_t lo, int64_t hi, int minus, uint8_t *out_host, void *stream);
+
+/* ---- K1: interval tables -- replaces the per-child work of ParentAnnotation.get_fasta
+ * (genome.py:687-705) and the slice arithmetic of BaseAnnotation.get_seq (genome.py:603-608).
+ * A plan is a list of n_rec output records.  Record r owns segments
+ * [rec_seg_off[r], rec_seg_off[r+1]) ALREADY in the reference's emission order (sorted by
+ * coords, duplicates collapsed, reversed when the last child's strand is '-'), plus a literal
+ * prefix (e.g. ">ID\n") and suffix (e.g. "\n") taken from `lit` at rec_lit_off[r]
+ * (prefix bytes immediately followed by suffix bytes).
+ * Segment coordinates are the raw, sorted GFF pair (start,end), 1-based inclusive; the device
+ * applies Python slice semantics contig[start-1:end] including negative / out-of-range values.
+ * seg_strand: 0 = '+' or '.', 1 = '-' (reverse-complement that segment).
+ * rec_phase (may be NULL): phase of the first segment in emission order, used only with
+ * MG_PROT_USE_PHASE.                                                                          */
+int mg_plan_create(mg_genome *g, int64_t n_rec, const int64_t *rec_seg_off,
+                   int64_t n_seg, const int32_t *seg_contig, const int64_t *seg_start,
+                   const int64_t *seg_end, const int8_t *seg_strand,
+                   const int64_t *rec_lit_off, const int32_t *rec_pre_len, const int32_t *rec_suf_len,
+                   const uint8_t *lit, int64_t n_lit, const int8_t *rec_phase,
+                   void *stream, mg_plan **out);
+int mg_plan_destroy(mg_plan *p);
+
+/* flags for mg_plan_prepare / emit */
+#define MG_PROT_TRIMX      1      /* Sequence.translate(trimX=True): drop ONE leading 'X' (genome.py:819-821) */
+#define MG_PROT_USE_PHASE  2      /* non-reference extension: start at the GFF phase of the first segment     */
+
+/* Clamp, measure and scan (warp/block prefix sums on the device).  Outputs (host, may be NULL):
+ * total bytes of the nucleotide text and of the protein text (literals included).
+ * Must be called once before any emit; everything stays on the device.                      */
+int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, int64_t *prot_total, void *stream);
+/* Per-record payload lengths to the host (for `longest=True`, genome.py:720-724).
+ * nuc_len[r] = spliced bases; aa_len[r] = amino acids, or -1 where the reference's translate
+ * returns None (spliced length <= 2, genome.py:810).  Either pointer may be NULL.           */
+int mg_plan_lengths(mg_plan *p, int64_t *nuc_len, int64_t *aa_len, void *stream);
+
+/* ---- K2: spliced nucleotides (+ per-segment reverse complement, + literal framing) ---------
+ * replaces ParentAnnotation.get_fasta seq_type="nucleotide" (genome.py:687-710) and
+ * Sequence.reverse_compliment (genome.py:784-793).  `out_dev` must be 16-byte aligned and hold
+ * nuc_total rounded up to a multiple of 16 bytes.                                            */
+int mg_emit_nuc_device(mg_plan *p, uint8_t *out_dev, void *stream);
+/* ---- K3: protein -- replaces Sequence.translate(frame=0,strand='+') (genome.py:795-822) on the
+ * spliced sequence (genome.py:707).  Same buffer rules with prot_total.                     */
+int mg_emit_prot_device(mg_plan *p, uint8_t *out_dev, void *stream);
+/* Host-buffer variants: run the kernel into a library-owned device buffer and copy the exact
+ * text (nuc_total / prot_total bytes) to `out_host` (pinned for full PCIe speed).  The copy is
+ * stream-ordered; call mg_stream_sync before reading.                                        */
+int mg_emit_nuc_host(mg_plan *p, uint8_t *out_host, void *stream);
+int mg_emit_prot_host(mg_plan *p, uint8_t *out_host, void *stream);
+
+/* ---- Sequence ops on arbitrary strings -----------------------------------------------------
+ * mg_revcomp: Sequence.reverse_compliment (genome.py:784-793) of n host bytes.
+ * mg_translate_ascii: Sequence.translate(frame, strand, trimX) (genome.py:795-822) of n_seq
+ * strings stored back to back (seq i = in[off[i], off[i+1])), all with the same parameters --
+ * backs cds2pep (genome_tools.py:664-675).  out_off[n_seq+1] receives the offsets of the results
+ * in `out` (capacity out_cap bytes; (n+2)/3 + n_seq always suffices); out_len[i] = -1 where
+ * the reference returns None.                                                                */
+int mg_revcomp(int device, const uint8_t *in_host, int64_t n, uint8_t *out_host, void *stream);
+int mg_translate_ascii(int device, const uint8_t *in_host, const int64_t *off, int64_t n_seq,
+                       int frame, int minus, int trimX, uint8_t *out_host, int64_t out_cap,
+                       int64_t *out_off, int64_t *out_len, void *stream);
+
+/* ---- K4: six-frame translation + ORF scan -- replaces Sequence.get_orfs (genome.py:824-851)
+ * over whole contigs [contig_lo, contig_hi).  Streams are visited in the reference's order
+ * (frame 0 '-', 0 '+', 1 '-', 1 '+', 2 '-', 2 '+'; genome.py:829-830) with its frame quirk;
+ * each translation is split on '*'; ORFs shorter than min_aa are dropped (0 == reference,
+ * empty strings included).  Pass 1 counts, pass 2 emits.                                    */
+typedef struct {
+    int32_t contig;
+    int8_t frame;                 /* 0,1,2 : the `frame` argument of translate()              */
+    int8_t minus;                 /* 1 = translated from the reverse complement               */
+    int16_t pad;
+    int64_t start;                /* index of the ORF's first residue in that translation     */
+    int64_t len;                  /* residues                                                 */
+    int64_t aa_off;               /* offset of its text in the emitted amino-acid buffer      */
+} mg_orf;
+int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig_hi, int64_t min_aa,
+                      int64_t *n_orf, int64_t *n_bytes, void *stream);
+/* Emits the result of the preceding mg_sixframe_count on this genome handle.  aa_out_host gets
+ * n_bytes residues (ORFs back to back, no separators), recs_host n_orf records.  Either may
+ * be NULL.  *_device variant leaves the residues in `aa_out_dev` (16-byte aligned, n_bytes
+ * rounded up to 16).                                                                          */
+int mg_sixframe_emit(mg_genome *g, uint8_t *aa_out_host, mg_orf *recs_host, void *stream);
+int mg_sixframe_emit_device(mg_genome *g, uint8_t *aa_out_dev, mg_orf *recs_dev, void *stream);
+
+/* ---- timing / sync helpers ----------------------------------------------------------------- */
+int mg_stream_sync(int device, void *stream);
+/* Number of kernels launched by this library since load (per process), for bench accounting. */
+int64_t mg_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGOT_B200_H */

@@ -1,0 +1,360 @@
+// mg_genome.cu -- K0: device-resident nibble-packed genome (replaces the storage half of
+// GenomeSequence.__init__, genome.py:856-877) and range decode (GenomeSequence slicing,
+// coords2fasta genome_tools.py:656-661, BaseAnnotation.get_seq genome.py:603-608).
+#include <algorithm>
+#include <numeric>
+#include <stdarg.h>
+#include <string.h>
+#include "mg_common.cuh"
+
+// ---- error plumbing / misc API -------------------------------------------------------------------
+static thread_local char t_err[512] = "";
+int64_t g_mg_launches = 0;
+
+void mg_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int mg_version(void) { return MG_VERSION; }
+extern "C" const char *mg_last_error(void) { return t_err; }
+extern "C" int64_t mg_kernel_launches(void) { return g_mg_launches; }
+
+extern "C" int mg_device_count(int *n_out) {
+    MG_REQUIRE(n_out != nullptr, "n_out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *n_out = 0;
+        mg_set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return MG_ECUDA;
+    }
+    *n_out = n;
+    return MG_OK;
+}
+
+extern "C" int mg_stream_sync(int device, void *stream) {
+    MG_CUDA(cudaSetDevice(device));
+    MG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return MG_OK;
+}
+
+// ---- 4096-entry translation table -----------------------------------------------------------------
+// index = n0 | n1<<4 | n2<<8 (n0 = first base of the codon, nibble codes as above).  Any nibble >= 8
+// (N, n, '-', IUPAC, exception) gives 'X' (genome.py:816-817); case bit 2 is ignored, which is the
+// `.upper()` of genome.py:812.  Amino acids follow the reference's table (genome.py:795-802).
+static void build_aa4096(uint8_t *t) {
+    // reference table is indexed T,C,A,G; our base codes are A=0,C=1,G=2,T=3
+    static const char *tcag = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    static const int to_tcag[4] = {2, 1, 3, 0};
+    for (int i = 0; i < 4096; i++) {
+        const int n0 = i & 15, n1 = (i >> 4) & 15, n2 = (i >> 8) & 15;
+        if (n0 >= 8 || n1 >= 8 || n2 >= 8) {
+            t[i] = 'X';
+        } else {
+            t[i] = (uint8_t)tcag[to_tcag[n0 & 3] * 16 + to_tcag[n1 & 3] * 4 + to_tcag[n2 & 3]];
+        }
+    }
+}
+
+// ---- create / destroy -----------------------------------------------------------------------------
+extern "C" int mg_genome_create(int device, int64_t n_contigs, const int64_t *contig_len, mg_genome **out) {
+    MG_REQUIRE(out != nullptr, "out is NULL");
+    MG_REQUIRE(n_contigs >= 0 && (n_contigs == 0 || contig_len != nullptr), "bad contig table");
+    int ndev = 0;
+    int rc = mg_device_count(&ndev);
+    if (rc != MG_OK) return rc;
+    if (device < 0 || device >= ndev) {
+        mg_set_error("device %d not available (%d CUDA devices); libmagot_b200 has no CPU fallback", device, ndev);
+        return MG_ECUDA;
+    }
+    MG_CUDA(cudaSetDevice(device));
+    mg_genome *g = new mg_genome();
+    g->device = device;
+    g->n_contigs = n_contigs;
+    g->h_contig_len.assign(contig_len, contig_len + n_contigs);
+    g->h_contig_base.resize(n_contigs + 1);
+    int64_t base = MG_FRONT_PAD;
+    for (int64_t c = 0; c < n_contigs; c++) {
+        if (contig_len[c] < 0) { delete g; mg_set_error("negative contig length"); return MG_EINVAL; }
+        g->h_contig_base[c] = base;
+        base += (contig_len[c] + 31) / 32 * 32;
+    }
+    g->h_contig_base[n_contigs] = base;
+    g->total_bases = base;
+    const int64_t words = base / 8 + MG_TAIL_WORDS;
+    MG_CUDA(cudaMalloc(&g->d_packed, words * sizeof(uint32_t)));
+    // padding decodes as 'N' (0x8 per nibble) so that stray reads are harmless and deterministic
+    MG_CUDA(cudaMemset(g->d_packed, 0x88, words * sizeof(uint32_t)));
+    MG_CUDA(cudaMalloc(&g->d_contig_len, std::max<int64_t>(1, n_contigs) * sizeof(int64_t)));
+    MG_CUDA(cudaMalloc(&g->d_contig_base, (n_contigs + 1) * sizeof(int64_t)));
+    if (n_contigs) MG_CUDA(cudaMemcpy(g->d_contig_len, contig_len, n_contigs * sizeof(int64_t), cudaMemcpyHostToDevice));
+    MG_CUDA(cudaMemcpy(g->d_contig_base, g->h_contig_base.data(), (n_contigs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    MG_CUDA(cudaMalloc(&g->d_exc_count, sizeof(unsigned long long)));
+    g->exc_cap = 1 << 16;
+    MG_CUDA(cudaMalloc(&g->d_exc_pos, g->exc_cap * sizeof(int64_t)));
+    MG_CUDA(cudaMalloc(&g->d_exc_byte, g->exc_cap));
+    uint8_t tbl[4096];
+    build_aa4096(tbl);
+    MG_CUDA(cudaMalloc(&g->d_aa4096, 4096));
+    MG_CUDA(cudaMemcpy(g->d_aa4096, tbl, 4096, cudaMemcpyHostToDevice));
+    g->device_bytes = words * 4 + (2 * n_contigs + 1) * 8 + 4096;
+    // keep freed stream-ordered allocations cached: plans are created and destroyed per batch
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = g;
+    return MG_OK;
+}
+
+void mg_sixframe_free(mg_genome *g);
+
+extern "C" int mg_genome_destroy(mg_genome *g) {
+    if (!g) return MG_OK;
+    cudaSetDevice(g->device);
+    mg_sixframe_free(g);
+    cudaFree(g->d_packed);
+    cudaFree(g->d_contig_len);
+    cudaFree(g->d_contig_base);
+    cudaFree(g->d_exc_pos);
+    cudaFree(g->d_exc_byte);
+    cudaFree(g->d_exc_count);
+    cudaFree(g->d_stage);
+    cudaFree(g->d_aa4096);
+    if (g->h_pin) cudaFreeHost(g->h_pin);
+    delete g;
+    return MG_OK;
+}
+
+extern "C" int64_t mg_genome_bytes(const mg_genome *g) { return g ? g->device_bytes : 0; }
+
+int mg_ensure_stage(mg_genome *g, int64_t bytes) {
+    if (g->stage_cap >= bytes) return MG_OK;
+    if (g->d_stage) MG_CUDA(cudaFree(g->d_stage));
+    g->d_stage = nullptr;
+    g->stage_cap = 0;
+    MG_CUDA(cudaMalloc(&g->d_stage, bytes));
+    g->stage_cap = bytes;
+    return MG_OK;
+}
+
+int mg_ensure_pin(mg_genome *g, int64_t bytes) {
+    if (g->pin_cap >= bytes) return MG_OK;
+    if (g->h_pin) MG_CUDA(cudaFreeHost(g->h_pin));
+    g->h_pin = nullptr;
+    g->pin_cap = 0;
+    MG_CUDA(cudaMallocHost(&g->h_pin, bytes));
+    g->pin_cap = bytes;
+    return MG_OK;
+}
+
+// ---- K0 pack kernel ---------------------------------------------------------------------------------
+// One thread packs 16 ASCII bytes (one 16-byte load) into 2 words (one 8-byte store).  HBM traffic:
+// 1 B/base read + 0.5 B/base written.  Bytes outside the 15-symbol alphabet become code 15 and are
+// appended to the exception list (rare in real assemblies; dense lists still work, only slower).
+__global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ ascii, int64_t n, int64_t g0,
+                                              uint32_t *__restrict__ packed, int64_t *__restrict__ exc_pos,
+                                              uint8_t *__restrict__ exc_byte, int64_t exc_cap,
+                                              unsigned long long *__restrict__ exc_count) {
+    const int64_t nchunk = (n + 15) >> 4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nchunk; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b0 = i << 4;
+        uint32_t w[4];
+        if (b0 + 16 <= n) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ascii + b0));
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+            w[0] = w[1] = w[2] = w[3] = 0x4E4E4E4Eu;   // 'N' padding past the end of the chunk
+            for (int k = 0; b0 + k < n; k++) {
+                const uint32_t c = ascii[b0 + k];
+                w[k >> 2] = (w[k >> 2] & ~(0xFFu << ((k & 3) * 8))) | (c << ((k & 3) * 8));
+            }
+        }
+        uint32_t o[2] = {0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint8_t c = (uint8_t)(w[k >> 2] >> ((k & 3) * 8));
+            const uint32_t code = mg_encode(c);
+            o[k >> 3] |= code << ((k & 7) * 4);
+            if (code == MG_CODE_EXC && b0 + k < n) {
+                const unsigned long long slot = atomicAdd(exc_count, 1ull);
+                if ((int64_t)slot < exc_cap) {
+                    exc_pos[slot] = g0 + b0 + k;
+                    exc_byte[slot] = c;
+                }
+            }
+        }
+        *reinterpret_cast<uint2 *>(packed + ((g0 + b0) >> 3)) = make_uint2(o[0], o[1]);
+    }
+}
+
+static int pack_device_chunk(mg_genome *g, int64_t gbase, const uint8_t *d_ascii, int64_t n, cudaStream_t st) {
+    for (;;) {
+        MG_CUDA(cudaMemsetAsync(g->d_exc_count, 0, sizeof(unsigned long long), st));
+        const int64_t nchunk = (n + 15) / 16;
+        const int blocks = (int)std::min<int64_t>((nchunk + 255) / 256, 148 * 16);
+        k_pack<<<std::max(blocks, 1), 256, 0, st>>>(d_ascii, n, gbase, g->d_packed, g->d_exc_pos, g->d_exc_byte,
+                                                   g->exc_cap, g->d_exc_count);
+        MG_LAUNCH_CHECK();
+        unsigned long long cnt = 0;
+        MG_CUDA(cudaMemcpyAsync(&cnt, g->d_exc_count, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        MG_CUDA(cudaStreamSynchronize(st));
+        if ((int64_t)cnt > g->exc_cap) {              // rare: grow and redo this chunk
+            MG_CUDA(cudaFree(g->d_exc_pos));
+            MG_CUDA(cudaFree(g->d_exc_byte));
+            g->exc_cap = (int64_t)cnt + 1024;
+            MG_CUDA(cudaMalloc(&g->d_exc_pos, g->exc_cap * sizeof(int64_t)));
+            MG_CUDA(cudaMalloc(&g->d_exc_byte, g->exc_cap));
+            continue;
+        }
+        if (cnt) {
+            const size_t old = g->h_exc_pos.size();
+            g->h_exc_pos.resize(old + cnt);
+            g->h_exc_byte.resize(old + cnt);
+            MG_CUDA(cudaMemcpy(g->h_exc_pos.data() + old, g->d_exc_pos, cnt * sizeof(int64_t), cudaMemcpyDeviceToHost));
+            MG_CUDA(cudaMemcpy(g->h_exc_byte.data() + old, g->d_exc_byte, cnt, cudaMemcpyDeviceToHost));
+        }
+        return MG_OK;
+    }
+}
+
+static int check_pack_args(mg_genome *g, int64_t contig, int64_t offset, const void *p, int64_t n) {
+    MG_REQUIRE(g != nullptr, "genome handle is NULL");
+    MG_REQUIRE(contig >= 0 && contig < g->n_contigs, "contig index out of range");
+    MG_REQUIRE(n >= 0 && offset >= 0 && offset + n <= g->h_contig_len[contig], "chunk outside the contig");
+    MG_REQUIRE(n == 0 || p != nullptr, "ascii is NULL");
+    MG_REQUIRE(offset % 32 == 0, "chunk offset must be a multiple of 32 bases");
+    MG_REQUIRE(n % 32 == 0 || offset + n == g->h_contig_len[contig], "chunk length must be a multiple of 32 unless it ends the contig");
+    return MG_OK;
+}
+
+extern "C" int mg_genome_pack_device(mg_genome *g, int64_t contig, int64_t offset, const uint8_t *ascii_dev,
+                                     int64_t n, void *stream) {
+    int rc = check_pack_args(g, contig, offset, ascii_dev, n);
+    if (rc) return rc;
+    MG_REQUIRE(((uintptr_t)ascii_dev & 15) == 0, "device text must be 16-byte aligned");
+    MG_CUDA(cudaSetDevice(g->device));
+    g->finalized = false;
+    if (n == 0) return MG_OK;
+    return pack_device_chunk(g, g->h_contig_base[contig] + offset, ascii_dev, n, (cudaStream_t)stream);
+}
+
+extern "C" int mg_genome_pack(mg_genome *g, int64_t contig, int64_t offset, const uint8_t *ascii, int64_t n, void *stream) {
+    int rc = check_pack_args(g, contig, offset, ascii, n);
+    if (rc) return rc;
+    MG_CUDA(cudaSetDevice(g->device));
+    g->finalized = false;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t STAGE = 64ll << 20;
+    rc = mg_ensure_stage(g, std::min<int64_t>(STAGE, (n + 255) / 256 * 256));
+    if (rc) return rc;
+    for (int64_t done = 0; done < n;) {
+        const int64_t m = std::min<int64_t>(g->stage_cap / 32 * 32, n - done);
+        MG_CUDA(cudaMemcpyAsync(g->d_stage, ascii + done, m, cudaMemcpyHostToDevice, st));
+        rc = pack_device_chunk(g, g->h_contig_base[contig] + offset + done, g->d_stage, m, st);
+        if (rc) return rc;
+        done += m;
+    }
+    return MG_OK;
+}
+
+extern "C" int mg_genome_finalize(mg_genome *g, int64_t *n_exceptions_out) {
+    MG_REQUIRE(g != nullptr, "genome handle is NULL");
+    MG_CUDA(cudaSetDevice(g->device));
+    const int64_t n = (int64_t)g->h_exc_pos.size();
+    // a position packed twice (re-sent chunk) keeps its last byte
+    std::vector<int64_t> idx(n);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return g->h_exc_pos[a] < g->h_exc_pos[b]; });
+    std::vector<int64_t> pos;
+    std::vector<uint8_t> byt;
+    pos.reserve(n);
+    byt.reserve(n);
+    for (int64_t k = 0; k < n; k++) {
+        const int64_t i = idx[k];
+        if (!pos.empty() && pos.back() == g->h_exc_pos[i]) byt.back() = g->h_exc_byte[i];
+        else { pos.push_back(g->h_exc_pos[i]); byt.push_back(g->h_exc_byte[i]); }
+    }
+    g->n_exc = (int64_t)pos.size();
+    if (g->n_exc > g->exc_cap) {
+        MG_CUDA(cudaFree(g->d_exc_pos));
+        MG_CUDA(cudaFree(g->d_exc_byte));
+        g->exc_cap = g->n_exc;
+        MG_CUDA(cudaMalloc(&g->d_exc_pos, g->exc_cap * sizeof(int64_t)));
+        MG_CUDA(cudaMalloc(&g->d_exc_byte, g->exc_cap));
+    }
+    if (g->n_exc) {
+        MG_CUDA(cudaMemcpy(g->d_exc_pos, pos.data(), g->n_exc * sizeof(int64_t), cudaMemcpyHostToDevice));
+        MG_CUDA(cudaMemcpy(g->d_exc_byte, byt.data(), g->n_exc, cudaMemcpyHostToDevice));
+    }
+    g->h_exc_pos.swap(pos);
+    g->h_exc_byte.swap(byt);
+    g->finalized = true;
+    if (n_exceptions_out) *n_exceptions_out = g->n_exc;
+    return MG_OK;
+}
+
+// ---- range decode -----------------------------------------------------------------------------------
+// out[i] for i in [0, n): forward = base g_lo+i; minus = complement of base g_hi-1-i.  16 bytes / thread.
+__global__ void __launch_bounds__(256) k_fetch(const uint32_t *__restrict__ packed, int64_t g_lo, int64_t n, int minus,
+                                               const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte,
+                                               int64_t n_exc, uint8_t *__restrict__ out) {
+    const int64_t nchunk = (n + 15) >> 4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nchunk; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o = i << 4;
+        uint64_t v;
+        if (!minus) {
+            v = mg_ld_nib16(packed, g_lo + o);
+        } else {
+            v = mg_rc_nib16(mg_ld_nib16(packed, g_lo + n - o - 16));
+        }
+        uint32_t b0, b1, b2, b3;
+        mg_decode8((uint32_t)v, b0, b1);
+        mg_decode8((uint32_t)(v >> 32), b2, b3);
+        if (!minus && n_exc > 0) {
+            uint32_t w[4] = {b0, b1, b2, b3};
+            for (int k = 0; k < 16; k++) {
+                if (((v >> (4 * k)) & 15u) == MG_CODE_EXC && o + k < n) {
+                    const uint32_t c = mg_exc_byte(exc_pos, exc_byte, n_exc, g_lo + o + k);
+                    w[k >> 2] = (w[k >> 2] & ~(0xFFu << ((k & 3) * 8))) | (c << ((k & 3) * 8));
+                }
+            }
+            b0 = w[0]; b1 = w[1]; b2 = w[2]; b3 = w[3];
+        }
+        mg_st16(out + o, b0, b1, b2, b3);
+    }
+}
+
+extern "C" int mg_genome_fetch(mg_genome *g, int64_t contig, int64_t lo, int64_t hi, int minus, uint8_t *out_host, void *stream) {
+    MG_REQUIRE(g != nullptr, "genome handle is NULL");
+    MG_REQUIRE(g->finalized, "mg_genome_finalize has not been called");
+    MG_REQUIRE(contig >= 0 && contig < g->n_contigs, "contig index out of range");
+    MG_REQUIRE(lo >= 0 && lo <= hi && hi <= g->h_contig_len[contig], "range outside the contig");
+    if (hi == lo) return MG_OK;
+    MG_REQUIRE(out_host != nullptr, "out_host is NULL");
+    MG_CUDA(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = hi - lo;
+    const int64_t STAGE = 64ll << 20;
+    int rc = mg_ensure_stage(g, std::min<int64_t>(STAGE, (n + 255) / 256 * 256));
+    if (rc) return rc;
+    const int64_t gl = g->h_contig_base[contig] + lo;
+    const int64_t step = g->stage_cap / 16 * 16;
+    for (int64_t done = 0; done < n;) {
+        const int64_t m = std::min<int64_t>(step, n - done);
+        // forward: output [done, done+m) = bases gl+done ..; minus: output [done, done+m) = rc of bases [gl+n-done-m, gl+n-done)
+        const int64_t sub_lo = minus ? gl + n - done - m : gl + done;
+        const int blocks = (int)std::min<int64_t>(((m + 15) / 16 + 255) / 256, 148 * 16);
+        k_fetch<<<std::max(blocks, 1), 256, 0, st>>>(g->d_packed, sub_lo, m, minus, g->d_exc_pos, g->d_exc_byte, g->n_exc, g->d_stage);
+        MG_LAUNCH_CHECK();
+        MG_CUDA(cudaMemcpyAsync(out_host + done, g->d_stage, m, cudaMemcpyDeviceToHost, st));
+        MG_CUDA(cudaStreamSynchronize(st));
+        done += m;
+    }
+    return MG_OK;
+}

@@ -1,0 +1,267 @@
+// mg_plan.cu -- K1: SoA interval tables on the device, Python-slice clamping, piece table, prefix sums.
+//
+// A plan turns "n_rec records, each a list of segments in emission order + a literal prefix/suffix"
+// into ONE flat piece table for the nucleotide text and ONE flat record table for the protein text:
+//
+//   piece p of record r:  F(r) = rec_seg_off[r] + 2r      -> literal prefix  (">ID\n")
+//                         F(r)+1+k                          -> k-th segment   (genome interval, fwd or rc)
+//                         F(r+1)-1                          -> literal suffix ("\n")
+//   piece_off[p]  = byte offset of piece p in the nucleotide text (exclusive prefix sum of lengths)
+//   piece_src[p]  = global base index of the lowest base of the interval (or offset into lit[]) | kind<<62
+//
+// so the emit kernels are flat, perfectly load-balanced passes over OUTPUT bytes (16 per thread), not
+// over transcripts -- transcript lengths are heavy-tailed (188..8502 bp in the reference's own test set).
+// Replaces the per-child bookkeeping of ParentAnnotation.get_fasta (genome.py:687-705) and the slice
+// arithmetic of BaseAnnotation.get_seq (genome.py:603-608).
+#include <algorithm>
+#include "mg_common.cuh"
+#include "mg_gather.cuh"
+
+// ---- kernels ----------------------------------------------------------------------------------------
+
+// thread per piece: find its record (binary search over F), clamp like a Python slice, write len + src
+__global__ void __launch_bounds__(256) k_plan_pieces(int64_t n_piece, int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
+                                                     const int32_t *__restrict__ seg_contig, const int64_t *__restrict__ seg_start,
+                                                     const int64_t *__restrict__ seg_end, const int8_t *__restrict__ seg_strand,
+                                                     const int64_t *__restrict__ rec_lit_off, const int32_t *__restrict__ rec_pre,
+                                                     const int32_t *__restrict__ rec_suf, const int64_t *__restrict__ contig_len,
+                                                     const int64_t *__restrict__ contig_base, int64_t n_contigs,
+                                                     int32_t *__restrict__ piece_len, int64_t *__restrict__ piece_src) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n_piece) return;
+    // largest r with F(r) = rec_seg_off[r] + 2r <= p
+    int64_t lo = 0, hi = n_rec;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(rec_seg_off + mid) + 2 * mid <= p) lo = mid; else hi = mid;
+    }
+    const int64_t r = lo;
+    const int64_t s0 = __ldg(rec_seg_off + r), s1 = __ldg(rec_seg_off + r + 1);
+    const int64_t local = p - (s0 + 2 * r);
+    if (local == 0) {                                   // literal prefix
+        piece_len[p] = rec_pre[r];
+        piece_src[p] = rec_lit_off[r] | (int64_t)(MG_KIND_LIT << MG_KIND_SHIFT);
+    } else if (local == s1 - s0 + 1) {                  // literal suffix
+        piece_len[p] = rec_suf[r];
+        piece_src[p] = (rec_lit_off[r] + rec_pre[r]) | (int64_t)(MG_KIND_LIT << MG_KIND_SHIFT);
+    } else {                                            // genome segment
+        const int64_t e = s0 + local - 1;
+        const int32_t c = seg_contig[e];
+        int64_t len = 0, src = MG_FRONT_PAD;
+        if (c >= 0 && c < n_contigs) {
+            const int64_t L = contig_len[c];
+            // contig[start-1:end] with Python slice semantics (genome.py:606)
+            int64_t i = seg_start[e] - 1, j = seg_end[e];
+            if (i < 0) { i += L; if (i < 0) i = 0; } else if (i > L) i = L;
+            if (j < 0) { j += L; if (j < 0) j = 0; } else if (j > L) j = L;
+            len = j > i ? j - i : 0;
+            if (len > 0x7fffffff) len = 0x7fffffff;     // rejected on the host side (see mg_plan_prepare)
+            src = contig_base[c] + i;
+        }
+        piece_len[p] = (int32_t)len;
+        const uint64_t kind = seg_strand[e] ? MG_KIND_RC : MG_KIND_FWD;
+        piece_src[p] = src | (int64_t)(kind << MG_KIND_SHIFT);
+    }
+}
+
+// thread per record: spliced length -> amino-acid count (Sequence.translate, genome.py:810-821)
+__global__ void __launch_bounds__(256) k_plan_records(int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
+                                                      const int64_t *__restrict__ piece_off, const int64_t *__restrict__ piece_src,
+                                                      const uint32_t *__restrict__ packed, const int8_t *__restrict__ rec_phase,
+                                                      int flags, int32_t *__restrict__ rec_aa, int8_t *__restrict__ rec_skip,
+                                                      int32_t *__restrict__ prot_len) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const int64_t f0 = rec_seg_off[r] + 2 * r, f1 = rec_seg_off[r + 1] + 2 * (r + 1);
+    const int64_t pay0 = piece_off[f0 + 1], pay1 = piece_off[f1 - 1];
+    const int64_t pre = pay0 - piece_off[f0], suf = piece_off[f1] - pay1;
+    int64_t L = pay1 - pay0;
+    int skip = 0;
+    if ((flags & MG_PROT_USE_PHASE) && rec_phase) { skip = rec_phase[r]; if (skip < 0 || skip > 2) skip = 0; }
+    L -= skip;
+    int64_t naa;
+    if (L <= 2) {
+        naa = -1;                                        // reference returns None (genome.py:810)
+    } else {
+        naa = L / 3;
+        if (flags & MG_PROT_TRIMX) {                     // drop exactly one leading X (genome.py:819-821)
+            uint64_t acc[3];
+            const int64_t S = pay0 + skip;
+            const int64_t j = mg_search_le(piece_off, f0 + 1, f1 - 1, S);
+            mg_gather_nib(packed, piece_off, piece_src, j, S, 3, acc);
+            const uint32_t n3 = (uint32_t)acc[0] & 0xFFFu;
+            if (n3 & 0x888u) { naa -= 1; skip += 3; }
+        }
+    }
+    if (naa > 0x7fffffff) naa = 0x7fffffff;
+    rec_aa[r] = (int32_t)naa;
+    rec_skip[r] = (int8_t)skip;
+    prot_len[r] = (int32_t)(pre + (naa > 0 ? naa : 0) + suf);
+}
+
+// thread per tile: index of the piece / record that contains the tile's first byte
+__global__ void __launch_bounds__(256) k_plan_tiles(const int64_t *__restrict__ off, int64_t n, int64_t tile_bytes,
+                                                    int64_t n_tile, int64_t *__restrict__ tile_first) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t > n_tile) return;
+    if (t == n_tile) { tile_first[t] = n > 0 ? n - 1 : 0; return; }
+    tile_first[t] = mg_search_le(off, 0, n, t * tile_bytes);
+}
+
+__global__ void __launch_bounds__(256) k_plan_lengths(int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
+                                                      const int64_t *__restrict__ piece_off, const int32_t *__restrict__ rec_aa,
+                                                      int64_t *__restrict__ nuc_len, int64_t *__restrict__ aa_len) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const int64_t f0 = rec_seg_off[r] + 2 * r, f1 = rec_seg_off[r + 1] + 2 * (r + 1);
+    if (nuc_len) nuc_len[r] = piece_off[f1 - 1] - piece_off[f0 + 1];
+    if (aa_len) aa_len[r] = rec_aa[r];
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+
+template <typename T>
+static int upload(mg_plan *p, T **dst, const T *src, int64_t n, cudaStream_t st) {
+    void *d = nullptr;
+    MG_CUDA(cudaMallocAsync(&d, std::max<int64_t>(1, n) * sizeof(T), st));
+    p->owned.push_back(d);
+    if (n > 0 && src) MG_CUDA(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    *dst = (T *)d;
+    return MG_OK;
+}
+
+template <typename T>
+static int dalloc(mg_plan *p, T **dst, int64_t n, cudaStream_t st) {
+    void *d = nullptr;
+    MG_CUDA(cudaMallocAsync(&d, std::max<int64_t>(1, n) * sizeof(T), st));
+    p->owned.push_back(d);
+    *dst = (T *)d;
+    return MG_OK;
+}
+
+extern "C" int mg_plan_create(mg_genome *g, int64_t n_rec, const int64_t *rec_seg_off, int64_t n_seg,
+                              const int32_t *seg_contig, const int64_t *seg_start, const int64_t *seg_end,
+                              const int8_t *seg_strand, const int64_t *rec_lit_off, const int32_t *rec_pre_len,
+                              const int32_t *rec_suf_len, const uint8_t *lit, int64_t n_lit, const int8_t *rec_phase,
+                              void *stream, mg_plan **out) {
+    MG_REQUIRE(g != nullptr && out != nullptr, "NULL handle");
+    MG_REQUIRE(g->finalized, "mg_genome_finalize has not been called");
+    MG_REQUIRE(n_rec >= 0 && n_seg >= 0 && n_lit >= 0, "negative size");
+    MG_REQUIRE(rec_seg_off != nullptr, "rec_seg_off is NULL");
+    MG_REQUIRE(n_seg == 0 || (seg_contig && seg_start && seg_end && seg_strand), "segment arrays are NULL");
+    MG_REQUIRE(n_rec == 0 || (rec_lit_off && rec_pre_len && rec_suf_len), "record arrays are NULL");
+    MG_REQUIRE(rec_seg_off[0] == 0 && rec_seg_off[n_rec] == n_seg, "rec_seg_off must start at 0 and end at n_seg");
+    MG_CUDA(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    mg_plan *p = new mg_plan();
+    p->g = g;
+    p->device = g->device;
+    p->n_rec = n_rec;
+    p->n_seg = n_seg;
+    p->n_piece = n_seg + 2 * n_rec;
+    p->n_lit = n_lit;
+    int rc = MG_OK;
+#define TRY(x) do { rc = (x); if (rc) { mg_plan_destroy(p); return rc; } } while (0)
+    TRY(upload(p, &p->d_rec_seg_off, rec_seg_off, n_rec + 1, st));
+    TRY(upload(p, &p->d_seg_contig, seg_contig, n_seg, st));
+    TRY(upload(p, &p->d_seg_start, seg_start, n_seg, st));
+    TRY(upload(p, &p->d_seg_end, seg_end, n_seg, st));
+    TRY(upload(p, &p->d_seg_strand, seg_strand, n_seg, st));
+    TRY(upload(p, &p->d_rec_lit_off, rec_lit_off, n_rec, st));
+    TRY(upload(p, &p->d_rec_pre, rec_pre_len, n_rec, st));
+    TRY(upload(p, &p->d_rec_suf, rec_suf_len, n_rec, st));
+    TRY(upload(p, &p->d_lit, lit, n_lit, st));
+    if (rec_phase) TRY(upload(p, &p->d_rec_phase, rec_phase, n_rec, st));
+    TRY(dalloc(p, &p->d_piece_len, p->n_piece, st));
+    TRY(dalloc(p, &p->d_piece_src, p->n_piece, st));
+    TRY(dalloc(p, &p->d_piece_off, p->n_piece + 1, st));
+    TRY(dalloc(p, &p->d_prot_len, n_rec, st));
+    TRY(dalloc(p, &p->d_prot_off, n_rec + 1, st));
+    TRY(dalloc(p, &p->d_rec_aa, n_rec, st));
+    TRY(dalloc(p, &p->d_rec_skip, n_rec, st));
+    p->scan_tmp_cap = mg_scan_tmp_elems(std::max(p->n_piece, n_rec)) + 2;
+    TRY(dalloc(p, &p->d_scan_tmp, p->scan_tmp_cap, st));
+#undef TRY
+    *out = p;
+    return MG_OK;
+}
+
+extern "C" int mg_plan_destroy(mg_plan *p) {
+    if (!p) return MG_OK;
+    cudaSetDevice(p->device);
+    for (void *d : p->owned) cudaFreeAsync(d, 0);
+    if (p->d_out) cudaFreeAsync(p->d_out, 0);
+    delete p;
+    return MG_OK;
+}
+
+extern "C" int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, int64_t *prot_total, void *stream) {
+    MG_REQUIRE(p != nullptr, "plan handle is NULL");
+    MG_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    mg_genome *g = p->g;
+    p->prot_flags = prot_flags;
+    int64_t totals[2] = {0, 0};
+    if (p->n_rec > 0) {
+        k_plan_pieces<<<(unsigned)((p->n_piece + 255) / 256), 256, 0, st>>>(
+            p->n_piece, p->n_rec, p->d_rec_seg_off, p->d_seg_contig, p->d_seg_start, p->d_seg_end, p->d_seg_strand,
+            p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, g->d_contig_len, g->d_contig_base, g->n_contigs,
+            p->d_piece_len, p->d_piece_src);
+        MG_LAUNCH_CHECK();
+        int rc = mg_scan_i32(p->d_piece_len, p->d_piece_off, p->n_piece, p->d_scan_tmp, p->scan_tmp_cap, st);
+        if (rc) return rc;
+        k_plan_records<<<(unsigned)((p->n_rec + 255) / 256), 256, 0, st>>>(
+            p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_piece_src, g->d_packed, p->d_rec_phase, prot_flags,
+            p->d_rec_aa, p->d_rec_skip, p->d_prot_len);
+        MG_LAUNCH_CHECK();
+        rc = mg_scan_i32(p->d_prot_len, p->d_prot_off, p->n_rec, p->d_scan_tmp, p->scan_tmp_cap, st);
+        if (rc) return rc;
+        MG_CUDA(cudaMemcpyAsync(&totals[0], p->d_piece_off + p->n_piece, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        MG_CUDA(cudaMemcpyAsync(&totals[1], p->d_prot_off + p->n_rec, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        MG_CUDA(cudaStreamSynchronize(st));
+    }
+    p->nuc_total = totals[0];
+    p->prot_total = totals[1];
+    // tile -> first piece / first record (removes every global binary search from the emit kernels)
+    p->n_nuc_tile = (p->nuc_total + MG_NUC_TILE - 1) / MG_NUC_TILE;
+    p->n_prot_tile = (p->prot_total + MG_PROT_TILE - 1) / MG_PROT_TILE;
+    {
+        void *d = nullptr;
+        MG_CUDA(cudaMallocAsync(&d, (p->n_nuc_tile + 1 + p->n_prot_tile + 1) * sizeof(int64_t), st));
+        p->owned.push_back(d);
+        p->d_nuc_tile = (int64_t *)d;
+        p->d_prot_tile = p->d_nuc_tile + p->n_nuc_tile + 1;
+    }
+    if (p->n_nuc_tile > 0) {
+        k_plan_tiles<<<(unsigned)((p->n_nuc_tile + 256) / 256), 256, 0, st>>>(p->d_piece_off, p->n_piece, MG_NUC_TILE,
+                                                                              p->n_nuc_tile, p->d_nuc_tile);
+        MG_LAUNCH_CHECK();
+    }
+    if (p->n_prot_tile > 0) {
+        k_plan_tiles<<<(unsigned)((p->n_prot_tile + 256) / 256), 256, 0, st>>>(p->d_prot_off, p->n_rec, MG_PROT_TILE,
+                                                                               p->n_prot_tile, p->d_prot_tile);
+        MG_LAUNCH_CHECK();
+    }
+    p->prepared = true;
+    if (nuc_total) *nuc_total = p->nuc_total;
+    if (prot_total) *prot_total = p->prot_total;
+    return MG_OK;
+}
+
+extern "C" int mg_plan_lengths(mg_plan *p, int64_t *nuc_len, int64_t *aa_len, void *stream) {
+    MG_REQUIRE(p != nullptr, "plan handle is NULL");
+    MG_REQUIRE(p->prepared, "mg_plan_prepare has not been called");
+    if (p->n_rec == 0 || (!nuc_len && !aa_len)) return MG_OK;
+    MG_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t *d = nullptr;
+    MG_CUDA(cudaMallocAsync((void **)&d, 2 * p->n_rec * sizeof(int64_t), st));
+    k_plan_lengths<<<(unsigned)((p->n_rec + 255) / 256), 256, 0, st>>>(p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_rec_aa,
+                                                                        d, d + p->n_rec);
+    MG_LAUNCH_CHECK();
+    if (nuc_len) MG_CUDA(cudaMemcpyAsync(nuc_len, d, p->n_rec * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (aa_len) MG_CUDA(cudaMemcpyAsync(aa_len, d + p->n_rec, p->n_rec * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MG_CUDA(cudaStreamSynchronize(st));
+    MG_CUDA(cudaFreeAsync(d, st));
+    return MG_OK;
+}

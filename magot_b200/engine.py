@@ -1,0 +1,265 @@
+"""Host-side plumbing between the Python API (magot_b200.genome) and the C ABI.
+
+`DeviceGenome`  -- one packed, device-resident genome replica (mg_genome handle).
+`RecordTable`   -- the SoA interval tables the host flattener produces (contig id, start, end,
+                   strand per segment, sorted per transcript in reference emission order, plus the
+                   literal framing of each FASTA record).
+`run_table`     -- create a plan, prepare (clamp + scans on the device), emit, copy back.
+`ShardedGenome` -- replicas on several GPUs of one box; records are split into contiguous,
+                   byte-balanced batches, one per GPU, and the texts are concatenated on the host
+                   in record order (the path has no cross-shard reduction, hence no NCCL).
+
+PyTorch is used only to obtain pinned host buffers; everything else is ctypes + numpy.
+"""
+import ctypes
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check
+
+_CHUNK = 64 << 20          # bases per mg_genome_pack call (multiple of 32)
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def pinned_empty(nbytes):
+    """uint8 host buffer of nbytes, page-locked when torch + CUDA are available (plumbing only)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, pin_memory=True)
+            return t.numpy()[:nbytes]          # the ndarray keeps the tensor's storage alive
+    except Exception:
+        pass
+    return np.empty(nbytes, dtype=np.uint8)
+
+
+class DeviceGenome(object):
+    """A genome replica on one CUDA device: nibble-packed contigs + exception side list."""
+
+    def __init__(self, contig_lens, device=0):
+        _lib.require_device(device)
+        self.device = device
+        self.lens = np.ascontiguousarray(contig_lens, dtype=np.int64)
+        self.handle = ctypes.c_void_p()
+        check(lib.mg_genome_create(device, len(self.lens), _ptr(self.lens), ctypes.byref(self.handle)))
+        self.n_exceptions = None
+
+    def pack(self, contig, ascii_arr, offset=0):
+        """Pack a uint8 array of FASTA bytes (newlines removed) into contig `contig` at `offset`."""
+        a = np.ascontiguousarray(ascii_arr, dtype=np.uint8)
+        n = a.size
+        done = 0
+        while done < n or (n == 0 and done == 0):
+            m = min(_CHUNK, n - done)
+            check(lib.mg_genome_pack(self.handle, contig, offset + done, ctypes.c_void_p(a.ctypes.data + done), m, None))
+            done += m
+            if n == 0:
+                break
+
+    def pack_device(self, contig, dev_ptr, n, offset=0, stream=None):
+        check(lib.mg_genome_pack_device(self.handle, contig, offset, ctypes.c_void_p(dev_ptr), n, stream))
+
+    def finalize(self):
+        n = ctypes.c_int64(0)
+        check(lib.mg_genome_finalize(self.handle, ctypes.byref(n)))
+        self.n_exceptions = n.value
+        return n.value
+
+    def fetch(self, contig, lo, hi, minus=False):
+        """Exact FASTA bytes of contig[lo:hi] (already clamped), or their reverse complement."""
+        n = hi - lo
+        if n <= 0:
+            return b""
+        out = np.empty(n, dtype=np.uint8)
+        check(lib.mg_genome_fetch(self.handle, contig, lo, hi, 1 if minus else 0, _ptr(out), None))
+        return out.tobytes()
+
+    def device_bytes(self):
+        return lib.mg_genome_bytes(self.handle)
+
+    def close(self):
+        if self.handle:
+            lib.mg_genome_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RecordTable(object):
+    """SoA tables for n_rec output records (see mg_plan_create in include/magot_b200.h)."""
+
+    __slots__ = ("rec_seg_off", "seg_contig", "seg_start", "seg_end", "seg_strand", "rec_lit_off",
+                 "rec_pre_len", "rec_suf_len", "lit", "rec_phase")
+
+    def __init__(self, rec_seg_off, seg_contig, seg_start, seg_end, seg_strand, rec_lit_off, rec_pre_len,
+                 rec_suf_len, lit, rec_phase=None):
+        self.rec_seg_off = np.ascontiguousarray(rec_seg_off, dtype=np.int64)
+        self.seg_contig = np.ascontiguousarray(seg_contig, dtype=np.int32)
+        self.seg_start = np.ascontiguousarray(seg_start, dtype=np.int64)
+        self.seg_end = np.ascontiguousarray(seg_end, dtype=np.int64)
+        self.seg_strand = np.ascontiguousarray(seg_strand, dtype=np.int8)
+        self.rec_lit_off = np.ascontiguousarray(rec_lit_off, dtype=np.int64)
+        self.rec_pre_len = np.ascontiguousarray(rec_pre_len, dtype=np.int32)
+        self.rec_suf_len = np.ascontiguousarray(rec_suf_len, dtype=np.int32)
+        self.lit = np.ascontiguousarray(lit, dtype=np.uint8)
+        self.rec_phase = None if rec_phase is None else np.ascontiguousarray(rec_phase, dtype=np.int8)
+
+    @property
+    def n_rec(self):
+        return self.rec_seg_off.size - 1
+
+    @property
+    def n_seg(self):
+        return self.seg_contig.size
+
+    def slice(self, r0, r1):
+        """Records [r0, r1) as an independent table (literal buffer shared, offsets kept)."""
+        s0, s1 = int(self.rec_seg_off[r0]), int(self.rec_seg_off[r1])
+        return RecordTable(self.rec_seg_off[r0:r1 + 1] - s0, self.seg_contig[s0:s1], self.seg_start[s0:s1],
+                           self.seg_end[s0:s1], self.seg_strand[s0:s1], self.rec_lit_off[r0:r1],
+                           self.rec_pre_len[r0:r1], self.rec_suf_len[r0:r1], self.lit,
+                           None if self.rec_phase is None else self.rec_phase[r0:r1])
+
+    def approx_bytes_per_record(self):
+        """Upper estimate of each record's nucleotide text size (before clamping), for shard balancing."""
+        seg_len = np.maximum(self.seg_end - self.seg_start + 1, 0)
+        csum = np.concatenate(([0], np.cumsum(seg_len)))
+        pay = csum[self.rec_seg_off[1:]] - csum[self.rec_seg_off[:-1]]
+        return pay + self.rec_pre_len + self.rec_suf_len
+
+
+class Plan(object):
+    """mg_plan wrapper: create -> prepare -> emit."""
+
+    def __init__(self, genome, table, stream=None):
+        self.genome = genome
+        self.table = table                       # keeps the host arrays alive
+        self.stream = stream
+        self.handle = ctypes.c_void_p()
+        t = table
+        check(lib.mg_plan_create(genome.handle, t.n_rec, _ptr(t.rec_seg_off), t.n_seg, _ptr(t.seg_contig),
+                                 _ptr(t.seg_start), _ptr(t.seg_end), _ptr(t.seg_strand), _ptr(t.rec_lit_off),
+                                 _ptr(t.rec_pre_len), _ptr(t.rec_suf_len), _ptr(t.lit), t.lit.size,
+                                 _ptr(t.rec_phase), stream, ctypes.byref(self.handle)))
+        self.nuc_total = None
+        self.prot_total = None
+
+    def prepare(self, trimx=True, use_phase=False):
+        flags = (_lib.MG_PROT_TRIMX if trimx else 0) | (_lib.MG_PROT_USE_PHASE if use_phase else 0)
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(lib.mg_plan_prepare(self.handle, flags, ctypes.byref(a), ctypes.byref(b), self.stream))
+        self.nuc_total, self.prot_total = a.value, b.value
+        return self.nuc_total, self.prot_total
+
+    def lengths(self):
+        n = self.table.n_rec
+        nuc = np.empty(n, dtype=np.int64)
+        aa = np.empty(n, dtype=np.int64)
+        check(lib.mg_plan_lengths(self.handle, _ptr(nuc), _ptr(aa), self.stream))
+        return nuc, aa
+
+    def emit_host(self, protein=False, out=None):
+        total = self.prot_total if protein else self.nuc_total
+        if out is None:
+            out = np.empty(total, dtype=np.uint8)
+        if total:
+            fn = lib.mg_emit_prot_host if protein else lib.mg_emit_nuc_host
+            check(fn(self.handle, _ptr(out), self.stream))
+            check(lib.mg_stream_sync(self.genome.device, self.stream))
+        return out[:total]
+
+    def emit_device(self, dev_ptr, protein=False):
+        fn = lib.mg_emit_prot_device if protein else lib.mg_emit_nuc_device
+        check(fn(self.handle, ctypes.c_void_p(dev_ptr), self.stream))
+
+    def close(self):
+        if self.handle:
+            lib.mg_plan_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_table(genome, table, protein=False, trimx=True, use_phase=False, want_lengths=False):
+    """One pass of the hot path over one batch on one GPU. Returns (text bytes, (nuc_len, aa_len) | None)."""
+    plan = Plan(genome, table)
+    try:
+        plan.prepare(trimx=trimx, use_phase=use_phase)
+        lens = plan.lengths() if want_lengths else None
+        text = plan.emit_host(protein=protein).tobytes()
+    finally:
+        plan.close()
+    return text, lens
+
+
+def shard_bounds(weights, n_shards):
+    """Split records into n_shards contiguous batches of ~equal total weight (prefix sum / n)."""
+    n = len(weights)
+    if n_shards <= 1 or n == 0:
+        return [0, n]
+    csum = np.cumsum(np.asarray(weights, dtype=np.float64))
+    total = csum[-1] if n else 0.0
+    bounds = [0]
+    for k in range(1, n_shards):
+        target = total * k / n_shards
+        bounds.append(min(n, max(bounds[-1], int(np.searchsorted(csum, target, side="left")) + 1)))
+    bounds.append(n)
+    return bounds
+
+
+class ShardedGenome(object):
+    """The same packed genome replicated on several GPUs of one box."""
+
+    def __init__(self, replicas):
+        self.replicas = list(replicas)
+
+    @property
+    def primary(self):
+        return self.replicas[0]
+
+    def run_table(self, table, protein=False, trimx=True, use_phase=False, want_lengths=False):
+        if len(self.replicas) == 1 or table.n_rec < 2 * len(self.replicas):
+            return run_table(self.primary, table, protein, trimx, use_phase, want_lengths)
+        bounds = shard_bounds(table.approx_bytes_per_record(), len(self.replicas))
+        results = [None] * len(self.replicas)
+        errors = []
+
+        def work(k):
+            try:
+                r0, r1 = bounds[k], bounds[k + 1]
+                if r1 > r0:
+                    results[k] = run_table(self.replicas[k], table.slice(r0, r1), protein, trimx, use_phase, want_lengths)
+                else:
+                    results[k] = (b"", (np.empty(0, np.int64), np.empty(0, np.int64)) if want_lengths else None)
+            except Exception as e:      # re-raised on the caller's thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(self.replicas))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        text = b"".join(r[0] for r in results)
+        lens = None
+        if want_lengths:
+            lens = (np.concatenate([r[1][0] for r in results]), np.concatenate([r[1][1] for r in results]))
+        return text, lens
+
+    def close(self):
+        for r in self.replicas:
+            r.close()

@@ -1,0 +1,714 @@
+"""Drop-in mirror of the sequence half of MAGOT's `genome` module (reference: genome.py).
+
+Same names, signatures, return types and text output as the reference for the
+annotation-driven sequence path; underneath, the genome is packed once into a device-resident
+nibble buffer, annotations are flattened on the host into SoA interval tables and the
+extraction / reverse-complement / translation run as sm_100a CUDA kernels behind the C ABI in
+include/magot_b200.h.  There is no CPU fallback for any of that work.
+
+Reference API kept (file:line in /root/reference/genome.py):
+  Sequence(str)            :781   reverse_compliment :784, translate :795, get_orfs :824
+  GenomeSequence           :854   dict-like seqid -> contig (values are lazy device views)
+  Genome                   :880   ctor :883, get_scaffold_fasta :907, get_genome_fasta :910,
+                                   get_seqids :935, read_gff :970
+  read_gff                 :242   (presets= is not supported: it relies on py2 `exec` semantics)
+  AnnotationSet            :524   __getitem__ :536, read_gff :546, get_fasta :578
+  BaseAnnotation           :586   get_coords :600, get_seq :603
+  ParentAnnotation         :649   get_coords :663, get_fasta :677
+Record order: the reference iterates Python-2.7 dicts; `RECORD_ORDER = "py2"` (default) replays
+that order (magot_b200.py2dict) so whole files are byte-identical; "insertion" keeps file order.
+"""
+import io
+import os
+
+import numpy as np
+
+from . import _lib
+from . import engine
+from .py2dict import py2_order, py2_order_after_deepcopy
+
+verbose = True                      # genome.py:22
+RECORD_ORDER = "py2"                # "py2" (reference-identical) | "insertion"
+DEFAULT_DEVICES = None              # None -> [0]; or a list of CUDA device indices to shard over
+
+
+def _order(keys, deepcopy=False):
+    if RECORD_ORDER != "py2":
+        return list(keys)
+    return py2_order_after_deepcopy(keys) if deepcopy else py2_order(keys)
+
+
+# ---------------------------------------------------------------------------------------------
+# magot_smallfuncs.ensure_file (magot_smallfuncs.py:32-43)
+# ---------------------------------------------------------------------------------------------
+
+def ensure_file(potential_file):
+    """Path -> opened file, file -> itself, anything unopenable -> the argument as literal text.
+    Text is read as latin-1 with '\\n'-only line ends, i.e. byte-for-byte like Python 2."""
+    if potential_file is None:
+        return None
+    if hasattr(potential_file, "read"):
+        return potential_file
+    try:
+        return open(potential_file, encoding="latin-1", newline="\n")
+    except (IOError, OSError, ValueError):
+        return io.StringIO(potential_file, newline="\n")
+
+
+def _read_all_bytes(potential_file):
+    """ensure_file semantics, returning the whole content as bytes (fast path for big FASTA)."""
+    if potential_file is None:
+        return None
+    if hasattr(potential_file, "read"):
+        data = potential_file.read()
+        return data.encode("latin-1") if isinstance(data, str) else bytes(data)
+    try:
+        with open(potential_file, "rb") as fh:
+            return fh.read()
+    except (IOError, OSError, ValueError, TypeError):
+        return potential_file.encode("latin-1") if isinstance(potential_file, str) else bytes(potential_file)
+
+
+# ---------------------------------------------------------------------------------------------
+# Sequence (genome.py:781-851)
+# ---------------------------------------------------------------------------------------------
+
+def _device():
+    return (DEFAULT_DEVICES or [0])[0]
+
+
+def _translate_many(seqs, frame=0, strand='+', trimX=True):
+    """Sequence.translate on a batch of byte strings in one launch; returns list of str | None."""
+    import ctypes
+    n_seq = len(seqs)
+    if n_seq == 0:
+        return []
+    if frame not in (0, 1, 2):
+        raise ValueError("frame must be 0, 1 or 2")
+    if strand not in ('+', '-'):
+        raise UnboundLocalError("local variable 'seq' referenced before assignment")   # genome.py:806-810
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=n_seq)
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    data = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    total = int(off[-1])
+    cap = (total + 2) // 3 + n_seq + 16
+    out = np.empty(cap, dtype=np.uint8)
+    out_off = np.zeros(n_seq + 1, dtype=np.int64)
+    out_len = np.zeros(n_seq, dtype=np.int64)
+    _lib.require_device(_device())
+    _lib.check(_lib.lib.mg_translate_ascii(_device(), ctypes.c_void_p(data.ctypes.data) if total else None,
+                                           ctypes.c_void_p(off.ctypes.data), n_seq, frame, 1 if strand == '-' else 0,
+                                           1 if trimX else 0, ctypes.c_void_p(out.ctypes.data), cap,
+                                           ctypes.c_void_p(out_off.ctypes.data), ctypes.c_void_p(out_len.ctypes.data), None))
+    buf = out.tobytes()
+    res = []
+    for i in range(n_seq):
+        if out_len[i] < 0:
+            res.append(None)
+        else:
+            res.append(buf[out_off[i]:out_off[i + 1]].decode("latin-1"))
+    return res
+
+
+class Sequence(str):
+    """DNA sequence (genome.py:781).  The work runs on the GPU; results are plain strings."""
+
+    def reverse_compliment(self):
+        """genome.py:784-793: reversed, complemented, every byte outside acgtACGTnN- -> 'n'."""
+        import ctypes
+        n = len(self)
+        if n == 0:
+            return Sequence("")
+        src = np.frombuffer(self.encode("latin-1"), dtype=np.uint8)
+        out = np.empty(n, dtype=np.uint8)
+        _lib.require_device(_device())
+        _lib.check(_lib.lib.mg_revcomp(_device(), ctypes.c_void_p(src.ctypes.data), n, ctypes.c_void_p(out.ctypes.data), None))
+        return Sequence(out.tobytes().decode("latin-1"))
+
+    def translate(self, library=None, frame=0, strand='+', trimX=True):
+        """genome.py:795-822 with the reference's frame quirk; returns None when len <= 2 + frame.
+        Only the reference's default codon table (NCBI table 1) is implemented on the device."""
+        if library is not None:
+            raise NotImplementedError("custom codon libraries are not supported by the device path")
+        return _translate_many([self.encode("latin-1")], frame=frame, strand=strand, trimX=trimX)[0]
+
+    def get_orfs(self, longest=False, strand='both', from_atg=False):
+        """genome.py:824-851 (the `strand` argument is shadowed in the reference and ignored)."""
+        orflist = []
+        candidate_list = []
+        longest_orf_len = 0
+        raw = self.encode("latin-1")
+        for frame in (0, 1, 2):
+            for st in ('-', '+'):
+                translated_seq = _translate_many([raw], frame=frame, strand=st)[0]
+                if translated_seq:
+                    for orf in translated_seq.split('*'):
+                        output_orf = ('M' + ''.join(orf.split('M')[1:])) if from_atg else orf
+                        if longest:
+                            if len(output_orf) > longest_orf_len:
+                                candidate_list.append(output_orf)
+                                longest_orf_len = len(output_orf)
+                        else:
+                            orflist.append(output_orf)
+        if longest:
+            return candidate_list[-1]
+        return orflist
+
+
+# ---------------------------------------------------------------------------------------------
+# GenomeSequence (genome.py:854-877)
+# ---------------------------------------------------------------------------------------------
+
+class DeviceContig(object):
+    """Lazy view of one contig held in the packed device genome.  Behaves like the reference's
+    plain `str` value for the operations the reference and its tools perform on it (len, slicing,
+    concatenation, comparison, iteration); anything else is served by decoding to `str`."""
+
+    __slots__ = ("_gs", "_index", "_len")
+
+    def __init__(self, gs, index, length):
+        self._gs = gs
+        self._index = index
+        self._len = length
+
+    def __len__(self):
+        return self._len
+
+    def _fetch(self, lo, hi, minus=False):
+        return self._gs._engine().primary.fetch(self._index, lo, hi, minus).decode("latin-1")
+
+    def __str__(self):
+        return self._fetch(0, self._len)
+
+    def __repr__(self):
+        return repr(str(self))
+
+    def __getitem__(self, key):
+        if isinstance(key, slice):
+            lo, hi, step = key.indices(self._len)
+            if step == 1:
+                return self._fetch(lo, hi) if hi > lo else ""
+            return str(self)[key]
+        i = key + self._len if key < 0 else key
+        if not 0 <= i < self._len:
+            raise IndexError("string index out of range")
+        return self._fetch(i, i + 1)
+
+    def __iter__(self):
+        return iter(str(self))
+
+    def __add__(self, other):
+        return str(self) + str(other)
+
+    def __radd__(self, other):
+        return str(other) + str(self)
+
+    def __eq__(self, other):
+        if isinstance(other, (str, DeviceContig)):
+            return len(self) == len(other) and str(self) == str(other)
+        return NotImplemented
+
+    def __ne__(self, other):
+        r = self.__eq__(other)
+        return r if r is NotImplemented else not r
+
+    def __hash__(self):
+        return hash(str(self))
+
+    def __contains__(self, sub):
+        return sub in str(self)
+
+    def __getattr__(self, name):             # any other str method works on the decoded text
+        return getattr(str(self), name)
+
+
+class GenomeSequence(dict):
+    """genome sequence class, multi-fasta input (genome.py:854).  Keys are seqids, values are
+    `DeviceContig` views; iteration order is the reference's (Python-2.7 dict order)."""
+
+    def __init__(self, genome_sequence=None, truncate_names=False, devices=None):
+        dict.__init__(self)
+        self._devices = list(devices) if devices is not None else list(DEFAULT_DEVICES or [0])
+        self._sharded = None
+        self._pending = {}                   # seqid -> np.uint8 array, host text waiting to be packed
+        self._index = {}
+        data = _read_all_bytes(genome_sequence)
+        if data is not None:
+            names, arrays = _parse_fasta(data, truncate_names)
+            for name in _order(names):
+                self._pending[name] = arrays[name]
+                dict.__setitem__(self, name, None)
+            self._build()
+
+    # -- packing ------------------------------------------------------------------------------
+    def _build(self):
+        names = list(dict.keys(self))
+        arrays = [self._pending[n] for n in names]
+        lens = np.array([a.size for a in arrays], dtype=np.int64)
+        if self._sharded is not None:
+            self._sharded.close()
+        replicas = []
+        for dev in self._devices:
+            g = engine.DeviceGenome(lens, device=dev)
+            for ci, a in enumerate(arrays):
+                g.pack(ci, a)
+            g.finalize()
+            replicas.append(g)
+        self._sharded = engine.ShardedGenome(replicas)
+        self._index = {}
+        for ci, n in enumerate(names):
+            self._index[n] = ci
+            dict.__setitem__(self, n, DeviceContig(self, ci, int(lens[ci])))
+        self._pending = {}
+        self._dirty = False
+
+    def _engine(self):
+        if self._sharded is None or getattr(self, "_dirty", False):
+            self._rebuild_from_values()
+        return self._sharded
+
+    def _rebuild_from_values(self):
+        pend = {}
+        for k in dict.keys(self):
+            v = dict.__getitem__(self, k)
+            if isinstance(v, DeviceContig) and v._gs is self and self._sharded is not None:
+                pend[k] = np.frombuffer(str(v).encode("latin-1"), dtype=np.uint8)
+            else:
+                pend[k] = np.frombuffer(str(v).encode("latin-1"), dtype=np.uint8)
+        self._pending = pend
+        self._build()
+
+    def __setitem__(self, key, value):
+        """Assigning a plain string re-packs the genome on next use (rare; the reference allows it)."""
+        dict.__setitem__(self, key, value)
+        self._dirty = True
+
+    def contig_index(self, seqid):
+        self._engine()
+        return self._index[seqid]
+
+    def contig_length(self, seqid):
+        return len(dict.__getitem__(self, seqid))
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if not isinstance(v, DeviceContig):
+            self._engine()
+            v = dict.__getitem__(self, key)
+        return v
+
+    def close(self):
+        if self._sharded is not None:
+            self._sharded.close()
+            self._sharded = None
+
+
+def _parse_fasta(data, truncate_names):
+    """genome.py:856-877 on a bytes buffer.  Lines end at '\\n' only; '\\r' and '\\n' are removed from
+    sequence lines, every other byte is kept; records with an empty sequence are dropped; text
+    before the first header belongs to seqid ''; a repeated header replaces the earlier record."""
+    arr = np.frombuffer(data, dtype=np.uint8)
+    n = arr.size
+    names = []
+    arrays = {}
+    if n == 0:
+        return names, arrays
+    nl = np.flatnonzero(arr == 10)
+    line_starts = np.concatenate(([0], nl + 1))
+    line_starts = line_starts[line_starts < n]
+    is_hdr = arr[line_starts] == 62
+    hdr_starts = line_starts[is_hdr]
+    # end (exclusive, at the '\n' or EOF) of each header line
+    if hdr_starts.size and nl.size:
+        pos = np.searchsorted(nl, hdr_starts)
+        hdr_ends = np.where(pos < nl.size, nl[np.minimum(pos, nl.size - 1)], n)
+    else:
+        hdr_ends = np.full(hdr_starts.size, n, dtype=np.int64)
+
+    def put(name, lo, hi):
+        if hi <= lo:
+            return
+        seq = data[lo:hi].translate(None, b"\r\n")
+        if not seq:
+            return
+        if name not in arrays:
+            names.append(name)
+        arrays[name] = np.frombuffer(seq, dtype=np.uint8)
+
+    first = int(hdr_starts[0]) if hdr_starts.size else n
+    put("", 0, first)
+    for k in range(hdr_starts.size):
+        hs, he = int(hdr_starts[k]), int(hdr_ends[k])
+        raw = data[hs + 1:he].replace(b"\r", b"").decode("latin-1")
+        seqid = raw.split()[0] if truncate_names is True else raw
+        body_lo = min(he + 1, n)
+        body_hi = int(hdr_starts[k + 1]) if k + 1 < hdr_starts.size else n
+        put(seqid, body_lo, body_hi)
+    return names, arrays
+
+
+# ---------------------------------------------------------------------------------------------
+# Annotation model (genome.py:524-778)
+# ---------------------------------------------------------------------------------------------
+
+class BaseAnnotation(object):
+    """Bottom-most level annotation (CDS, match_part, ...), genome.py:586."""
+
+    def __init__(self, ID, seqid, coords, feature_type, parent=None, strand=".", other_attributes={}, annotation_set=None):
+        self.ID = ID
+        self.seqid = seqid
+        self.coords = coords
+        self.feature_type = feature_type
+        self.annotation_set = annotation_set
+        for attribute in other_attributes:
+            setattr(self, attribute, other_attributes[attribute])
+        self.parent = parent
+        self.strand = strand
+
+    def get_coords(self):
+        return self.coords
+
+    def get_seq(self):
+        """genome.py:603-614: contig[start-1:end] (Python slice clamping), reverse-complemented on '-'.
+        Prints and returns None on an invalid strand or any lookup failure, like the reference."""
+        try:
+            if self.strand == '+' or self.strand == '.' or self.strand == '-':
+                gs = self.annotation_set.genome.genome_sequence
+                contig = gs[self.seqid]
+                lo, hi, _ = slice(self.coords[0] - 1, self.coords[1]).indices(len(contig))
+                if hi <= lo:
+                    return Sequence("")
+                raw = gs._engine().primary.fetch(gs.contig_index(self.seqid), lo, hi, self.strand == '-')
+                return Sequence(raw.decode("latin-1"))
+            else:
+                print(self.ID + ' has invalid strand value "' + self.strand + '"')
+        except _lib.MagotError:
+            raise
+        except Exception:
+            print("either base_annotation has not annotation_set, or annotation_set has no genome, or genome has no"
+                  "            genome sequence, or genome sequence has no matching seqid, or coords are out of range on that seqid")
+            print(self.seqid)
+
+
+class ParentAnnotation(object):
+    """Parent of any BaseAnnotation (genes, transcripts), genome.py:649."""
+
+    def __init__(self, ID, seqid, feature_type, child_list=[], parent=None, strand=".", annotation_set=None, other_attributes={}):
+        self.ID = ID
+        self.seqid = seqid
+        self.feature_type = feature_type
+        self.child_list = list(child_list)
+        self.parent = parent
+        self.annotation_set = annotation_set
+        self.strand = strand
+        for attribute in other_attributes:
+            setattr(self, attribute, other_attributes[attribute])
+
+    def get_coords(self):
+        """genome.py:663-675 -- (min, max) over all descendants; None when childless."""
+        if len(self.child_list) > 0 and self.annotation_set is not None:
+            coords_list = []
+            for child in self.child_list:
+                child_object = self.annotation_set[child]
+                if isinstance(child_object, ParentAnnotation):
+                    coords_list = coords_list + list(child_object.get_coords())    # TypeError on None, as the reference
+                elif isinstance(child_object, BaseAnnotation):
+                    coords_list = coords_list + list(child_object.coords)
+            return (min(coords_list), max(coords_list))
+
+    def get_fasta(self, seq_type="nucleotide", longest=False, genomic=False, name_from='ID'):
+        """genome.py:677-731.  One device pass for this annotation and all its descendants."""
+        if genomic is not True and not (len(self.child_list) > 0 and self.annotation_set is not None):
+            return ""
+        if self.annotation_set is None or self.annotation_set.genome is None:
+            return None if genomic is True else ""
+        from .flatten import Flattener
+        fl = Flattener(self.annotation_set)
+        fl.add_top(self, seq_type=seq_type, longest=longest, genomic=genomic, name_from=name_from)
+        return fl.run(seq_type)
+
+
+class AnnotationSet(object):
+    """A set of annotations of a single genome, one dict per feature type (genome.py:524)."""
+
+    def __init__(self, genome=None):
+        self.gene = {}
+        self.transcript = {}
+        self.CDS = {}
+        self.UTR = {}
+        self.genome = genome
+
+    def _dict_names(self):
+        return sorted(k for k, v in self.__dict__.items() if type(v) == dict)
+
+    def __getitem__(self, item):
+        """genome.py:536-544: look in every dict attribute in dir() (sorted) order; the LAST hit wins."""
+        hit = None
+        found = False
+        d = self.__dict__
+        for name in self._dict_names():
+            t = d[name]
+            try:
+                hit = t[item]
+                found = True
+            except (KeyError, TypeError):
+                pass
+        if not found:
+            raise KeyError(item)
+        return hit
+
+    def build_index(self):
+        """ID -> object for every feature with __getitem__'s precedence (one pass, used by the flattener)."""
+        idx = {}
+        for name in self._dict_names():
+            idx.update(self.__dict__[name])
+        return idx
+
+    def read_gff(self, gff, *args, **kwargs):
+        kwargs["annotation_set_to_modify"] = self
+        read_gff(gff, *args, **kwargs)
+
+    def get_fasta(self, feature, seq_type="nucleotide", longest=False, genomic=False):
+        """genome.py:578-582: '\\n'.join of every <feature> annotation's fasta, in dict order
+        (empty results stay in the list -> blank lines).  All records go through ONE device plan."""
+        table = getattr(self, feature)
+        from .flatten import Flattener
+        fl = Flattener(self)
+        for key in table:
+            obj = table[key]
+            if not hasattr(obj, "get_fasta"):
+                raise AttributeError("%s instance has no attribute 'get_fasta'" % obj.__class__.__name__)
+            fl.add_top(obj, seq_type=seq_type, longest=longest, genomic=genomic, name_from='ID')
+        return fl.run(seq_type)
+
+
+def read_gff(gff, annotation_set_to_modify=None, base_features=['CDS', 'match_part', 'similarity', 'region'],
+             features_to_ignore=['exon'], gff_version="auto", parents_hierarchy=[], features_to_replace=[],
+             IDfield="ID", parent_field="Parent", presets=None):
+    """genome.py:242-415 -- GFF3 / GTF reader with the reference's ID, de-dup and implicit-parent
+    semantics.  Returns a new AnnotationSet (dicts in the order the reference's deepcopy leaves
+    them) unless annotation_set_to_modify is given."""
+    if presets is not None:
+        raise NotImplementedError("read_gff presets rely on Python-2 exec semantics and are out of scope")
+    parents_hierarchy = list(parents_hierarchy)
+    version = gff_version
+    gff_file = ensure_file(gff)
+    replace = [("\n", ""), ("\r", "")]
+    for feature in features_to_replace:
+        replace.append(("\t" + feature[0] + "\t", "\t" + feature[1] + "\t"))
+    extra_replace = replace[2:]
+    if annotation_set_to_modify is None:
+        annotation_set = AnnotationSet()
+    else:
+        annotation_set = annotation_set_to_modify
+    generate_new_ID_dict = {}
+    adict = annotation_set.__dict__
+    # __getitem__ precedence index kept incrementally: ID -> (dict name, object); a later dict name wins
+    owner = {}
+    for name in annotation_set._dict_names():
+        for k, v in adict[name].items():
+            owner[k] = (name, v)
+
+    def register(ftype, ID, obj):
+        cur = owner.get(ID)
+        if cur is None or ftype >= cur[0]:
+            owner[ID] = (ftype, obj)
+
+    phase_ok = ('0', '1', '2')
+    for original_line in gff_file:
+        if original_line[0] != "#" and original_line.count('\t') == 8:
+            line = original_line.replace("\n", "").replace("\r", "")
+            for a, b in extra_replace:
+                line = line.replace(a, b)
+            fields = line.split('\t')
+            f8 = fields[8]
+            if version == "auto":
+                if "=" in f8:
+                    version = 3
+                else:
+                    version = 2
+                    if IDfield is not None:
+                        if (" " + IDfield + " ") not in (" " + f8.replace(';', ' ')) and parents_hierarchy == []:
+                            IDfield = None
+                            parent_field = None
+                            if "gene_id" in f8 and "transcript_id" in f8:
+                                parents_hierarchy = ['transcript_id', 'gene_id']
+                            elif "gene_id" in f8:
+                                parents_hierarchy = ['gene_id']
+            ID = None
+            parent = None
+            other_attributes = {}
+            seqid = fields[0]
+            other_attributes['source'] = fields[1]
+            feature_type = fields[2]
+            if feature_type in features_to_ignore:
+                continue
+            c0, c1 = int(fields[3]), int(fields[4])
+            coords = (c0, c1) if c0 <= c1 else (c1, c0)
+            try:
+                other_attributes['score'] = float(fields[5])
+            except ValueError:
+                pass
+            strand = fields[6]
+            if fields[7] in phase_ok:
+                other_attributes['phase'] = int(fields[7])
+            defline_dict = {}
+            for defline_field in f8.split(';'):
+                if defline_field != "":
+                    if parent_field == "":
+                        defline_dict[""] = defline_field
+                    elif version == 2:
+                        if '"' in defline_field:
+                            defline_dict[defline_field.split()[0]] = defline_field.split('"')[1]
+                        else:
+                            try:
+                                sp = defline_field.split()
+                                defline_dict[sp[0]] = sp[1]
+                            except Exception:
+                                print(defline_field)
+                                return None
+                    elif version == 3:
+                        sp = defline_field.split('=')
+                        defline_dict[sp[0]] = sp[1]
+            if parent_field is not None:
+                if parent_field in defline_dict:
+                    parent = defline_dict[parent_field]
+            elif parents_hierarchy != []:
+                for parent_type in parents_hierarchy:
+                    if parent_type in defline_dict:
+                        parent = defline_dict[parent_type]
+                        break
+            if IDfield is not None:
+                if IDfield in defline_dict:
+                    ID = defline_dict[IDfield]
+                elif parent is not None:
+                    ID = parent + '-' + feature_type
+            elif parent is not None:
+                ID = parent + '-' + feature_type
+            else:
+                ID = seqid + '-' + feature_type + fields[3]
+            if ID in owner:                                     # annotation_set[ID] succeeded (genome.py:355-364)
+                if ID in generate_new_ID_dict:
+                    generate_new_ID_dict[ID] = generate_new_ID_dict[ID] + 1
+                    ID = ID + "-" + str(generate_new_ID_dict[ID])
+                else:
+                    generate_new_ID_dict[ID] = 2
+                    ID = ID + '2'
+            if parent is not None:
+                child_to_assign = ID
+                for parent_feature_index in range(len(parents_hierarchy)):
+                    parent_feature = parents_hierarchy[parent_feature_index]
+                    if parent_feature in defline_dict:
+                        parent_feature_ID = defline_dict[parent_feature]
+                        parent_feature_type = parent_feature.split('_')[0]
+                        parents_parent = None
+                        if parent_feature_index != len(parents_hierarchy) - 1:
+                            for parents_parent_feature in parents_hierarchy[parent_feature_index + 1:]:
+                                if parents_parent_feature in defline_dict:
+                                    parents_parent = defline_dict[parents_parent_feature]
+                        if parent_feature_type not in adict:
+                            adict[parent_feature_type] = {}
+                        tbl = adict[parent_feature_type]
+                        if parent_feature_ID in tbl:
+                            cl = tbl[parent_feature_ID].child_list
+                            if child_to_assign not in cl:
+                                cl.append(child_to_assign)
+                        else:
+                            pobj = ParentAnnotation(parent_feature_ID, seqid, parent_feature_type, child_list=[child_to_assign],
+                                                    parent=parents_parent, strand=strand, annotation_set=annotation_set)
+                            tbl[parent_feature_ID] = pobj
+                            register(parent_feature_type, parent_feature_ID, pobj)
+                        child_to_assign = parent_feature_ID
+                got = owner.get(parent)
+                if got is None:
+                    print("""It seems that this line has a parent attribute but that that parent doesn't have a line itself nor
+                    does this line have a defline attribute that specifies a parent type. I'm afraid this function can't currently
+                    deal with that.""")
+                    print(ID)
+                    print(parent)
+                    return None
+                cl = got[1].child_list
+                if ID not in cl:
+                    cl.append(ID)
+            for defline_attribute in defline_dict:
+                if defline_attribute != IDfield and defline_attribute != parent_field:
+                    other_attributes[defline_attribute] = defline_dict[defline_attribute]
+            if feature_type not in adict:
+                adict[feature_type] = {}
+            if feature_type in base_features:
+                obj = BaseAnnotation(ID, seqid, coords, feature_type, parent, strand, other_attributes, annotation_set)
+            else:
+                obj = ParentAnnotation(ID, seqid, feature_type, [], parent, strand, annotation_set, other_attributes)
+            adict[feature_type][ID] = obj
+            register(feature_type, ID, obj)
+    if annotation_set_to_modify is None:
+        # copy.deepcopy (genome.py:415) re-inserts every dict in Python-2.7 slot order
+        for name in annotation_set._dict_names():
+            tbl = adict[name]
+            if tbl:
+                adict[name] = {k: tbl[k] for k in _order(list(tbl), deepcopy=True)}
+        return annotation_set
+
+
+# ---------------------------------------------------------------------------------------------
+# Genome (genome.py:880-978)
+# ---------------------------------------------------------------------------------------------
+
+class Genome(object):
+    """genome class: sequence + annotations (genome.py:880)."""
+
+    def __init__(self, genome_sequence=None, annotations=None, varients=None, annotation_format='annotation_set',
+                 truncate_names=False):
+        if genome_sequence.__class__.__name__ == 'GenomeSequence' or genome_sequence is None:
+            self.genome_sequence = genome_sequence
+        else:
+            self.genome_sequence = GenomeSequence(genome_sequence, truncate_names=truncate_names)
+        if annotations is not None:
+            # genome.py:889 tests for the misspelt class name "AnotationSet", so an AnnotationSet object is
+            # never attached by the reference constructor; mirrored (the attribute is simply not set).
+            if annotations.__class__.__name__ == "AnotationSet" and annotation_format == 'annotation_set':
+                self.annotations = annotations
+                self.annotations.genome = self
+            elif annotation_format == 'gff3':
+                self.annotations = read_gff(annotations)
+                self.annotations.genome = self
+            elif annotation_format in ('cegma_gff', 'blast_csv', 'exonerate_output'):
+                raise NotImplementedError("annotation_format %r is outside the B200 hot path (SURVEY 8f)" % annotation_format)
+        else:
+            self.annotations = annotations
+
+    def get_scaffold_fasta(self, seqid):
+        return '>' + seqid + '\n' + self.genome_sequence[seqid]
+
+    def get_genome_fasta(self, remove_spaces=False):
+        fasta_list = []
+        for seqid in self.genome_sequence:
+            fasta_header = seqid.split()[0] if remove_spaces else seqid
+            fasta_list.append('>' + fasta_header + '\n' + self.genome_sequence[seqid])
+        return "\n".join(fasta_list)
+
+    def get_seqids(self, from_annotations=False):
+        seqid_list = []
+        warning = False
+        if self.genome_sequence is not None:
+            for seqid in self.genome_sequence:
+                seqid_list.append(seqid)
+        if self.annotations is not None and from_annotations:
+            seen = set()
+            for name in self.annotations._dict_names():
+                for feature in self.annotations.__dict__[name].values():
+                    seen.add(feature.seqid)
+            for seqid in seen:
+                if seqid not in seqid_list:
+                    seqid_list.append(seqid)
+                    warning = True
+        if warning:
+            print("warning, some annotations possessed seqids not found in sequence dictionary")
+        return seqid_list
+
+    def read_gff(self, gff, *args, **kwargs):
+        if getattr(self, "annotations", None) is not None:
+            self.annotations.read_gff(gff, *args, **kwargs)
+        else:
+            self.annotations = read_gff(gff, *args, **kwargs)
+            self.annotations.genome = self

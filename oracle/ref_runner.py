@@ -1,0 +1,62 @@
+"""TEST INFRASTRUCTURE -- runs the reference's OWN code (shimmed by make_ref.py) with the
+Python-2.7 dict order restored, so its output equals what `python2 genome_tools.py ...` prints.
+
+Used by tests/golden/make_golden.py (fixture generation), by tests that run in this
+container (where /root/reference exists) and by `bench.py --impl reference`.  On a box
+without /root/reference it works only if the git-ignored oracle/_ref/ travelled there.
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_ref                      # noqa: E402
+from py2dict import py2_order, py2_order_after_deepcopy   # noqa: E402
+
+_genome = None
+
+
+def ref():
+    """The shimmed reference `genome` module, or None."""
+    global _genome
+    if _genome is None:
+        _genome = make_ref.load()
+    return _genome
+
+
+def reorder_annotation_set(aset):
+    """Apply CPython-2.7 + deepcopy (genome.py:415) iteration order to every feature dict."""
+    for name, val in list(aset.__dict__.items()):
+        if type(val) == dict:
+            order = py2_order_after_deepcopy(list(val))
+            aset.__dict__[name] = {k: val[k] for k in order}
+    return aset
+
+
+def reorder_genome_sequence(gs):
+    """Apply CPython-2.7 iteration order to a GenomeSequence (no deepcopy on that path)."""
+    items = {k: gs[k] for k in py2_order(list(gs))}
+    gs.clear()
+    gs.update(items)
+    return gs
+
+
+def load_genome(fasta, gff=None, truncate_names=False, **read_gff_kwargs):
+    g = ref()
+    my = g.Genome(fasta, truncate_names=truncate_names)
+    if my.genome_sequence is not None:
+        reorder_genome_sequence(my.genome_sequence)
+    if gff is not None:
+        my.read_gff(gff, **read_gff_kwargs)
+        if my.annotations is not None:
+            reorder_annotation_set(my.annotations)
+    return my
+
+
+def gff2fasta(fasta, gff, from_exons="False", seq_type="nucleotide", longest="False", genomic="False"):
+    """stdout of genome_tools.py:324-330."""
+    if from_exons == "True":
+        my = load_genome(fasta, gff, features_to_ignore="CDS", features_to_replace=[('exon', 'CDS')])
+    else:
+        my = load_genome(fasta, gff)
+    return my.annotations.get_fasta('gene', seq_type=seq_type, longest=eval(longest), genomic=eval(genomic)) + "\n"

@@ -1,0 +1,158 @@
+#!/usr/bin/env python3
+"""Generates the committed golden fixtures in tests/golden/ by running the REFERENCE's own
+code (shimmed for Python 3 by oracle/make_ref.py, Python-2.7 dict order restored by
+oracle/ref_runner.py).  Run in the build container, where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+Writes
+  ref_test_data/*.gz   the reference's data fixtures (test_data/, DATA not source), gzipped,
+                       so the GPU box -- which has no /root/reference -- can run the same cases
+  manifest.json        POSIX cksum + byte count of the reference's stdout for every whole-file
+                       case (plus the three cksums hard-coded in test_data/test_suite.py)
+  kat.json             known-answer vectors for Sequence.reverse_compliment / translate /
+                       get_orfs / BaseAnnotation.get_seq clamping produced by the reference
+"""
+import gzip
+import json
+import os
+import random
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_runner            # noqa: E402
+import surrogate_c14         # noqa: E402
+from cksum import cksum      # noqa: E402
+
+REF_DATA = "/root/reference/test_data"
+DATA_FILES = ["O.biroi_refseqGenomeSubset.fasta", "O.biroi_NCBIrefseq_gff3Subset.gff", "StandardGTF.gtf",
+              "transcriptlessGTF.gtf", "minimalGFF3.gff", "CDSannotations.cds"]
+
+
+def copy_data():
+    out = os.path.join(HERE, "ref_test_data")
+    os.makedirs(out, exist_ok=True)
+    for f in DATA_FILES:
+        with open(os.path.join(REF_DATA, f), "rb") as fh:
+            raw = fh.read()
+        with open(os.path.join(out, f + ".gz"), "wb") as fh:
+            fh.write(gzip.compress(raw, 9, mtime=0))
+
+
+def whole_file_cases(tmp):
+    g = ref_runner.ref()
+    T = REF_DATA + "/"
+    ob_fa, ob_gff = T + DATA_FILES[0], T + DATA_FILES[1]
+    c14 = os.path.join(tmp, "C14.fasta")
+    with open(c14, "w", encoding="latin-1", newline="\n") as fh:
+        fh.write(surrogate_c14.build(T + "StandardGTF.gtf", T + "CDSannotations.cds"))
+    cases = {}
+
+    def put(name, text):
+        c, n = cksum(text)
+        cases[name] = {"cksum": c, "bytes": n}
+
+    # --- hard-coded by the reference's own test-suite (test_data/test_suite.py:8,12-14)
+    cases["suite:exclude_from_fasta"] = {"cksum": 1797510917, "bytes": 256187}
+    cases["suite:gff2fasta_C14_StandardGTF"] = {"cksum": 2836090577, "bytes": 690750}
+    cases["suite:gff2fasta_C14_StandardGTF_protein"] = {"cksum": 111942461, "bytes": 233762}
+    cases["suite:cds2pep"] = {"cksum": 111942461, "bytes": 233762}
+
+    # --- BASELINE config 1: O.biroi FASTA + GFF3
+    put("obiroi:gff2fasta", ref_runner.gff2fasta(ob_fa, ob_gff))
+    put("obiroi:gff2fasta_protein", ref_runner.gff2fasta(ob_fa, ob_gff, seq_type="protein"))
+    put("obiroi:gff2fasta_from_exons", ref_runner.gff2fasta(ob_fa, ob_gff, from_exons="True"))
+    my = ref_runner.load_genome(ob_fa, ob_gff, base_features=['exon', 'match_part', 'similarity', 'region'],
+                                features_to_ignore=['CDS'])
+    put("obiroi:exon_transcripts", my.annotations.get_fasta('gene') + "\n")
+    my = ref_runner.load_genome(ob_fa, ob_gff)
+    put("obiroi:get_fasta_mRNA", my.annotations.get_fasta('mRNA') + "\n")
+    put("obiroi:get_fasta_mRNA_protein", my.annotations.get_fasta('mRNA', seq_type="protein") + "\n")
+    put("obiroi:mRNA_name_from_Name",
+        "\n".join(my.annotations.mRNA[k].get_fasta(name_from='Name') for k in my.annotations.mRNA) + "\n")
+    put("obiroi:mRNA_genomic",
+        "\n".join(my.annotations.mRNA[k].get_fasta(genomic=True) for k in my.annotations.mRNA) + "\n")
+    put("obiroi:genome_fasta", my.get_genome_fasta() + "\n")
+    put("obiroi:cds_get_seq",
+        "\n".join(k + "\t" + my.annotations.CDS[k].get_seq() for k in my.annotations.CDS) + "\n")
+
+    # --- BASELINE config 2: surrogate C14 x three annotation formats
+    for gff in ("StandardGTF.gtf", "transcriptlessGTF.gtf", "minimalGFF3.gff"):
+        put("c14:%s" % gff, ref_runner.gff2fasta(c14, T + gff))
+        put("c14:%s:protein" % gff, ref_runner.gff2fasta(c14, T + gff, seq_type="protein"))
+    put("c14:StandardGTF.gtf:genomic", ref_runner.gff2fasta(c14, T + "StandardGTF.gtf", genomic="True"))
+    put("c14:StandardGTF.gtf:longest", ref_runner.gff2fasta(c14, T + "StandardGTF.gtf", longest="True"))
+    my = ref_runner.load_genome(c14, T + "StandardGTF.gtf")
+    put("c14:StandardGTF.gtf:get_fasta_transcript", my.annotations.get_fasta('transcript') + "\n")
+    return cases
+
+
+ALPHABETS = {
+    "acgt": "ACGT",
+    "mixed": "ACGTacgtNn",
+    "iupac": "ACGTacgtNnRYKMSWBDHVrykm-*. xU",
+}
+
+
+def kat_vectors():
+    g = ref_runner.ref()
+    rnd = random.Random(20261018)
+    vec = {"reverse_compliment": [], "translate": [], "get_orfs": [], "get_seq": []}
+    seqs = ["", "A", "AC", "ACG", "ACGT", "NNNATG", "acgRYKn-", "ATGTAA", "atgtaa", "ATGNNNTAA", "TAATAGTGA",
+            "ATG-AATAG", "NNATGAAATAG", "XATGCC"]
+    for name, alpha in ALPHABETS.items():
+        for n in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 31, 32, 33, 63, 64, 65, 100, 257, 1000):
+            seqs.append("".join(rnd.choice(alpha) for _ in range(n)))
+    for s in seqs:
+        vec["reverse_compliment"].append([s, str(g.Sequence(s).reverse_compliment())])
+        for frame in (0, 1, 2):
+            for strand in "+-":
+                for trimX in (True, False):
+                    try:
+                        r = g.Sequence(s).translate(frame=frame, strand=strand, trimX=trimX)
+                    except IndexError:
+                        r = "!IndexError"
+                    vec["translate"].append([s, frame, strand, trimX, r])
+    orf_inputs = [s for s in seqs if len(s) >= 3]
+    for n in (300, 999, 2000):
+        # stop-poor sequence so that long ORFs exist
+        orf_inputs.append("".join(rnd.choice("ACG" * 6 + "T" + "Nn") for _ in range(n)))
+    for s in orf_inputs:
+        for from_atg in (False, True):
+            vec["get_orfs"].append([s, from_atg, g.Sequence(s).get_orfs(from_atg=from_atg)])
+        try:
+            lo = g.Sequence(s).get_orfs(longest=True)
+        except IndexError:
+            lo = "!IndexError"
+        vec["get_orfs"].append([s, "longest", lo])
+    # BaseAnnotation.get_seq: Python-slice clamping at contig ends (genome.py:603-608)
+    contig = "".join(rnd.choice("ACGTacgtN") for _ in range(50))
+    gs = g.GenomeSequence(">c1\n" + contig + "\n")
+    for (a, b) in [(1, 50), (1, 1), (50, 50), (10, 20), (45, 60), (50, 80), (51, 60), (0, 5), (0, 50), (0, 60),
+                   (-3, 10), (-3, 60), (30, 29), (7, 7)]:
+        for strand in "+-.":
+            aset = g.AnnotationSet()
+            my = g.Genome(gs)
+            my.annotations = aset
+            aset.genome = my
+            base = g.BaseAnnotation("x", "c1", tuple(sorted((a, b))), "CDS", None, strand, {}, aset)
+            vec["get_seq"].append([contig, a, b, strand, str(base.get_seq())])
+    return vec
+
+
+def main():
+    import tempfile
+    copy_data()
+    with tempfile.TemporaryDirectory() as tmp:
+        cases = whole_file_cases(tmp)
+    with open(os.path.join(HERE, "manifest.json"), "w") as fh:
+        json.dump(cases, fh, indent=1, sort_keys=True)
+    with open(os.path.join(HERE, "kat.json"), "w") as fh:
+        json.dump(kat_vectors(), fh, indent=0)
+    print("wrote", len(cases), "whole-file cases")
+
+
+if __name__ == "__main__":
+    main()

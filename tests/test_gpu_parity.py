@@ -1,0 +1,271 @@
+"""Parity of the CUDA path (through the C ABI / the Python API above it) against the oracle and the
+reference-generated goldens.  Everything here is bit-exact (integer / byte work)."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+import coracle
+import magot_oracle as mo
+from cksum import cksum
+
+pytestmark = pytest.mark.gpu
+
+
+def _ck(text):
+    c, n = cksum(text)
+    return {"cksum": c, "bytes": n}
+
+
+def _stdout_of(fn, *a, **k):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        fn(*a, **k)
+    return buf.getvalue()
+
+
+@pytest.fixture(scope="module")
+def mg():
+    import magot_b200
+    return magot_b200
+
+
+# ---- Sequence ops against the reference-generated known answers ---------------------------------------
+
+def test_kat_reverse_compliment(mg, kat):
+    for s, r in kat["reverse_compliment"]:
+        assert str(mg.Sequence(s).reverse_compliment()) == r
+
+
+def test_kat_translate_all_frames(mg, kat):
+    for s, frame, strand, trimx, r in kat["translate"]:
+        if r == "!IndexError":
+            continue
+        assert mg.Sequence(s).translate(frame=frame, strand=strand, trimX=trimx) == r, (s[:30], frame, strand, trimx)
+
+
+def test_kat_get_orfs(mg, kat):
+    for s, mode, r in kat["get_orfs"][:90]:
+        if mode == "longest":
+            if r != "!IndexError":
+                assert mg.Sequence(s).get_orfs(longest=True) == r
+        else:
+            assert mg.Sequence(s).get_orfs(from_atg=mode) == r
+
+
+def test_translate_batch_large(mg):
+    rng = np.random.default_rng(5)
+    alpha = np.frombuffer(b"ACGTacgtNn", dtype=np.uint8)
+    seqs = [alpha[rng.integers(0, 10, size=int(n))].tobytes() for n in rng.integers(0, 4000, size=300)]
+    for frame in (0, 1, 2):
+        for strand in "+-":
+            got = mg.genome._translate_many(seqs, frame=frame, strand=strand)
+            for s, g in zip(seqs, got):
+                w = coracle.translate(s, frame, strand == '-', True)
+                assert g == (None if w is None else w.decode())
+
+
+# ---- config 1 / config 2: whole files against the reference's cksums ----------------------------------------
+
+def test_suite_goldens_via_entry_points(mg, ref_data, manifest):
+    from magot_b200 import genome_tools as gt
+    out = _stdout_of(gt.main, ["genome_tools.py", "exclude_from_fasta", os.path.join(ref_data, "O.biroi_refseqGenomeSubset.fasta"), "NW_011924881.1"])
+    assert _ck(out) == manifest["suite:exclude_from_fasta"]
+    out = _stdout_of(gt.main, ["genome_tools.py", "cds2pep", os.path.join(ref_data, "CDSannotations.cds")])
+    assert _ck(out) == manifest["suite:cds2pep"]
+    fa, gtf = os.path.join(ref_data, "C14.fasta"), os.path.join(ref_data, "StandardGTF.gtf")
+    out = _stdout_of(gt.main, ["genome_tools.py", "gff2fasta", fa, gtf])
+    assert _ck(out) == manifest["suite:gff2fasta_C14_StandardGTF"]
+    with open(os.path.join(ref_data, "CDSannotations.cds"), encoding="latin-1", newline="\n") as fh:
+        assert out == fh.read()
+    out = _stdout_of(gt.main, ["genome_tools.py", "gff2fasta", fa, gtf, "seq_type=protein"])
+    assert _ck(out) == manifest["suite:gff2fasta_C14_StandardGTF_protein"]
+
+
+@pytest.mark.parametrize("gff", ["transcriptlessGTF.gtf", "minimalGFF3.gff"])
+def test_c14_annotation_formats(mg, ref_data, manifest, gff):
+    from magot_b200 import genome_tools as gt
+    fa = os.path.join(ref_data, "C14.fasta")
+    assert _ck(_stdout_of(gt.gff2fasta, fa, os.path.join(ref_data, gff))) == manifest["c14:%s" % gff]
+    assert _ck(_stdout_of(gt.gff2fasta, fa, os.path.join(ref_data, gff), seq_type="protein")) == manifest["c14:%s:protein" % gff]
+
+
+def test_c14_genomic_longest_transcript(mg, ref_data, manifest):
+    from magot_b200 import genome_tools as gt
+    fa, gtf = os.path.join(ref_data, "C14.fasta"), os.path.join(ref_data, "StandardGTF.gtf")
+    assert _ck(_stdout_of(gt.gff2fasta, fa, gtf, genomic="True")) == manifest["c14:StandardGTF.gtf:genomic"]
+    assert _ck(_stdout_of(gt.gff2fasta, fa, gtf, longest="True")) == manifest["c14:StandardGTF.gtf:longest"]
+    g = mg.Genome(fa)
+    g.read_gff(gtf)
+    assert _ck(g.annotations.get_fasta('transcript') + "\n") == manifest["c14:StandardGTF.gtf:get_fasta_transcript"]
+
+
+def test_obiroi_whole_api(mg, ref_data, manifest):
+    from magot_b200 import genome_tools as gt
+    fa = os.path.join(ref_data, "O.biroi_refseqGenomeSubset.fasta")
+    gff = os.path.join(ref_data, "O.biroi_NCBIrefseq_gff3Subset.gff")
+    out = _stdout_of(gt.gff2fasta, fa, gff)
+    assert out == mo.gff2fasta(fa, gff)
+    assert _ck(out) == manifest["obiroi:gff2fasta"]
+    assert _ck(_stdout_of(gt.gff2fasta, fa, gff, seq_type="protein")) == manifest["obiroi:gff2fasta_protein"]
+    assert _ck(_stdout_of(gt.gff2fasta, fa, gff, from_exons="True")) == manifest["obiroi:gff2fasta_from_exons"]
+    g = mg.Genome(fa)
+    g.read_gff(gff, base_features=['exon', 'match_part', 'similarity', 'region'], features_to_ignore=['CDS'])
+    assert _ck(g.annotations.get_fasta('gene') + "\n") == manifest["obiroi:exon_transcripts"]
+    g = mg.Genome(fa, gff, annotation_format='gff3')
+    a = g.annotations
+    assert _ck(a.get_fasta('mRNA') + "\n") == manifest["obiroi:get_fasta_mRNA"]
+    assert _ck(a.get_fasta('mRNA', seq_type="protein") + "\n") == manifest["obiroi:get_fasta_mRNA_protein"]
+    assert _ck("\n".join(a.mRNA[k].get_fasta(name_from='Name') for k in a.mRNA) + "\n") == manifest["obiroi:mRNA_name_from_Name"]
+    assert _ck("\n".join(a.mRNA[k].get_fasta(genomic=True) for k in a.mRNA) + "\n") == manifest["obiroi:mRNA_genomic"]
+    assert _ck(g.get_genome_fasta() + "\n") == manifest["obiroi:genome_fasta"]
+    assert _ck("\n".join(k + "\t" + a.CDS[k].get_seq() for k in a.CDS) + "\n") == manifest["obiroi:cds_get_seq"]
+    # the reference crashes here (a gene without CDS children): same exception types
+    with pytest.raises(TypeError):
+        a.get_fasta('gene', genomic=True)
+    with pytest.raises(ValueError):
+        a.get_fasta('gene', longest=True)
+    with pytest.raises(AttributeError):
+        a.get_fasta('CDS')
+
+
+def test_coords2fasta_and_scaffold(mg, ref_data):
+    from magot_b200 import genome_tools as gt
+    fa = os.path.join(ref_data, "O.biroi_refseqGenomeSubset.fasta")
+    for (s, e) in [("1", "80"), ("10000", "12780"), ("0", "5"), ("64000", "99999999"), ("-5", "20")]:
+        assert _stdout_of(gt.coords2fasta, fa, "NW_011924877.1", s, e) == mo.coords2fasta(fa, "NW_011924877.1", s, e)
+    assert _stdout_of(gt.get_seq_from_fasta, fa, "NW_011924876.1") == mo.get_seq_from_fasta(fa, "NW_011924876.1")
+
+
+def test_extract_upstream_downstream(mg, ref_data):
+    from magot_b200 import genome_tools as gt
+    fa = os.path.join(ref_data, "O.biroi_refseqGenomeSubset.fasta")
+    gff = os.path.join(ref_data, "O.biroi_NCBIrefseq_gff3Subset.gff")
+    for stream in ("up", "down"):
+        for n in ("50", "30000"):
+            assert _stdout_of(gt.extract_upstream_downstream, fa, gff, n, stream) == mo.extract_upstream_downstream(fa, gff, n, stream)
+
+
+def test_kat_get_seq_clamping(mg, kat):
+    for contig, a, b, strand, r in kat["get_seq"]:
+        gs = mg.GenomeSequence(">c1\n" + contig + "\n")
+        my = mg.Genome(gs)
+        aset = mg.AnnotationSet()
+        my.annotations = aset
+        aset.genome = my
+        base = mg.BaseAnnotation("x", "c1", tuple(sorted((a, b))), "CDS", None, strand, {}, aset)
+        assert str(base.get_seq()) == r, (a, b, strand)
+        gs.close()
+
+
+# ---- storage: pack -> fetch round trips, arbitrary bytes ------------------------------------------------------
+
+def test_pack_fetch_roundtrip_arbitrary_bytes(mg):
+    rng = np.random.default_rng(9)
+    alpha = np.frombuffer(b"ACGTacgtNn-RYKMrykmSWBDHV*. xU\xe9\xff", dtype=np.uint8)
+    contigs = {}
+    for i, n in enumerate([1, 2, 15, 16, 17, 31, 32, 33, 63, 64, 65, 1000, 4097, 70001]):
+        p = np.ones(alpha.size)
+        p[:10] = 30
+        contigs["c%d" % i] = alpha[rng.choice(alpha.size, size=n, p=p / p.sum())].tobytes().decode("latin-1")
+    fasta = "".join(">%s\n%s\n" % kv for kv in contigs.items())
+    gs = mg.GenomeSequence(fasta)
+    assert gs._engine().primary.n_exceptions > 0
+    for k, v in contigs.items():
+        assert len(gs[k]) == len(v)
+        assert str(gs[k]) == v
+        for (a, b) in [(0, 1), (3, 40), (len(v) // 2, len(v)), (len(v) - 1, len(v)), (5, 5)]:
+            assert gs[k][a:b] == v[a:b]
+        raw = gs._engine().primary.fetch(gs.contig_index(k), 0, len(v), True).decode("latin-1")
+        assert raw == mo.reverse_compliment(v)
+    assert gs["c11"][-5:] == contigs["c11"][-5:] and gs["c11"][7] == contigs["c11"][7]
+    gs.close()
+
+
+# ---- synthetic twins of configs 3/4 against the C oracle --------------------------------------------------------
+
+def _oracle_products(contigs, tbl):
+    lens = np.array([a.size for a in contigs])
+    # Python slice semantics for in-range/overrunning coordinates (all synthetic starts are >= 1)
+    lo = np.clip(tbl.seg_start - 1, 0, lens[tbl.seg_contig])
+    hi = np.clip(tbl.seg_end, 0, lens[tbl.seg_contig])
+    nuc, off = coracle.splice([a.tobytes() for a in contigs], tbl.rec_seg_off, tbl.seg_contig, lo, hi, tbl.seg_strand)
+    aa, aa_off, aa_len = coracle.splice_translate(nuc, off)
+    return nuc, off, aa, aa_off, aa_len
+
+
+@pytest.mark.parametrize("kind,total,ntx,seed", [("human", 6_000_000, 3000, 4), ("insect", 3_000_000, 2000, 3)])
+def test_synthetic_twin_against_c_oracle(mg, kind, total, ntx, seed):
+    from magot_b200 import engine, synth
+    layout = synth.contig_layout(kind, total, seed)
+    contigs = synth.synth_genome_host(layout, seed, n_mean=300)
+    # sprinkle bytes outside the packed alphabet
+    rng = np.random.default_rng(seed)
+    for a in contigs[:5]:
+        idx = rng.integers(0, a.size, size=50)
+        a[idx] = np.frombuffer(b"RYKMSWBDHVrykm*", dtype=np.uint8)[rng.integers(0, 15, size=50)]
+    ann = synth.synth_annotation(layout, ntx, seed)
+    g = engine.DeviceGenome([a.size for a in contigs], device=0)
+    for i, a in enumerate(contigs):
+        g.pack(i, a)
+    g.finalize()
+    for which in ("cds", "exon"):
+        tbl = ann.table(which, framing=False)
+        nuc, off, aa, aa_off, aa_len = _oracle_products(contigs, tbl)
+        plan = engine.Plan(g, tbl)
+        nt, pt = plan.prepare()
+        assert nt == nuc.size and pt == aa.size
+        got_n, got_a = plan.lengths()
+        assert np.array_equal(got_n, np.diff(off)) and np.array_equal(got_a, aa_len)
+        assert plan.emit_host(protein=False).tobytes() == nuc.tobytes()
+        assert plan.emit_host(protein=True).tobytes() == aa.tobytes()
+        plan.close()
+        # with FASTA framing: one D2H yields the final file
+        tblf = ann.table(which, framing=True)
+        text, _ = engine.run_table(g, tblf)
+        want = b"".join(b">" + n.encode() + b"\n" + nuc[off[i]:off[i + 1]].tobytes() + b"\n" for i, n in enumerate(ann.names))
+        assert text == want
+        textp, _ = engine.run_table(g, tblf, protein=True)
+        wantp = b"".join(b">" + n.encode() + b"\n" + aa[aa_off[i]:aa_off[i + 1]].tobytes() + b"\n" for i, n in enumerate(ann.names))
+        assert textp == wantp
+    g.close()
+
+
+def test_edge_records(mg):
+    """Empty records, zero-length segments, 1-base segments, records <= 2 bases (translate -> None)."""
+    from magot_b200 import engine
+    contig = np.frombuffer(b"ACGTNNacgtTTGACCATGGGTAAACTGATCGATCGTAGCTAGCTAGCTAGCATCGATCGAT" * 3, dtype=np.uint8)
+    g = engine.DeviceGenome([contig.size], device=0)
+    g.pack(0, contig)
+    g.finalize()
+    L = contig.size
+    recs = [[], [(5, 4, 0)], [(1, 1, 0)], [(1, 2, 1)], [(1, 3, 1)], [(L, L, 1), (1, 1, 0)], [(L - 1, L + 50, 0)], [(L + 5, L + 9, 0)],
+            [(1, L, 1)], [(2, 1, 0), (3, 2, 0), (10, 30, 0)], [(1, 3, 0)] * 40, [(7, 7, 1)] * 33, [(1, L, 0)]]
+    rec_off, cid, st, en, sd = [0], [], [], [], []
+    for r in recs:
+        for (a, b, m) in r:
+            cid.append(0); st.append(a); en.append(b); sd.append(m)
+        rec_off.append(len(cid))
+    R = len(recs)
+    z = np.zeros(R, dtype=np.int32)
+    tbl = engine.RecordTable(rec_off, cid, st, en, sd, np.zeros(R, np.int64), z, z, np.zeros(0, np.uint8))
+    text = contig.tobytes().decode()
+    want_n, want_p, want_len = [], [], []
+    for r in recs:
+        s = "".join(mo.reverse_compliment(text[a - 1:b]) if m else text[a - 1:b] for (a, b, m) in r)
+        want_n.append(s)
+        t = mo.translate(s)
+        want_len.append(-1 if t is None else len(t))
+        want_p.append(t or "")
+    plan = engine.Plan(g, tbl)
+    plan.prepare()
+    nl, al = plan.lengths()
+    assert list(nl) == [len(s) for s in want_n] and list(al) == want_len
+    assert plan.emit_host(False).tobytes().decode() == "".join(want_n)
+    assert plan.emit_host(True).tobytes().decode() == "".join(want_p)
+    plan.close()
+    empty = engine.RecordTable([0], [], [], [], [], [], [], [], np.zeros(0, np.uint8))
+    assert engine.run_table(g, empty)[0] == b""
+    g.close()
