@@ -182,8 +182,8 @@ __device__ __forceinline__ void mg_decode8(uint32_t x, uint32_t &o0, uint32_t &o
         uint32_t m0 = ((t & 0x8u) << 4) | ((t & 0x80u) << 8) | ((t & 0x800u) << 12) | ((t & 0x8000u) << 16);
         t = h >> 16;
         uint32_t m1 = ((t & 0x8u) << 4) | ((t & 0x80u) << 8) | ((t & 0x800u) << 12) | ((t & 0x8000u) << 16);
-        m0 = __byte_perm(m0, 0, 0xBA98);   // replicate each byte's sign bit -> 0xFF / 0x00
-        m1 = __byte_perm(m1, 0, 0xBA98);
+        m0 = (m0 >> 7) * 0xFFu;             // bit 7 of each byte -> 0xFF / 0x00 byte mask
+        m1 = (m1 >> 7) * 0xFFu;
         o0 = (o0 & ~m0) | (h0 & m0);
         o1 = (o1 & ~m1) | (h1 & m1);
     }

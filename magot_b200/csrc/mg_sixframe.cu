@@ -1,6 +1,723 @@
-// TEMPORARY stub while K4 is being written (see mg_sixframe.cu.draft)
+// mg_sixframe.cu -- K4: six-frame translation + stop-codon / ORF scan over whole contigs.
+// Replaces Sequence.get_orfs (genome.py:824-851) applied to every contig, i.e. what dna2orfs
+// (genome_tools.py:145-180) intended: translations in the order (frame 0,'-'), (0,'+'), (1,'-'),
+// (1,'+'), (2,'-'), (2,'+') with the reference's frame quirk (frame 1 == codons from offset 2,
+// frame 2 == codons from offset 4, frame 0 == offset 0, or 3 when the first codon is 'X' and is
+// trimmed), each split on '*', ORFs shorter than min_aa dropped (min_aa = 0 == reference).
+//
+// Design: stops are found bit-parallel on the nibble-packed genome (16 positions per 64-bit op, both
+// strands from the same forward read: reverse-strand stops TAA/TAG/TGA are TTA/CTA/TCA forward).
+// Every stream (contig, frame, strand) is a chain of stops in ascending genome coordinate, bracketed
+// by a virtual stop at each contig end; each consecutive pair of stops bounds one ORF, attributed to
+// the HIGHER stop.  "Previous stop" is a prefix-max: warp shuffles inside the CTA, a three-phase
+// max-scan across CTA tiles.  Two passes over the genome count and emit (the ORF count is data
+// dependent), a prefix sum assigns output slots in reference order (plus strands ascend, minus
+// strands descend), and the residues are produced by a flat 16-residue-per-thread gather like K3.
+#include <algorithm>
 #include "mg_common.cuh"
-void mg_sixframe_free(mg_genome *) {}
-extern "C" int mg_sixframe_count(mg_genome *, int64_t, int64_t, int64_t, int64_t *, int64_t *, void *) { mg_set_error("K4 not built yet"); return MG_ESTATE; }
-extern "C" int mg_sixframe_emit(mg_genome *, uint8_t *, mg_orf *, void *) { mg_set_error("K4 not built yet"); return MG_ESTATE; }
-extern "C" int mg_sixframe_emit_device(mg_genome *, uint8_t *, mg_orf *, void *) { mg_set_error("K4 not built yet"); return MG_ESTATE; }
+
+#define SIX_THREADS 256
+#define SIX_BPT 48                                   // bases per thread
+#define SIX_TILE (SIX_THREADS * SIX_BPT)             // 12288 bases per CTA (multiple of 3 and of 16)
+#define AA_TILE 8192
+#define AA_THREADS 256
+#define AA_CAP 512
+
+struct mg_sixframe_state {
+    int64_t contig_lo = 0, contig_hi = 0, min_aa = 0;
+    int64_t n_tiles = 0;
+    std::vector<int64_t> h_tile_base;                // [n_contig_in_range + 1], starts at 0
+    int64_t *d_tile_base = nullptr;
+    int32_t *d_cs = nullptr;                         // [nc*6] first-codon offset of each stream
+    int64_t *d_m = nullptr;                          // [nc*6] residues in each stream's translation
+    int64_t *d_tile_last = nullptr;                  // [6][n_tiles] last stop (global base index) or -1
+    int64_t *d_carry = nullptr;                      // [6][n_tiles] last stop before the tile
+    int64_t *d_chunk = nullptr;                      // max-scan scratch
+    int32_t *d_cnt = nullptr;                        // [n_tiles*6] kept ORFs per (contig, stream, tile) in output order
+    int64_t *d_cnt_off = nullptr;                    // [n_tiles*6+1]
+    int64_t *d_scan_tmp = nullptr;
+    int64_t scan_tmp_cap = 0;
+    int64_t n_orf = 0, n_bytes = 0;
+    mg_orf *d_recs = nullptr;
+    int32_t *d_len = nullptr;
+    int64_t *d_aa_off = nullptr;                     // [n_orf+1]
+    int64_t *d_src = nullptr;                        // [n_orf] first base (plus) / one past last base | 1<<62 (minus)
+    int64_t *d_aa_tile = nullptr;
+    int64_t n_aa_tile = 0;
+    uint8_t *d_aa = nullptr;                         // library-owned residue buffer for the host variant
+    int64_t aa_cap = 0;
+    std::vector<void *> owned;
+    bool counted = false;
+};
+
+// ---- per-stream geometry ------------------------------------------------------------------------------
+// stream index sidx = 2*frame + (plus ? 1 : 0): reference order is sidx ascending.
+__global__ void k_six_streams(const uint32_t *__restrict__ packed, const int64_t *__restrict__ contig_len,
+                              const int64_t *__restrict__ contig_base, int64_t contig_lo, int64_t nc,
+                              int32_t *__restrict__ cs_out, int64_t *__restrict__ m_out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nc * 6) return;
+    const int64_t c = contig_lo + i / 6;
+    const int sidx = (int)(i % 6), f = sidx >> 1, plus = sidx & 1;
+    const int64_t L = contig_len[c], gb = contig_base[c];
+    int cs = 0;
+    int64_t m = 0;
+    if (L > 2 + f) {                                 // otherwise translate() returns None (genome.py:810)
+        cs = f == 0 ? 0 : (f == 1 ? 2 : 4);
+        if (f == 0) {                                // trimX: one leading X is removed (genome.py:819-821)
+            const uint64_t v = plus ? mg_ld_nib16(packed, gb) : mg_ld_nib16(packed, gb + L - 3);
+            if ((uint32_t)v & 0x888u) cs = 3;        // complementing does not change validity
+        }
+        m = (L - cs) / 3;
+        if (m < 0) m = 0;
+    }
+    cs_out[i] = cs;
+    m_out[i] = m;
+}
+
+// ---- stop masks of one thread's 48 positions ---------------------------------------------------------
+#define NIBM 0x1111111111111111ull
+__device__ __forceinline__ uint64_t res_mask(int r) {     // nibble slots k with k % 3 == r
+    return r == 0 ? 0x1001001001001001ull : (r == 1 ? 0x0010010010010010ull : 0x0100100100100100ull);
+}
+
+struct SixMasks {
+    uint64_t pm[3], mm[3];                           // plus / minus stop flags, bit 4k of group g = position 16g+k
+};
+
+// x0 = contig offset of the thread's first position (multiple of 48); gb = contig's global base index
+__device__ __forceinline__ void six_masks(const uint32_t *__restrict__ packed, int64_t gb, int64_t L, int64_t x0,
+                                          const int32_t *cs6, SixMasks &s) {
+    uint64_t v[4];
+    const uint2 *p = reinterpret_cast<const uint2 *>(packed + ((gb + x0) >> 3));
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+        const uint2 w = __ldg(p + g);
+        v[g] = ((uint64_t)w.y << 32) | w.x;
+    }
+    v[3] = __ldg(packed + ((gb + x0 + 48) >> 3));   // only nibbles 48,49 are needed
+    uint64_t T[4], A[4], G[4], C[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const uint64_t inv = (v[g] >> 3) & NIBM, b0 = v[g] & NIBM, b1 = (v[g] >> 1) & NIBM;
+        T[g] = b1 & b0 & ~inv;
+        A[g] = NIBM & ~(b1 | b0 | inv);
+        G[g] = b1 & ~b0 & ~inv;
+        C[g] = b0 & ~b1 & ~inv;
+    }
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+        const uint64_t A1 = (A[g] >> 4) | (A[g + 1] << 60), A2 = (A[g] >> 8) | (A[g + 1] << 56);
+        const uint64_t G1 = (G[g] >> 4) | (G[g + 1] << 60), G2 = (G[g] >> 8) | (G[g + 1] << 56);
+        const uint64_t T1 = (T[g] >> 4) | (T[g + 1] << 60);
+        const uint64_t C1 = (C[g] >> 4) | (C[g + 1] << 60);
+        s.pm[g] = T[g] & ((A1 & (A2 | G2)) | (G1 & A2));              // TAA TAG TGA
+        s.mm[g] = A2 & ((T1 & (T[g] | C[g])) | (C1 & T[g]));          // TTA CTA TCA = rc of the above
+    }
+    // ---- validity at the contig ends
+    const int64_t lim = L - 2 - x0;                  // positions t >= lim have no full codon
+    if (lim < 48) {
+#pragma unroll
+        for (int g = 0; g < 3; g++) {
+            const int64_t k = lim - 16 * g;
+            const uint64_t keep = k <= 0 ? 0ull : (k >= 16 ? ~0ull : ((1ull << (4 * k)) - 1ull));
+            s.pm[g] &= keep;
+            s.mm[g] &= keep;
+        }
+    }
+    if (x0 == 0) {
+        if (cs6[1] == 3) s.pm[0] &= ~1ull;           // frame 0 '+': trimmed first codon
+        s.pm[0] &= ~(1ull << 4);                     // frame 2 '+' starts at offset 4: codon at 1 is not read
+    }
+    // minus strand: oriented start q0 = L-3-x; frame 0 trimmed drops q0 = 0, frame 2 never reads q0 = 1
+    {
+        const int64_t t0 = L - 3 - x0, t1 = L - 4 - x0;
+        if (cs6[0] == 3 && t0 >= 0 && t0 < 48) s.mm[t0 >> 4] &= ~(1ull << (4 * (t0 & 15)));
+        if (t1 >= 0 && t1 < 48) s.mm[t1 >> 4] &= ~(1ull << (4 * (t1 & 15)));
+    }
+}
+
+// residue (t % 3) selected by stream sidx: plus frame f -> rho_f, minus -> (L%3 - rho_f) % 3
+__device__ __forceinline__ int stream_res(int sidx, int Lm3) {
+    const int f = sidx >> 1;
+    const int rho = f == 0 ? 0 : (f == 1 ? 2 : 1);
+    return (sidx & 1) ? rho : (Lm3 - rho + 3) % 3;
+}
+
+// first / last stop of stream in the thread (tile-local thread-relative position 0..47, or -1)
+__device__ __forceinline__ void stream_first_last(const SixMasks &s, int sidx, int Lm3, int &first, int &last) {
+    const int r = stream_res(sidx, Lm3);
+    const uint64_t *msk = (sidx & 1) ? s.pm : s.mm;
+    first = -1;
+    last = -1;
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+        const uint64_t x = msk[g] & res_mask((r - g + 3) % 3);
+        if (x) {
+            if (first < 0) first = 16 * g + ((__ffsll((long long)x) - 1) >> 2);
+            last = 16 * g + ((63 - __clzll((long long)x)) >> 2);
+        }
+    }
+}
+
+struct TileInfo {
+    int64_t c, k, gb, L, Tc;                         // contig, tile index in contig, global base, length, tiles in contig
+    int Lm3;
+    int32_t cs[6];
+    int64_t m[6];
+};
+
+__device__ __forceinline__ void tile_info(int64_t tile, const int64_t *__restrict__ tile_base, int64_t nc, int64_t contig_lo,
+                                          const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base,
+                                          const int32_t *__restrict__ cs, const int64_t *__restrict__ m, TileInfo &ti) {
+    int64_t lo = 0, hi = nc;                          // largest ci with tile_base[ci] <= tile
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (tile_base[mid] <= tile) lo = mid; else hi = mid;
+    }
+    // contigs without tiles (L == 0) share a tile_base value with their successor: take the last one
+    ti.c = contig_lo + lo;
+    ti.k = tile - tile_base[lo];
+    ti.Tc = tile_base[lo + 1] - tile_base[lo];
+    ti.gb = contig_base[ti.c];
+    ti.L = contig_len[ti.c];
+    ti.Lm3 = (int)(ti.L % 3);
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        ti.cs[s] = cs[lo * 6 + s];
+        ti.m[s] = m[lo * 6 + s];
+    }
+}
+
+// ---- pass A: last stop of every stream in every tile ------------------------------------------------
+__global__ void __launch_bounds__(SIX_THREADS) k_six_last(const uint32_t *__restrict__ packed, const int64_t *__restrict__ tile_base,
+                                                          int64_t nc, int64_t contig_lo, const int64_t *__restrict__ contig_len,
+                                                          const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
+                                                          const int64_t *__restrict__ m, int64_t n_tiles,
+                                                          int64_t *__restrict__ tile_last) {
+    __shared__ TileInfo ti;
+    __shared__ int s_last[6];
+    if (threadIdx.x == 0) tile_info(blockIdx.x, tile_base, nc, contig_lo, contig_len, contig_base, cs, m, ti);
+    if (threadIdx.x < 6) s_last[threadIdx.x] = -1;
+    __syncthreads();
+    const int64_t x0 = ti.k * SIX_TILE + (int64_t)threadIdx.x * SIX_BPT;
+    if (x0 < ti.L) {
+        SixMasks sm;
+        six_masks(packed, ti.gb, ti.L, x0, ti.cs, sm);
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            int first, last;
+            stream_first_last(sm, s, ti.Lm3, first, last);
+            if (last >= 0) atomicMax(&s_last[s], (int)threadIdx.x * SIX_BPT + last);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int v = s_last[threadIdx.x];
+        tile_last[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = v < 0 ? -1 : ti.gb + ti.k * SIX_TILE + v;
+    }
+}
+
+// ---- pass B: exclusive max-scan of tile_last along tiles, one row per stream (blockIdx.y) ----------------
+#define MS_THREADS 256
+#define MS_ITEMS 8
+#define MS_TILE (MS_THREADS * MS_ITEMS)
+
+__device__ __forceinline__ int64_t warp_incl_max(int64_t v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d && t > v) v = t;
+    }
+    return v;
+}
+// exclusive max-scan across the block (identity -1); *total = block max
+__device__ __forceinline__ int64_t block_excl_max(int64_t v, int64_t *s_warp, int64_t *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t inc = warp_incl_max(v);
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int64_t w = lane < (MS_THREADS / 32) ? s_warp[lane] : -1;
+        w = warp_incl_max(w);
+        if (lane < (MS_THREADS / 32)) s_warp[lane] = w;
+    }
+    __syncthreads();
+    int64_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) ex = -1;
+    if (wid && s_warp[wid - 1] > ex) ex = s_warp[wid - 1];
+    *total = s_warp[MS_THREADS / 32 - 1];
+    __syncthreads();
+    return ex;
+}
+__global__ void __launch_bounds__(MS_THREADS) k_ms_reduce(const int64_t *__restrict__ in, int64_t n, int64_t nb, int64_t *__restrict__ cmax) {
+    __shared__ int64_t s_warp[MS_THREADS / 32];
+    const int64_t *row = in + (int64_t)blockIdx.y * n;
+    const int64_t base = (int64_t)blockIdx.x * MS_TILE;
+    int64_t v = -1;
+    for (int j = 0; j < MS_ITEMS; j++) {
+        const int64_t i = base + j * MS_THREADS + threadIdx.x;
+        if (i < n && row[i] > v) v = row[i];
+    }
+    int64_t total;
+    block_excl_max(v, s_warp, &total);
+    if (threadIdx.x == 0) cmax[(int64_t)blockIdx.y * nb + blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(MS_THREADS) k_ms_chunks(int64_t *__restrict__ cmax, int64_t nb) {
+    __shared__ int64_t s_warp[MS_THREADS / 32];
+    int64_t *row = cmax + (int64_t)blockIdx.y * nb;
+    int64_t carry = -1;
+    for (int64_t b0 = 0; b0 < nb; b0 += MS_THREADS) {
+        const int64_t i = b0 + threadIdx.x;
+        const int64_t v = i < nb ? row[i] : -1;
+        int64_t total;
+        int64_t ex = block_excl_max(v, s_warp, &total);
+        if (carry > ex) ex = carry;
+        if (i < nb) row[i] = ex;
+        if (total > carry) carry = total;
+    }
+}
+__global__ void __launch_bounds__(MS_THREADS) k_ms_apply(const int64_t *__restrict__ in, int64_t n, int64_t nb,
+                                                         const int64_t *__restrict__ cmax, int64_t *__restrict__ out) {
+    __shared__ int64_t s_warp[MS_THREADS / 32];
+    const int64_t *row = in + (int64_t)blockIdx.y * n;
+    int64_t *orow = out + (int64_t)blockIdx.y * n;
+    const int64_t base = (int64_t)blockIdx.x * MS_TILE;
+    int64_t carry = cmax[(int64_t)blockIdx.y * nb + blockIdx.x];
+    for (int j = 0; j < MS_ITEMS; j++) {
+        const int64_t i = base + j * MS_THREADS + threadIdx.x;
+        const int64_t v = i < n ? row[i] : -1;
+        int64_t total;
+        int64_t ex = block_excl_max(v, s_warp, &total);
+        if (carry > ex) ex = carry;
+        if (i < n) orow[i] = ex;
+        if (total > carry) carry = total;
+    }
+}
+
+// ---- passes C/D: count, then emit, the kept ORFs of every tile ---------------------------------------------
+// ORF between a lower stop xl and a higher stop xh of one stream (contig offsets; !xl_real = virtual stop at
+// the low end of the contig, !xh_real = virtual stop at the high end).  Residue index of a stop at x:
+// plus (x-cs)/3, minus (L-3-cs-x)/3 (descending in x).
+__device__ __forceinline__ void orf_of(int plus, int64_t L, int cs, int64_t m, int64_t xl, int64_t xh, bool xl_real,
+                                       bool xh_real, int64_t &start, int64_t &len) {
+    if (plus) {
+        const int64_t il = xl_real ? (xl - cs) / 3 : -1;
+        const int64_t ih = xh_real ? (xh - cs) / 3 : m;
+        start = il + 1;
+        len = ih - il - 1;
+    } else {
+        const int64_t il = xl_real ? (L - 3 - cs - xl) / 3 : m;
+        const int64_t ih = xh_real ? (L - 3 - cs - xh) / 3 : -1;
+        start = ih + 1;
+        len = il - ih - 1;
+    }
+}
+
+__device__ __forceinline__ int64_t layout_index(const TileInfo &ti, const int64_t *__restrict__ tile_base, int64_t contig_lo, int s) {
+    // output order: contig, then stream (reference order), then tiles ascending ('+') or descending ('-')
+    return tile_base[ti.c - contig_lo] * 6 + (int64_t)s * ti.Tc + ((s & 1) ? ti.k : ti.Tc - 1 - ti.k);
+}
+
+// Enumerate the ORFs this thread owns in stream s (each ORF belongs to its higher stop).  WRITE == false: count.
+// WRITE == true: k-th kept ORF (ascending position) goes to slot0 + k ('+') or slot0 + (n_mine-1-k) ('-').
+template <bool WRITE>
+__device__ __forceinline__ int enumerate_stream(const TileInfo &ti, const SixMasks &sm, int s, int64_t x0, int64_t prev,
+                                                bool is_end_thread, int64_t min_aa, int64_t slot0, int n_mine,
+                                                mg_orf *__restrict__ recs, int32_t *__restrict__ lens, int64_t *__restrict__ srcs) {
+    if (ti.m[s] <= 0) return 0;                       // `if translated_seq:` (genome.py:832)
+    const int plus = s & 1;
+    const int r = stream_res(s, ti.Lm3);
+    const uint64_t *msk = plus ? sm.pm : sm.mm;
+    int64_t xl = prev;
+    bool xl_real = prev >= 0;
+    int k = 0;
+    for (int g = 0; g <= 3; g++) {
+        uint64_t x = g < 3 ? (msk[g] & res_mask((r - g + 3) % 3)) : (is_end_thread ? 1ull : 0ull);
+        while (x) {
+            const int t = 16 * g + ((__ffsll((long long)x) - 1) >> 2);
+            x &= x - 1;
+            const bool real = g < 3;
+            const int64_t xh = x0 + t;
+            int64_t st, ln;
+            orf_of(plus, ti.L, ti.cs[s], ti.m[s], xl, xh, xl_real, real, st, ln);
+            if (ln >= min_aa) {
+                if (WRITE) {
+                    const int64_t slot = slot0 + (plus ? k : n_mine - 1 - k);
+                    mg_orf o;
+                    o.contig = (int32_t)ti.c; o.frame = (int8_t)(s >> 1); o.minus = (int8_t)(!plus); o.pad = 0;
+                    o.start = st; o.len = ln; o.aa_off = 0;
+                    recs[slot] = o;
+                    lens[slot] = (int32_t)ln;
+                    const int64_t q = ti.cs[s] + 3 * st;            // oriented offset of the ORF's first base
+                    srcs[slot] = plus ? (ti.gb + q) : ((ti.gb + ti.L - q) | (int64_t)(1ull << MG_KIND_SHIFT));
+                }
+                k++;
+            }
+            xl = xh;
+            xl_real = true;
+        }
+    }
+    return k;
+}
+
+__device__ __forceinline__ int64_t warp_incl_sum(int64_t v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ int64_t block_incl_sum(int64_t v, int64_t *s_warp, int64_t *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_incl_sum(v);
+    if (lane == 31) s_warp[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        int64_t w = lane < (SIX_THREADS / 32) ? s_warp[lane] : 0;
+        w = warp_incl_sum(w);
+        if (lane < (SIX_THREADS / 32)) s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int64_t off = wid ? s_warp[wid - 1] : 0;
+    *total = s_warp[SIX_THREADS / 32 - 1];
+    __syncthreads();
+    return v + off;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
+    const uint32_t *__restrict__ packed, const int64_t *__restrict__ tile_base, int64_t nc, int64_t contig_lo,
+    const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
+    const int64_t *__restrict__ m, int64_t n_tiles, const int64_t *__restrict__ carry, int64_t min_aa,
+    int32_t *__restrict__ cnt, const int64_t *__restrict__ cnt_off, mg_orf *__restrict__ recs, int32_t *__restrict__ lens,
+    int64_t *__restrict__ srcs) {
+    __shared__ TileInfo ti;
+    __shared__ int s_cnt[6];
+    __shared__ int64_t s_warp[SIX_THREADS / 32];
+    __shared__ int s_wlast[6][SIX_THREADS / 32];     // per-warp max of `last stop in thread`
+    if (threadIdx.x == 0) tile_info(blockIdx.x, tile_base, nc, contig_lo, contig_len, contig_base, cs, m, ti);
+    if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t tile0 = ti.k * SIX_TILE;
+    const int64_t x0 = tile0 + (int64_t)threadIdx.x * SIX_BPT;
+    const bool active = x0 < ti.L;
+    const bool is_end_thread = active && (x0 + SIX_BPT >= ti.L);       // owns the virtual high-end stops
+    SixMasks sm;
+    if (active) six_masks(packed, ti.gb, ti.L, x0, ti.cs, sm);
+    else { sm.pm[0] = sm.pm[1] = sm.pm[2] = sm.mm[0] = sm.mm[1] = sm.mm[2] = 0; }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+    // previous stop of each stream before this thread: exclusive max over lower threads, else the tile carry
+    int ex_local[6];
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        int first, last;
+        stream_first_last(sm, s, ti.Lm3, first, last);
+        int inc = last < 0 ? -1 : (int)threadIdx.x * SIX_BPT + last;   // tile-local position
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d && t > inc) inc = t;
+        }
+        if (lane == 31) s_wlast[s][wid] = inc;
+        int ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) ex = -1;
+        ex_local[s] = ex;
+    }
+    __syncthreads();
+    int64_t prev[6];
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        int ex = ex_local[s];
+        for (int w = 0; w < wid; w++) ex = max(ex, s_wlast[s][w]);
+        if (ex >= 0) prev[s] = tile0 + ex;            // contig offset
+        else {
+            const int64_t cg = carry[(int64_t)s * n_tiles + blockIdx.x];   // global base index; < gb: other contig
+            prev[s] = (cg >= ti.gb) ? cg - ti.gb : -1;
+        }
+    }
+
+    int my_cnt[6];
+#pragma unroll
+    for (int s = 0; s < 6; s++)
+        my_cnt[s] = active ? enumerate_stream<false>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, 0, 0, nullptr, nullptr, nullptr) : 0;
+
+    if (!EMIT) {
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            int c = my_cnt[s];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+            if (lane == 0 && c) atomicAdd(&s_cnt[s], c);
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) cnt[layout_index(ti, tile_base, contig_lo, threadIdx.x)] = s_cnt[threadIdx.x];
+    } else {
+        // ranks inside the tile: block prefix sums of the per-thread counts, three 21-bit fields per word
+        const int64_t pk0 = (int64_t)my_cnt[0] | ((int64_t)my_cnt[1] << 21) | ((int64_t)my_cnt[2] << 42);
+        const int64_t pk1 = (int64_t)my_cnt[3] | ((int64_t)my_cnt[4] << 21) | ((int64_t)my_cnt[5] << 42);
+        int64_t tot0, tot1;
+        const int64_t in0 = block_incl_sum(pk0, s_warp, &tot0);
+        const int64_t in1 = block_incl_sum(pk1, s_warp, &tot1);
+        if (active) {
+#pragma unroll
+            for (int s = 0; s < 6; s++) {
+                if (my_cnt[s] == 0) continue;
+                const int sh = 21 * (s % 3);
+                const int64_t inc = ((s < 3 ? in0 : in1) >> sh) & 0x1FFFFF;
+                const int64_t tot = ((s < 3 ? tot0 : tot1) >> sh) & 0x1FFFFF;
+                // '+': ascending, my first ORF has rank = exclusive prefix; '-': descending, ranks count from the top
+                const int64_t rank0 = (s & 1) ? inc - my_cnt[s] : tot - inc;
+                const int64_t slot0 = cnt_off[layout_index(ti, tile_base, contig_lo, s)] + rank0;
+                enumerate_stream<true>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, slot0, my_cnt[s], recs, lens, srcs);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_six_fill_off(int64_t n_orf, const int64_t *__restrict__ aa_off, mg_orf *__restrict__ recs) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n_orf) recs[i].aa_off = aa_off[i];
+}
+
+__global__ void __launch_bounds__(256) k_six_tiles(const int64_t *__restrict__ off, int64_t n, int64_t tile_bytes, int64_t n_tile,
+                                                   int64_t *__restrict__ tile_first) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t > n_tile) return;
+    if (t == n_tile) { tile_first[t] = n > 0 ? n - 1 : 0; return; }
+    tile_first[t] = mg_search_le(off, 0, n, t * tile_bytes);
+}
+
+// ---- pass E: residues of the kept ORFs, flat over output bytes (16 per thread) ------------------------------
+__global__ void __launch_bounds__(AA_THREADS) k_six_aa(const uint32_t *__restrict__ packed, const int64_t *__restrict__ aa_off,
+                                                       const int64_t *__restrict__ srcs, int64_t n_orf,
+                                                       const int64_t *__restrict__ tile_first, int64_t total,
+                                                       const uint8_t *__restrict__ aa4096, uint8_t *__restrict__ out) {
+    __shared__ __align__(16) uint8_t s_aa[4096];
+    __shared__ int64_t s_off[AA_CAP + 1];
+    reinterpret_cast<uint4 *>(s_aa)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(aa4096) + threadIdx.x);
+    const int64_t P0 = (int64_t)blockIdx.x * AA_TILE;
+    const int64_t o_lo = tile_first[blockIdx.x];
+    int64_t o_hi = tile_first[blockIdx.x + 1] + 1;
+    if (o_hi > n_orf) o_hi = n_orf;
+    const int ncache = (int)min((int64_t)AA_CAP, o_hi - o_lo);
+    for (int i = threadIdx.x; i <= ncache; i += AA_THREADS) s_off[i] = __ldg(aa_off + o_lo + i);
+    __syncthreads();
+    const int64_t cached_end = s_off[ncache];
+#pragma unroll 1
+    for (int cidx = 0; cidx < AA_TILE / 16 / AA_THREADS; cidx++) {
+        const int64_t P = P0 + ((int64_t)(cidx * AA_THREADS + threadIdx.x) << 4);
+        if (P >= total) break;
+        int64_t o;
+        if (P < cached_end) {
+            int lo = 0, hi = ncache;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid] <= P) lo = mid; else hi = mid;
+            }
+            o = o_lo + lo;
+        } else {
+            o = mg_search_le(aa_off, o_lo + ncache, n_orf, P);
+        }
+        uint64_t blo = 0, bhi = 0;
+        int filled = 0;
+        int64_t pos = P;
+        int64_t off_o = __ldg(aa_off + o), off_n = __ldg(aa_off + o + 1);
+        while (filled < 16 && pos < total) {
+            while (off_n <= pos) { o++; off_o = off_n; off_n = __ldg(aa_off + o + 1); }
+            const int64_t a = pos - off_o;
+            int c = 16 - filled;
+            if (off_n - pos < c) c = (int)(off_n - pos);
+            const uint64_t sk = (uint64_t)__ldg(srcs + o);
+            const int64_t src = (int64_t)(sk & MG_SRC_MASK);
+            uint64_t acc[3] = {0, 0, 0};
+            if ((sk >> MG_KIND_SHIFT) == 0) {
+                const int64_t g0 = src + 3 * a;
+                acc[0] = mg_ld_nib16(packed, g0);
+                if (3 * c > 16) acc[1] = mg_ld_nib16(packed, g0 + 16);
+                if (3 * c > 32) acc[2] = mg_ld_nib16(packed, g0 + 32);
+            } else {
+                const int64_t e = src - 3 * a;               // one past the last (genome) base of the first codon
+                acc[0] = mg_rc_nib16(mg_ld_nib16(packed, e - 16));
+                if (3 * c > 16) acc[1] = mg_rc_nib16(mg_ld_nib16(packed, e - 32));
+                if (3 * c > 32) acc[2] = mg_rc_nib16(mg_ld_nib16(packed, e - 48));
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (k < c) {
+                    const int bit = 12 * k, w = bit >> 6, sh = bit & 63;
+                    uint32_t idx = (uint32_t)(acc[w] >> sh);
+                    if (sh > 52) idx |= (uint32_t)(acc[w + 1] << (64 - sh));
+                    const uint64_t b = s_aa[idx & 0xFFFu];
+                    const int t = filled + k;
+                    if (t < 8) blo |= b << (8 * t); else bhi |= b << (8 * (t - 8));
+                }
+            }
+            filled += c;
+            pos += c;
+        }
+        mg_st16(out + P, (uint32_t)blo, (uint32_t)(blo >> 32), (uint32_t)bhi, (uint32_t)(bhi >> 32));
+    }
+}
+
+// ---- host API -------------------------------------------------------------------------------------------------
+static void six_release(mg_sixframe_state *s) {
+    for (void *d : s->owned) cudaFree(d);
+    s->owned.clear();
+    if (s->d_aa) cudaFree(s->d_aa);
+    s->d_aa = nullptr;
+    s->aa_cap = 0;
+}
+
+void mg_sixframe_free(mg_genome *g) {
+    if (g->six) {
+        six_release(g->six);
+        delete g->six;
+        g->six = nullptr;
+    }
+}
+
+template <typename T>
+static int six_alloc(mg_sixframe_state *s, T **p, int64_t n) {
+    void *d = nullptr;
+    MG_CUDA(cudaMalloc(&d, std::max<int64_t>(1, n) * sizeof(T)));
+    s->owned.push_back(d);
+    *p = (T *)d;
+    return MG_OK;
+}
+
+extern "C" int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig_hi, int64_t min_aa, int64_t *n_orf,
+                                 int64_t *n_bytes, void *stream) {
+    MG_REQUIRE(g != nullptr, "genome handle is NULL");
+    MG_REQUIRE(g->finalized, "mg_genome_finalize has not been called");
+    MG_REQUIRE(contig_lo >= 0 && contig_lo <= contig_hi && contig_hi <= g->n_contigs, "contig range out of bounds");
+    MG_REQUIRE(min_aa >= 0, "min_aa must be >= 0");
+    MG_CUDA(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    mg_sixframe_free(g);
+    mg_sixframe_state *s = new mg_sixframe_state();
+    g->six = s;
+    s->contig_lo = contig_lo;
+    s->contig_hi = contig_hi;
+    s->min_aa = min_aa;
+    const int64_t nc = contig_hi - contig_lo;
+    s->h_tile_base.assign(nc + 1, 0);
+    for (int64_t c = 0; c < nc; c++) {
+        const int64_t L = g->h_contig_len[contig_lo + c];
+        MG_REQUIRE(L < (1ll << 31), "contigs of 2^31 bases or more are not supported by the ORF scan");
+        s->h_tile_base[c + 1] = s->h_tile_base[c] + (L + SIX_TILE - 1) / SIX_TILE;
+    }
+    s->n_tiles = s->h_tile_base[nc];
+    s->n_orf = 0;
+    s->n_bytes = 0;
+    s->counted = true;
+    if (n_orf) *n_orf = 0;
+    if (n_bytes) *n_bytes = 0;
+    if (s->n_tiles == 0) return MG_OK;
+    int rc;
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+    TRY(six_alloc(s, &s->d_tile_base, nc + 1));
+    MG_CUDA(cudaMemcpyAsync(s->d_tile_base, s->h_tile_base.data(), (nc + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    TRY(six_alloc(s, &s->d_cs, nc * 6));
+    TRY(six_alloc(s, &s->d_m, nc * 6));
+    TRY(six_alloc(s, &s->d_tile_last, s->n_tiles * 6));
+    TRY(six_alloc(s, &s->d_carry, s->n_tiles * 6));
+    const int64_t nb = (s->n_tiles + MS_TILE - 1) / MS_TILE;
+    TRY(six_alloc(s, &s->d_chunk, nb * 6));
+    TRY(six_alloc(s, &s->d_cnt, s->n_tiles * 6));
+    TRY(six_alloc(s, &s->d_cnt_off, s->n_tiles * 6 + 1));
+    k_six_streams<<<(unsigned)((nc * 6 + 127) / 128), 128, 0, st>>>(g->d_packed, g->d_contig_len, g->d_contig_base, contig_lo, nc, s->d_cs, s->d_m);
+    MG_LAUNCH_CHECK();
+    k_six_last<<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, contig_lo, g->d_contig_len, g->d_contig_base,
+                                                              s->d_cs, s->d_m, s->n_tiles, s->d_tile_last);
+    MG_LAUNCH_CHECK();
+    k_ms_reduce<<<dim3((unsigned)nb, 6), MS_THREADS, 0, st>>>(s->d_tile_last, s->n_tiles, nb, s->d_chunk);
+    MG_LAUNCH_CHECK();
+    k_ms_chunks<<<dim3(1, 6), MS_THREADS, 0, st>>>(s->d_chunk, nb);
+    MG_LAUNCH_CHECK();
+    k_ms_apply<<<dim3((unsigned)nb, 6), MS_THREADS, 0, st>>>(s->d_tile_last, s->n_tiles, nb, s->d_chunk, s->d_carry);
+    MG_LAUNCH_CHECK();
+    k_six_orfs<false><<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, contig_lo, g->d_contig_len,
+                                                                   g->d_contig_base, s->d_cs, s->d_m, s->n_tiles, s->d_carry, min_aa,
+                                                                   s->d_cnt, nullptr, nullptr, nullptr, nullptr);
+    MG_LAUNCH_CHECK();
+    s->scan_tmp_cap = mg_scan_tmp_elems(s->n_tiles * 6) + 2;
+    TRY(six_alloc(s, &s->d_scan_tmp, s->scan_tmp_cap));
+    TRY(mg_scan_i32(s->d_cnt, s->d_cnt_off, s->n_tiles * 6, s->d_scan_tmp, s->scan_tmp_cap, st));
+    MG_CUDA(cudaMemcpyAsync(&s->n_orf, s->d_cnt_off + s->n_tiles * 6, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MG_CUDA(cudaStreamSynchronize(st));
+    if (s->n_orf > 0) {
+        TRY(six_alloc(s, &s->d_recs, s->n_orf));
+        TRY(six_alloc(s, &s->d_len, s->n_orf));
+        TRY(six_alloc(s, &s->d_src, s->n_orf));
+        TRY(six_alloc(s, &s->d_aa_off, s->n_orf + 1));
+        k_six_orfs<true><<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, contig_lo, g->d_contig_len,
+                                                                      g->d_contig_base, s->d_cs, s->d_m, s->n_tiles, s->d_carry, min_aa,
+                                                                      nullptr, s->d_cnt_off, s->d_recs, s->d_len, s->d_src);
+        MG_LAUNCH_CHECK();
+        const int64_t need = mg_scan_tmp_elems(s->n_orf) + 2;
+        int64_t *tmp = s->d_scan_tmp;
+        if (need > s->scan_tmp_cap) TRY(six_alloc(s, &tmp, need));
+        TRY(mg_scan_i32(s->d_len, s->d_aa_off, s->n_orf, tmp, std::max(need, s->scan_tmp_cap), st));
+        k_six_fill_off<<<(unsigned)((s->n_orf + 255) / 256), 256, 0, st>>>(s->n_orf, s->d_aa_off, s->d_recs);
+        MG_LAUNCH_CHECK();
+        MG_CUDA(cudaMemcpyAsync(&s->n_bytes, s->d_aa_off + s->n_orf, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        MG_CUDA(cudaStreamSynchronize(st));
+        s->n_aa_tile = (s->n_bytes + AA_TILE - 1) / AA_TILE;
+        TRY(six_alloc(s, &s->d_aa_tile, s->n_aa_tile + 1));
+        if (s->n_aa_tile > 0) {
+            k_six_tiles<<<(unsigned)((s->n_aa_tile + 256) / 256), 256, 0, st>>>(s->d_aa_off, s->n_orf, AA_TILE, s->n_aa_tile, s->d_aa_tile);
+            MG_LAUNCH_CHECK();
+        }
+    }
+#undef TRY
+    if (n_orf) *n_orf = s->n_orf;
+    if (n_bytes) *n_bytes = s->n_bytes;
+    return MG_OK;
+}
+
+extern "C" int mg_sixframe_emit_device(mg_genome *g, uint8_t *aa_out_dev, mg_orf *recs_dev, void *stream) {
+    MG_REQUIRE(g != nullptr, "genome handle is NULL");
+    if (!g->six || !g->six->counted) { mg_set_error("mg_sixframe_count has not been called"); return MG_ESTATE; }
+    MG_CUDA(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    mg_sixframe_state *s = g->six;
+    if (aa_out_dev && s->n_bytes > 0) {
+        MG_REQUIRE(((uintptr_t)aa_out_dev & 15) == 0, "aa_out_dev must be 16-byte aligned");
+        k_six_aa<<<(unsigned)s->n_aa_tile, AA_THREADS, 0, st>>>(g->d_packed, s->d_aa_off, s->d_src, s->n_orf, s->d_aa_tile, s->n_bytes,
+                                                                g->d_aa4096, aa_out_dev);
+        MG_LAUNCH_CHECK();
+    }
+    if (recs_dev && s->n_orf > 0)
+        MG_CUDA(cudaMemcpyAsync(recs_dev, s->d_recs, s->n_orf * sizeof(mg_orf), cudaMemcpyDeviceToDevice, st));
+    return MG_OK;
+}
+
+extern "C" int mg_sixframe_emit(mg_genome *g, uint8_t *aa_out_host, mg_orf *recs_host, void *stream) {
+    MG_REQUIRE(g != nullptr, "genome handle is NULL");
+    if (!g->six || !g->six->counted) { mg_set_error("mg_sixframe_count has not been called"); return MG_ESTATE; }
+    MG_CUDA(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    mg_sixframe_state *s = g->six;
+    if (aa_out_host && s->n_bytes > 0) {
+        const int64_t need = (s->n_bytes + 15) / 16 * 16;
+        if (s->aa_cap < need) {
+            if (s->d_aa) MG_CUDA(cudaFree(s->d_aa));
+            s->d_aa = nullptr;
+            s->aa_cap = 0;
+            MG_CUDA(cudaMalloc(&s->d_aa, need));
+            s->aa_cap = need;
+        }
+        int rc = mg_sixframe_emit_device(g, s->d_aa, nullptr, stream);
+        if (rc) return rc;
+        MG_CUDA(cudaMemcpyAsync(aa_out_host, s->d_aa, s->n_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    if (recs_host && s->n_orf > 0)
+        MG_CUDA(cudaMemcpyAsync(recs_host, s->d_recs, s->n_orf * sizeof(mg_orf), cudaMemcpyDeviceToHost, st));
+    MG_CUDA(cudaStreamSynchronize(st));
+    return MG_OK;
+}

@@ -131,8 +131,9 @@ class Flattener(object):
         seg_off = np.asarray(self.rec_seg_off, dtype=np.int64)
         ids = np.asarray(rec_ids, dtype=np.int64)
         valid = ids >= 0
-        lo = np.where(valid, seg_off[np.maximum(ids, 0)], 0)
-        hi = np.where(valid, seg_off[np.maximum(ids, 0) + 1], 0)
+        safe = np.minimum(np.maximum(ids, 0), seg_off.size - 2) if seg_off.size > 1 else np.zeros_like(ids)
+        lo = np.where(valid, seg_off[safe], 0)
+        hi = np.where(valid, seg_off[np.minimum(safe + 1, seg_off.size - 1)], 0)
         cnt = hi - lo
         rec_seg_off = np.concatenate(([0], np.cumsum(cnt)))
         total = int(rec_seg_off[-1])
@@ -160,7 +161,7 @@ class Flattener(object):
         lit = np.frombuffer(b"".join(lit_parts), dtype=np.uint8) if o else np.zeros(0, dtype=np.uint8)
         return engine.RecordTable(rec_seg_off, sc[src] if total else sc[:0], ss[src] if total else ss[:0],
                                   se[src] if total else se[:0], st[src] if total else st[:0], lit_off, pre_len,
-                                  suf_len, lit, np.where(valid, ph[np.maximum(ids, 0)] if ph.size else 0, 0).astype(np.int8))
+                                  suf_len, lit, np.where(valid, ph[safe] if ph.size else 0, 0).astype(np.int8))
 
     def run(self, seq_type):
         if seq_type not in ("nucleotide", "protein"):
