@@ -1,0 +1,509 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config.workload): synthetic 3.1 Gbp human-scale genome (24 chromosomes + 170 scaffolds,
+5 % N, 50 % soft-masked) resident on the GPU as 0.5 B/base, and a GTF-shaped annotation of 200k
+transcripts per GPU (weak scaling: every rank owns its own 200k-transcript batch over a replicated
+genome; the path has no cross-shard exchange, so there is no collective on the data path).
+One STEP = one pass of the hot path over one batch, producing all three products of config 4:
+CDS nucleotide FASTA, CDS protein FASTA, exon-based transcript FASTA (K1 clamp+scan, K2 splice+RC,
+K3 translate, FASTA framing on the device).
+metric  spliced+translated Gbp/s = (CDS bp spliced + CDS bp translated + exon bp spliced) / time.
+value   device-resident: interval tables already in HBM, outputs left in HBM (CUDA events).
+e2e     through the C ABI with HOST buffers: pinned SoA tables -> H2D -> kernels -> D2H of the three
+        texts into pinned memory, every step.
+The reference arm (--impl reference) times the reference's own Python get_fasta (oracle/_ref, the shimmed
+reference; else the oracle port) on the host cores on a bounded sample of the same workload shape.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GENOME_BP = int(os.environ.get("MAGOT_BENCH_GENOME_BP", 3_100_000_000))
+N_TX = int(os.environ.get("MAGOT_BENCH_TX", 200_000))
+SAMPLE_BP = int(os.environ.get("MAGOT_BENCH_SAMPLE_BP", 20_000_000))
+SAMPLE_TX = int(os.environ.get("MAGOT_BENCH_SAMPLE_TX", 1290))
+SEED = 4
+METRIC = "spliced+translated Gbp/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "MEASURED_PEAKS.json (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU legs (rank 0 only): the reference's own code on a bounded sample
+# ------------------------------------------------------------------------------------------------------
+def build_sample():
+    """Scaled twin of the workload (same generators): host genome + annotation + GTF text."""
+    from magot_b200 import synth
+    layout = synth.contig_layout("human", SAMPLE_BP, SEED)
+    contigs = synth.synth_genome_host(layout, SEED)
+    ann = synth.synth_annotation(layout, SAMPLE_TX, SEED)
+    return layout, contigs, ann
+
+
+def _sample_bp(ann):
+    return 2 * ann.spliced_bp("cds") + ann.spliced_bp("exon")
+
+
+_REF_STATE = {}
+
+
+def _ref_worker(args):
+    which, seq_type, keys = args
+    g = _REF_STATE[which]
+    n = 0
+    for k in keys:
+        n += len(g.annotations.gene[k].get_fasta(seq_type=seq_type))
+    return n
+
+
+def reference_setup(layout, contigs, ann):
+    """Build the reference's (or the port's) objects for the sample. Returns (kind, run_step(pool) -> bytes)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    names = [n for n, _ in layout]
+    fasta = "".join(">%s\n%s\n" % (n, c.tobytes().decode("latin-1")) for n, c in zip(names, contigs))
+    try:
+        import ref_runner
+        ref = ref_runner.ref()
+    except Exception:
+        ref = None
+    if ref is not None:
+        kind = "reference"
+        # The reference's own classes, populated directly (what its read_gff builds for a GTF: gene ->
+        # transcript -> CDS|exon); read_gff itself costs ~1 ms/line in the reference and is not the timed path.
+        for which in ("cds", "exon"):
+            gs = ref.GenomeSequence(fasta)
+            g = ref.Genome(gs)
+            aset = ref.AnnotationSet()
+            aset.genome = g
+            g.annotations = aset
+            off, st, en = (ann.cds_off, ann.cds_start, ann.cds_end) if which == "cds" else (ann.exon_off, ann.exon_start, ann.exon_end)
+            ftype = "CDS" if which == "cds" else "exon"
+            if ftype not in aset.__dict__:
+                aset.__dict__[ftype] = {}
+            for t in range(ann.n_tx):
+                tx = ann.names[t]
+                gid = "g%d" % ann.gene_of[t]
+                ctg = names[ann.contig[t]]
+                sd = "-" if ann.strand[t] else "+"
+                if gid not in aset.gene:
+                    aset.gene[gid] = ref.ParentAnnotation(gid, ctg, "gene", [], None, sd, aset)
+                aset.gene[gid].child_list.append(tx)
+                kids = []
+                for k in range(off[t], off[t + 1]):
+                    cid = "%s-%s%d" % (tx, ftype, k - off[t])
+                    kids.append(cid)
+                    aset.__dict__[ftype][cid] = ref.BaseAnnotation(cid, ctg, (int(st[k]), int(en[k])), ftype, tx, sd, {}, aset)
+                aset.transcript[tx] = ref.ParentAnnotation(tx, ctg, "transcript", kids, gid, sd, aset)
+            _REF_STATE[which] = g
+        keys = list(_REF_STATE["cds"].annotations.gene)
+    else:
+        kind = "port"
+        import magot_oracle as mo
+        gtf = ann.to_gtf(names)
+        seqs, _ = mo.read_fasta(fasta)
+
+        class _G(object):
+            pass
+        for which, kw in (("cds", {}), ("exon", {"base_features": ('exon', 'match_part', 'similarity', 'region'), "features_to_ignore": ('CDS',)})):
+            aset = mo.read_gff(gtf, **kw)
+            aset.genome = seqs
+            g = _G()
+            g.annotations = _G()
+
+            class _Wrap(object):
+                def __init__(self, o):
+                    self.o = o
+
+                def get_fasta(self, seq_type="nucleotide"):
+                    return mo.parent_get_fasta(self.o, seq_type=seq_type)
+            g.annotations.gene = {k: _Wrap(v) for k, v in aset.table('gene').items()}
+            _REF_STATE[which] = g
+        keys = list(_REF_STATE["cds"].annotations.gene)
+    return kind, keys
+
+
+def reference_step(pool, keys, workers):
+    tasks = []
+    for which, seq_type in (("cds", "nucleotide"), ("cds", "protein"), ("exon", "nucleotide")):
+        chunk = max(1, (len(keys) + workers * 4 - 1) // (workers * 4))
+        for i in range(0, len(keys), chunk):
+            tasks.append((which, seq_type, keys[i:i + chunk]))
+    if pool is None:
+        return sum(_ref_worker(t) for t in tasks)
+    return sum(pool.map(_ref_worker, tasks))
+
+
+def cpu_reference_rate(steps, warmup, workers):
+    """Gbp/s of the reference's get_fasta path on the sample with `workers` processes."""
+    import multiprocessing as mp
+    layout, contigs, ann = build_sample()
+    kind, keys = reference_setup(layout, contigs, ann)
+    bp = _sample_bp(ann)
+    pool = mp.get_context("fork").Pool(workers) if workers > 1 else None
+    try:
+        for _ in range(warmup):
+            reference_step(pool, keys, workers)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            reference_step(pool, keys, workers)
+        dt = (time.perf_counter() - t0) / max(steps, 1)
+    finally:
+        if pool is not None:
+            pool.terminate()
+    sample = "config-4 generators at 1/%d scale: %d bp genome, %d transcripts, CDS nuc + CDS protein + exon transcripts via get_fasta (%s, CPython %d.%d; Python 2.7 is not available)" % (
+        max(1, GENOME_BP // SAMPLE_BP), SAMPLE_BP, ann.n_tx, "shimmed reference oracle/_ref" if kind == "reference" else "oracle port", sys.version_info[0], sys.version_info[1])
+    return bp / dt / 1e9, dt, kind, sample
+
+
+def cpu_port_rate():
+    """Single-threaded C restatement (oracle/oracle.c) on a larger sample: tight-loop CPU figure."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import coracle
+    from magot_b200 import synth
+    layout = synth.contig_layout("human", 60_000_000, SEED)
+    contigs = synth.synth_genome_host(layout, SEED)
+    ann = synth.synth_annotation(layout, 20_000, SEED)
+    lens = np.array([a.size for a in contigs])
+    raw = [a.tobytes() for a in contigs]
+    t0 = time.perf_counter()
+    bp = 0
+    for which in ("cds", "exon"):
+        tbl = ann.table(which, framing=False)
+        lo = np.clip(tbl.seg_start - 1, 0, lens[tbl.seg_contig])
+        hi = np.clip(tbl.seg_end, 0, lens[tbl.seg_contig])
+        nuc, off = coracle.splice(raw, tbl.rec_seg_off, tbl.seg_contig, lo, hi, tbl.seg_strand)
+        bp += nuc.size
+        if which == "cds":
+            coracle.splice_translate(nuc, off)
+            bp += nuc.size
+    dt = time.perf_counter() - t0
+    return bp / dt / 1e9
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import numpy as np
+    import torch
+    from magot_b200 import _lib, engine, synth
+    lib = _lib.lib
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.require_device(local)
+    stream = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+
+    # ---- resident genome: synthesised on the device (torch, plumbing) and packed by K0
+    t_setup = time.perf_counter()
+    layout = synth.contig_layout("human", GENOME_BP, SEED)
+    g = engine.DeviceGenome([l for _, l in layout], device=local)
+    t_pack = 0.0
+    CH = 256 << 20
+    for ci, (_, L) in enumerate(layout):
+        for off in range(0, L, CH):
+            n = min(CH, L - off)
+            a = synth.synth_contig_device(n, SEED * 1000003 + ci * 64 + off // CH, dev)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            g.pack_device(ci, a.data_ptr(), n, offset=off, stream=sp)
+            torch.cuda.synchronize()
+            t_pack += time.perf_counter() - t0
+            del a
+    g.finalize()
+    torch.cuda.empty_cache()
+
+    # ---- this rank's batch: 200k transcripts (weak scaling: a different batch per rank)
+    ann = synth.synth_annotation(layout, N_TX, SEED + 1000 * rank)
+    tables = {"cds": ann.table("cds"), "exon": ann.table("exon")}
+    S_cds, S_exon = ann.spliced_bp("cds"), ann.spliced_bp("exon")
+    bp_step = 2 * S_cds + S_exon
+    setup_s = time.perf_counter() - t_setup
+
+    # pinned copies of the host tables for the e2e path
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t
+    pinned = {}
+    for k, t in tables.items():
+        pinned[k] = {f: pin(getattr(t, f)) for f in ("rec_seg_off", "seg_contig", "seg_start", "seg_end", "seg_strand", "rec_lit_off",
+                                                       "rec_pre_len", "rec_suf_len", "lit")}
+
+    def P(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def create_plan(k):
+        p = pinned[k]
+        h = ctypes.c_void_p()
+        _lib.check(lib.mg_plan_create(g.handle, tables[k].n_rec, P(p["rec_seg_off"]), tables[k].n_seg, P(p["seg_contig"]), P(p["seg_start"]),
+                                      P(p["seg_end"]), P(p["seg_strand"]), P(p["rec_lit_off"]), P(p["rec_pre_len"]), P(p["rec_suf_len"]),
+                                      P(p["lit"]), p["lit"].numel(), None, sp, ctypes.byref(h)))
+        return h
+
+    def prepare(h):
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.check(lib.mg_plan_prepare(h, _lib.MG_PROT_TRIMX, ctypes.byref(a), ctypes.byref(b), sp))
+        return a.value, b.value
+
+    h2d_bytes = sum(t.numel() * t.element_size() for k in pinned for t in pinned[k].values())
+
+    # ---- device-resident plans + output buffers
+    plans = {k: create_plan(k) for k in tables}
+    sizes = {k: prepare(plans[k]) for k in tables}
+    out_cds_n = torch.empty((sizes["cds"][0] + 15) // 16 * 16, dtype=torch.uint8, device=dev)
+    out_cds_p = torch.empty((sizes["cds"][1] + 15) // 16 * 16, dtype=torch.uint8, device=dev)
+    out_exon_n = torch.empty((sizes["exon"][0] + 15) // 16 * 16, dtype=torch.uint8, device=dev)
+    d2h_bytes = sizes["cds"][0] + sizes["cds"][1] + sizes["exon"][0]
+    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
+    nuc_events = []
+
+    def device_step(record):
+        prepare(plans["cds"])
+        e0, e1 = ev(), ev()
+        e0.record(stream)
+        _lib.check(lib.mg_emit_nuc_device(plans["cds"], P(out_cds_n), sp))
+        e1.record(stream)
+        _lib.check(lib.mg_emit_prot_device(plans["cds"], P(out_cds_p), sp))
+        prepare(plans["exon"])
+        e2, e3 = ev(), ev()
+        e2.record(stream)
+        _lib.check(lib.mg_emit_nuc_device(plans["exon"], P(out_exon_n), sp))
+        e3.record(stream)
+        if record:
+            nuc_events.append((e0, e1, e2, e3))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step(False)
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    l0 = lib.mg_kernel_launches()
+    s_ev, e_ev = ev(), ev()
+    s_ev.record(stream)
+    for _ in range(args.steps):
+        device_step(True)
+    e_ev.record(stream)
+    barrier()
+    launches = lib.mg_kernel_launches() - l0
+    dev_ms = s_ev.elapsed_time(e_ev) / args.steps
+    nuc_ms_cds = sum(a.elapsed_time(b) for a, b, _, _ in nuc_events) / len(nuc_events)
+    nuc_ms_exon = sum(c.elapsed_time(d) for _, _, c, d in nuc_events) / len(nuc_events)
+
+    # ---- end to end through the C ABI with host buffers
+    host_cds_n = torch.empty(sizes["cds"][0], dtype=torch.uint8, pin_memory=True)
+    host_cds_p = torch.empty(sizes["cds"][1], dtype=torch.uint8, pin_memory=True)
+    host_exon_n = torch.empty(sizes["exon"][0], dtype=torch.uint8, pin_memory=True)
+
+    def e2e_step():
+        hc = create_plan("cds")
+        prepare(hc)
+        _lib.check(lib.mg_emit_nuc_host(hc, P(host_cds_n), sp))
+        _lib.check(lib.mg_emit_prot_host(hc, P(host_cds_p), sp))
+        he = create_plan("exon")
+        prepare(he)
+        _lib.check(lib.mg_emit_nuc_host(he, P(host_exon_n), sp))
+        _lib.check(lib.mg_stream_sync(local, sp))
+        lib.mg_plan_destroy(hc)
+        lib.mg_plan_destroy(he)
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    s2, e2 = ev(), ev()
+    s2.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    e2.record(stream)
+    barrier()
+    e2e_ms = max(s2.elapsed_time(e2), (time.perf_counter() - t0) * 1e3) / args.steps
+    clk = clocks.stop()
+
+    # max over ranks
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_ms, nuc_ms_cds, nuc_ms_exon], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms, nuc_ms_cds, nuc_ms_exon = [float(x) for x in t.tolist()]
+        tot = torch.tensor([bp_step, h2d_bytes, d2h_bytes, launches], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        bp_all, h2d_all, d2h_all, launches_all = [float(x) for x in tot.tolist()]
+    else:
+        bp_all, h2d_all, d2h_all, launches_all = bp_step, h2d_bytes, d2h_bytes, launches
+
+    # ---- roofline of the dominant kernel (k_emit_nuc), per launch, from this rank's tables
+    peak, peak_src = peaks()
+
+    def alg_bytes(S, tbl, total_text):
+        # S*0.5 (packed read) + text written + 14 B/segment + 8 B/record (+ literal bytes read)
+        return S * 0.5 + total_text + tbl.n_seg * 14 + tbl.n_rec * 8 + tbl.lit.size
+    ab_cds = alg_bytes(S_cds, tables["cds"], sizes["cds"][0])
+    ab_exon = alg_bytes(S_exon, tables["exon"], sizes["exon"][0])
+    ach = (ab_cds + ab_exon) / ((nuc_ms_cds + nuc_ms_exon) * 1e-3) / 1e9
+    roofline = {"kernel": "k_emit_nuc (K2 splice + per-segment RC + FASTA framing)", "bound": "hbm", "achieved": round(ach, 1),
+                "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac_of_nominal_8TBs": round(ach / 8000.0, 4),
+                "launches_per_step": 2, "avg_launch_ms": round((nuc_ms_cds + nuc_ms_exon) / 2, 4),
+                "algorithmic_bytes_per_launch": int((ab_cds + ab_exon) / 2),
+                "per_launch": {"cds": {"ms": round(nuc_ms_cds, 4), "GBps": round(ab_cds / nuc_ms_cds / 1e6, 1)},
+                               "exon": {"ms": round(nuc_ms_exon, 4), "GBps": round(ab_exon / nuc_ms_exon / 1e6, 1)}}}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                v, dt, kind, sample = cpu_reference_rate(1, 0, 1)
+                cpu = {"value": v, "unit": "Gbp/s", "cores": 1, "kind": kind, "sample": sample, "seconds": round(dt, 2),
+                       "host_cpus": os.cpu_count()}
+                try:
+                    cpu["c_port_single_thread_Gbps"] = round(cpu_port_rate(), 4)
+                except Exception as e:      # the C port is extra information only
+                    cpu["c_port_error"] = str(e)[:200]
+            except Exception as e:
+                cpu = {"value": None, "unit": "Gbp/s", "cores": 1, "kind": "port", "sample": "failed: %s" % str(e)[:300]}
+        line = {
+            "metric": METRIC, "value": bp_all / (dev_ms * 1e-3) / 1e9, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "config 4: synthetic %.2f Gbp human-scale genome (replicated per GPU, 0.5 B/base resident) + %d-transcript GTF-shaped batch per GPU; products: CDS nucleotide FASTA + CDS protein FASTA + exon-based transcript FASTA" % (GENOME_BP / 1e9, N_TX),
+                       "genome_bp": GENOME_BP, "transcripts_per_gpu": N_TX, "cds_segments": int(tables["cds"].n_seg),
+                       "exons": int(tables["exon"].n_seg), "spliced_cds_bp": S_cds, "spliced_exon_bp": S_exon,
+                       "bp_per_step_per_gpu": bp_step, "parallelism": "transcript batches per GPU, genome replicated, no collective",
+                       "l2": "no flush: each step streams ~%.1f GB of distinct output + genome lines, far above the 126 MB L2" % ((d2h_bytes + 0.5 * bp_step) / 1e9),
+                       "genome_device_bytes": int(g.device_bytes()), "pack_s": round(t_pack, 3), "setup_s": round(setup_s, 1)},
+            "clocks": clk,
+            "e2e": {"value": bp_all / (e2e_ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all)},
+            "gpu_launches": int(launches_all),
+            "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+    for h in plans.values():
+        lib.mg_plan_destroy(h)
+    g.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    workers = max(1, min(os.cpu_count() or 1, 32))
+    v, dt, kind, sample = cpu_reference_rate(max(args.steps, 1), min(args.warmup, 1), workers)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "config 4 (bounded sample): each step = the reference's get_fasta over the sample, all host cores"},
+            "cpu_baseline": {"value": v, "unit": "Gbp/s", "cores": workers, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="magot_b200", choices=["magot_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

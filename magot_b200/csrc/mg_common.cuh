@@ -105,6 +105,9 @@ struct mg_plan {
     int64_t *d_nuc_tile = nullptr;            // first piece of each nucleotide tile
     int64_t *d_prot_tile = nullptr;           // first record of each protein tile
     int64_t n_nuc_tile = 0, n_prot_tile = 0;
+    int64_t *d_tile_buf = nullptr;
+    int64_t tile_cap = 0;
+    cudaStream_t last_stream = 0;             // frees are ordered after the last use on this stream
     int64_t *d_scan_tmp = nullptr;            // block sums for scans
     int64_t scan_tmp_cap = 0;
     int64_t nuc_total = -1, prot_total = -1;

@@ -160,6 +160,7 @@ extern "C" int mg_plan_create(mg_genome *g, int64_t n_rec, const int64_t *rec_se
     p->n_seg = n_seg;
     p->n_piece = n_seg + 2 * n_rec;
     p->n_lit = n_lit;
+    p->last_stream = st;
     int rc = MG_OK;
 #define TRY(x) do { rc = (x); if (rc) { mg_plan_destroy(p); return rc; } } while (0)
     TRY(upload(p, &p->d_rec_seg_off, rec_seg_off, n_rec + 1, st));
@@ -170,7 +171,15 @@ extern "C" int mg_plan_create(mg_genome *g, int64_t n_rec, const int64_t *rec_se
     TRY(upload(p, &p->d_rec_lit_off, rec_lit_off, n_rec, st));
     TRY(upload(p, &p->d_rec_pre, rec_pre_len, n_rec, st));
     TRY(upload(p, &p->d_rec_suf, rec_suf_len, n_rec, st));
-    TRY(upload(p, &p->d_lit, lit, n_lit, st));
+    {   // literal bytes sit 16 bytes into a zeroed, padded buffer: the emit kernels fetch 16-byte windows that
+        // may start up to 15 bytes before / end up to 19 bytes after the literal they need
+        uint8_t *d = nullptr;
+        TRY(dalloc(p, &d, n_lit + 64, st));
+        rc = cudaMemsetAsync(d, 0, n_lit + 64, st) == cudaSuccess ? MG_OK : MG_ECUDA;
+        if (rc == MG_OK && n_lit > 0 && cudaMemcpyAsync(d + 16, lit, n_lit, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = MG_ECUDA;
+        if (rc) { mg_set_error("literal upload failed"); mg_plan_destroy(p); return rc; }
+        p->d_lit = d + 16;
+    }
     if (rec_phase) TRY(upload(p, &p->d_rec_phase, rec_phase, n_rec, st));
     TRY(dalloc(p, &p->d_piece_len, p->n_piece, st));
     TRY(dalloc(p, &p->d_piece_src, p->n_piece, st));
@@ -189,8 +198,8 @@ extern "C" int mg_plan_create(mg_genome *g, int64_t n_rec, const int64_t *rec_se
 extern "C" int mg_plan_destroy(mg_plan *p) {
     if (!p) return MG_OK;
     cudaSetDevice(p->device);
-    for (void *d : p->owned) cudaFreeAsync(d, 0);
-    if (p->d_out) cudaFreeAsync(p->d_out, 0);
+    for (void *d : p->owned) cudaFreeAsync(d, p->last_stream);
+    if (p->d_out) cudaFreeAsync(p->d_out, p->last_stream);
     delete p;
     return MG_OK;
 }
@@ -201,6 +210,7 @@ extern "C" int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, i
     cudaStream_t st = (cudaStream_t)stream;
     mg_genome *g = p->g;
     p->prot_flags = prot_flags;
+    p->last_stream = st;
     int64_t totals[2] = {0, 0};
     if (p->n_rec > 0) {
         k_plan_pieces<<<(unsigned)((p->n_piece + 255) / 256), 256, 0, st>>>(
@@ -225,13 +235,16 @@ extern "C" int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, i
     // tile -> first piece / first record (removes every global binary search from the emit kernels)
     p->n_nuc_tile = (p->nuc_total + MG_NUC_TILE - 1) / MG_NUC_TILE;
     p->n_prot_tile = (p->prot_total + MG_PROT_TILE - 1) / MG_PROT_TILE;
-    {
+    const int64_t tile_need = p->n_nuc_tile + 1 + p->n_prot_tile + 1;
+    if (tile_need > p->tile_cap) {                   // re-used when the same plan is prepared again
         void *d = nullptr;
-        MG_CUDA(cudaMallocAsync(&d, (p->n_nuc_tile + 1 + p->n_prot_tile + 1) * sizeof(int64_t), st));
+        MG_CUDA(cudaMallocAsync(&d, tile_need * sizeof(int64_t), st));
         p->owned.push_back(d);
-        p->d_nuc_tile = (int64_t *)d;
-        p->d_prot_tile = p->d_nuc_tile + p->n_nuc_tile + 1;
+        p->d_tile_buf = (int64_t *)d;
+        p->tile_cap = tile_need;
     }
+    p->d_nuc_tile = p->d_tile_buf;
+    p->d_prot_tile = p->d_tile_buf + p->n_nuc_tile + 1;
     if (p->n_nuc_tile > 0) {
         k_plan_tiles<<<(unsigned)((p->n_nuc_tile + 256) / 256), 256, 0, st>>>(p->d_piece_off, p->n_piece, MG_NUC_TILE,
                                                                               p->n_nuc_tile, p->d_nuc_tile);
