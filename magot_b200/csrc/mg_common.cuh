@@ -8,7 +8,14 @@
 //               reverse complement (genome.py:784-793) three register ops per 8 bases.
 //   contigs are laid back to back in one global base index space; contig c starts at contig_base[c],
 //   a multiple of 32 bases (16 bytes); index 0..31 is front padding so that a 16-base window that
-//   ENDS at the first base of the genome can still be loaded with non-negative addresses.
+//   starts a little before the first base of the genome can still be loaded with non-negative addresses.
+//   TWO PLANES: indices [0, T) hold the forward strand, indices [T, 2T) hold the reverse complement of
+//   the whole index space (base g of the forward plane is base 2T-1-g of the reverse plane, complemented
+//   in code space, codes 11..15 already turned into 'n' as Sequence.reverse_compliment does).  A '-' strand
+//   interval is therefore a plain FORWARD read of the second plane: the kernels never branch on strand
+//   and never reverse in registers.  This doubles the resident footprint to 1 B/base (3.1 GB for a human
+//   genome on a 180 GB part) and leaves the HBM traffic per spliced base at 0.5 B; the round-1 ncu profile
+//   showed the emit kernels issue-bound, not bandwidth-bound, which is what this trade buys back.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -59,9 +66,9 @@ struct mg_sixframe_state;
 struct mg_genome {
     int device = 0;
     int64_t n_contigs = 0;
-    int64_t total_bases = 0;                  // padded global index space (incl. front pad)
+    int64_t total_bases = 0;                  // T: padded global index space of ONE plane (incl. front pad)
     std::vector<int64_t> h_contig_len, h_contig_base;
-    uint32_t *d_packed = nullptr;             // total_bases/8 + MG_TAIL_WORDS words
+    uint32_t *d_packed = nullptr;             // 2*total_bases/8 + MG_TAIL_WORDS words (forward plane, reverse plane)
     int64_t *d_contig_len = nullptr, *d_contig_base = nullptr;
     // exceptions, unsorted while packing (device), sorted after finalize
     int64_t *d_exc_pos = nullptr;

@@ -11,33 +11,39 @@
 // Algorithmic HBM bytes: K2 = 0.5 B/base packed read + 1 B/base text written (+ tables);
 // K3 = 0.5 B/base read + 1/3 B/base written.  No dense contraction exists -> no tensor cores.
 //
-// Round-1 ncu finding (profiles/r1a_*): the first version of these kernels was issue-bound (~520 / ~1900
-// warp instructions per 32 chunks, 18 of 32 lanes active), not HBM-bound.  This version therefore
-//   * stages the tile's piece table in shared memory in TILE-RELATIVE 32-bit form, with one 64-bit
-//     "base" per piece chosen so that  source index = base +/- (position in tile):  a chunk loads the 16
-//     nibbles that are ALREADY ALIGNED with its 16 output positions and only masks them -- no per-piece
-//     shifting, no 64-bit offset arithmetic in the inner loop;
-//   * replaces the per-chunk binary search by a 64-byte-unit -> piece lookup table built per tile;
-//   * copies literal bytes (FASTA headers) with 5 aligned word loads + funnel shifts instead of byte loops;
-//   * patches bytes outside the packed alphabet (code 15) in a rare tail path.
+// How the kernels got here (ncu evidence under profiles/):
+//   r1a  first version: 16 bytes/thread, per-chunk binary search, per-piece shifting, reverse complement in
+//        registers.  Issue-bound: ~520 (K2) / ~1900 (K3) warp instructions per 32 chunks, 17 of 32 lanes
+//        active, DRAM at 20 % -- nowhere near the HBM roofline the algorithm allows.
+//   r1b  tile-relative 32-bit tables in shared memory, position-aligned loads, 64-byte-unit lookup table:
+//        ~370 instructions per 32 chunks; what was left was divergence (second piece of a chunk executed by
+//        2 lanes, literal bytes by 1 lane) and the strand branch.
+//   r1c  (this file) * the genome keeps a second, reverse-complemented plane, so a '-' interval is a plain
+//        forward read: no strand branch, no register reversal (mg_common.cuh);
+//        * per tile, the GENOME pieces are compacted into shared memory (literal pieces and clamped-away
+//          empty ones dropped) so the first two pieces of every chunk are handled branch-free by all lanes;
+//          a third piece in 16 bytes is rare and takes a loop;
+//        * literal bytes (">ID\n", "\n") are not touched here at all: a tiny second kernel writes them
+//          afterwards, one thread per record.
 #include <algorithm>
 #include "mg_common.cuh"
 #include "mg_gather.cuh"
 
 #define NUC_THREADS 256
 #define NUC_CHUNKS (MG_NUC_TILE / 16 / NUC_THREADS)     // 4 chunks of 16 B per thread
-#define NUC_CAP 1024                                     // pieces cached in shared memory per tile
+#define NUC_PPT 4                                        // raw pieces examined per thread while staging
+#define NUC_CAP (NUC_THREADS * NUC_PPT)                  // raw pieces staged per tile
 #define NUC_UNITS (MG_NUC_TILE / 64)
 
 #define PROT_THREADS 256
 #define PROT_CHUNKS (MG_PROT_TILE / 16 / PROT_THREADS)  // 2
-#define PROT_RCAP 256                                    // records cached per tile
-#define PROT_PCAP 1536                                   // pieces cached per tile
+#define PROT_RPT 2
+#define PROT_RCAP (PROT_THREADS * PROT_RPT)              // records staged per tile
+#define PROT_PPT 6
+#define PROT_PCAP (PROT_THREADS * PROT_PPT)              // raw pieces staged per tile
 #define PROT_UNITS (MG_PROT_TILE / 64)
 
-#define KIND_FWD 0
-#define KIND_RC 1
-#define KIND_LIT 2
+#define BIG 0x7fffffff
 
 // expand the low 4 bits of x into a byte mask (bit k -> byte k = 0xFF)
 __device__ __forceinline__ uint32_t expand4(uint32_t x) {
@@ -49,43 +55,53 @@ __device__ __forceinline__ uint64_t nib_range_mask(int lo, int hi) {
     return ((~0ull) >> (64 - 4 * (hi - lo))) << (4 * lo);
 }
 
-// 16 bytes starting at byte index a of `lit` (a may be unaligned; the buffer is padded on both sides)
-__device__ __forceinline__ void ld_lit16(const uint8_t *__restrict__ lit, int64_t a, uint32_t w[4]) {
-    const uint32_t *p = reinterpret_cast<const uint32_t *>(lit) + (a >> 2);
-    const uint32_t sh = ((uint32_t)a & 3u) << 3;
-    const uint32_t x0 = __ldg(p), x1 = __ldg(p + 1), x2 = __ldg(p + 2), x3 = __ldg(p + 3), x4 = __ldg(p + 4);
-    w[0] = __funnelshift_r(x0, x1, sh);
-    w[1] = __funnelshift_r(x1, x2, sh);
-    w[2] = __funnelshift_r(x2, x3, sh);
-    w[3] = __funnelshift_r(x3, x4, sh);
+// exclusive prefix sum of one int per thread across a 256-thread block; *total = block sum
+__device__ __forceinline__ int block_excl_scan256(int v, int *s_warp, int *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < 8 ? s_warp[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += t;
+        }
+        if (lane < 8) s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int off = wid ? s_warp[wid - 1] : 0;
+    *total = s_warp[7];
+    __syncthreads();
+    return off + inc - v;
 }
 
 // ---- generic (slow, always correct) chunk assembly straight from global memory ------------------------------
-// Used for tiles whose piece list does not fit the shared-memory cache (thousands of tiny pieces per 16 KB).
+// Used for tiles whose piece list does not fit the shared-memory staging (thousands of tiny pieces per tile).
+// Writes genome bytes only; literal positions are left to k_emit_lit like in the fast path.
 __device__ __noinline__ void nuc_chunk_generic(const uint32_t *__restrict__ packed, const int64_t *__restrict__ piece_off,
-                                               const int64_t *__restrict__ piece_src, int64_t n_piece, int64_t j, int64_t P,
-                                               int64_t total, const uint8_t *__restrict__ lit, const int64_t *__restrict__ exc_pos,
-                                               const uint8_t *__restrict__ exc_byte, int64_t n_exc, uint8_t *__restrict__ out) {
+                                               const int64_t *__restrict__ piece_src, int64_t j, int64_t P, int64_t total,
+                                               int64_t T, const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte,
+                                               int64_t n_exc, uint8_t *__restrict__ out) {
     uint32_t w[4] = {0, 0, 0, 0};
     int64_t off_j = __ldg(piece_off + j), off_n = __ldg(piece_off + j + 1);
     for (int t = 0; t < 16 && P + t < total; t++) {
         const int64_t pos = P + t;
         while (off_n <= pos) { j++; off_j = off_n; off_n = __ldg(piece_off + j + 1); }
         const uint64_t sk = (uint64_t)__ldg(piece_src + j);
-        const uint64_t kind = sk >> MG_KIND_SHIFT;
-        const int64_t src = (int64_t)(sk & MG_SRC_MASK), o = pos - off_j;
-        uint32_t b;
-        if (kind == MG_KIND_LIT) {
-            b = __ldg(lit + src + o);
-        } else {
-            const int64_t gi = kind == MG_KIND_FWD ? src + o : src + (off_n - off_j) - 1 - o;
-            uint32_t code = (__ldg(packed + (gi >> 3)) >> (((uint32_t)gi & 7u) * 4)) & 15u;
-            if (kind == MG_KIND_RC) code = code < 8 ? (code ^ 3u) : (code > 10 ? 9u : code);
-            uint32_t d0, d1;
-            mg_decode8(code, d0, d1);
-            b = d0 & 0xFFu;
-            if (code == MG_CODE_EXC) b = mg_exc_byte(exc_pos, exc_byte, n_exc, gi);
-        }
+        if ((sk >> MG_KIND_SHIFT) == MG_KIND_LIT) continue;
+        const int64_t gi = (int64_t)(sk & MG_SRC_MASK) + (pos - off_j);
+        const uint32_t code = (__ldg(packed + (gi >> 3)) >> (((uint32_t)gi & 7u) * 4)) & 15u;
+        uint32_t d0, d1;
+        mg_decode8(code, d0, d1);
+        uint32_t b = d0 & 0xFFu;
+        if (code == MG_CODE_EXC && gi < T) b = mg_exc_byte(exc_pos, exc_byte, n_exc, gi);
         w[t >> 2] |= b << ((t & 3) * 8);
     }
     mg_st16(out + P, w[0], w[1], w[2], w[3]);
@@ -94,86 +110,95 @@ __device__ __noinline__ void nuc_chunk_generic(const uint32_t *__restrict__ pack
 // ---- K2 ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NUC_THREADS) k_emit_nuc(
     const uint32_t *__restrict__ packed, const int64_t *__restrict__ piece_off, const int64_t *__restrict__ piece_src,
-    int64_t n_piece, const int64_t *__restrict__ tile_first, int64_t total, const uint8_t *__restrict__ lit,
+    int64_t n_piece, const int64_t *__restrict__ tile_first, int64_t total, int64_t T,
     const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte, int64_t n_exc, uint8_t *__restrict__ out) {
-    __shared__ int64_t s_base[NUC_CAP];               // source index of tile position 0 (see header comment)
-    __shared__ int32_t s_rel[NUC_CAP + 1];            // piece start relative to the tile, clamped to [.., TILE]
-    __shared__ uint8_t s_kind[NUC_CAP];
-    __shared__ uint16_t s_unit[NUC_UNITS];            // piece holding byte 64*u of the tile
+    // compacted genome pieces of the tile: text range [c_start, c_end) relative to the tile, and the nibble
+    // index that tile position 0 would have (index of position q = c_base + q)
+    __shared__ int64_t c_base[NUC_CAP + 2];
+    __shared__ int32_t c_start[NUC_CAP + 2], c_end[NUC_CAP + 2];
+    __shared__ uint16_t s_unit[NUC_UNITS];            // first compacted piece that ends after byte 64*u
+    __shared__ int s_warp[8];
     const int64_t P0 = (int64_t)blockIdx.x * MG_NUC_TILE;
     const int64_t p_lo = tile_first[blockIdx.x];
     int64_t p_hi = tile_first[blockIdx.x + 1] + 1;    // one past the last piece this tile can touch
     if (p_hi > n_piece) p_hi = n_piece;
-    const int ncache = (int)min((int64_t)NUC_CAP, p_hi - p_lo);
-    for (int i = threadIdx.x; i <= ncache; i += NUC_THREADS) {
-        const int64_t off = __ldg(piece_off + p_lo + i);
-        const int64_t rel = off - P0;                 // > -2^31: piece lengths are int32
-        s_rel[i] = rel > MG_NUC_TILE ? MG_NUC_TILE : (int32_t)rel;
-        if (i < ncache) {
-            const uint64_t sk = (uint64_t)__ldg(piece_src + p_lo + i);
-            const int kind = (int)(sk >> MG_KIND_SHIFT);
-            const int64_t src = (int64_t)(sk & MG_SRC_MASK);
-            int64_t base;
-            if (kind == KIND_RC) base = src + (__ldg(piece_off + p_lo + i + 1) - off) - 1 + rel;   // index = base - q
-            else base = src - rel;                                                               // index = base + q
-            s_base[i] = base;
-            s_kind[i] = (uint8_t)kind;
+    const int nraw = (int)min((int64_t)NUC_CAP, p_hi - p_lo);
+    const int tile_len = (int)min((int64_t)MG_NUC_TILE, total - P0);
+
+    // ---- stage: each thread examines NUC_PPT consecutive raw pieces, keeps the non-empty genome ones
+    int64_t kb[NUC_PPT];
+    int32_t ks[NUC_PPT], ke[NUC_PPT];
+    int nk = 0;
+    {
+        const int i0 = (int)threadIdx.x * NUC_PPT;
+        int64_t off = i0 < nraw ? __ldg(piece_off + p_lo + i0) : 0;
+#pragma unroll
+        for (int k = 0; k < NUC_PPT; k++) {
+            const int i = i0 + k;
+            if (i < nraw) {
+                const int64_t nxt = __ldg(piece_off + p_lo + i + 1);
+                const uint64_t sk = (uint64_t)__ldg(piece_src + p_lo + i);
+                const int64_t rs = off - P0, re = nxt - P0;
+                if ((sk >> MG_KIND_SHIFT) != MG_KIND_LIT && re > rs && re > 0 && rs < MG_NUC_TILE) {
+                    kb[nk] = (int64_t)(sk & MG_SRC_MASK) - rs;
+                    ks[nk] = rs < -BIG ? -BIG : (int32_t)rs;
+                    ke[nk] = re > MG_NUC_TILE ? MG_NUC_TILE : (int32_t)re;
+                    nk++;
+                }
+                off = nxt;
+            }
         }
     }
+    int n_c;
+    const int my0 = block_excl_scan256(nk, s_warp, &n_c);
+#pragma unroll
+    for (int k = 0; k < NUC_PPT; k++) {
+        if (k < nk) { c_base[my0 + k] = kb[k]; c_start[my0 + k] = ks[k]; c_end[my0 + k] = ke[k]; }
+    }
+    if (threadIdx.x < 2) { c_start[n_c + threadIdx.x] = BIG; c_end[n_c + threadIdx.x] = BIG; c_base[n_c + threadIdx.x] = 0; }
     __syncthreads();
-    for (int i = threadIdx.x; i < ncache; i += NUC_THREADS) {
-        const int r0 = s_rel[i] < 0 ? 0 : s_rel[i], r1 = s_rel[i + 1] < 0 ? 0 : s_rel[i + 1];
-        const int u1 = min((r1 + 63) >> 6, NUC_UNITS);
-        for (int u = (r0 + 63) >> 6; u < u1; u++) s_unit[u] = (uint16_t)i;
+    for (int i = threadIdx.x; i <= n_c; i += NUC_THREADS) {
+        const int e0 = i ? c_end[i - 1] : 0, e1 = i < n_c ? c_end[i] : MG_NUC_TILE;
+        const int u1 = min((e1 + 63) >> 6, NUC_UNITS);
+        for (int u = i ? ((e0 + 63) >> 6) : 0; u < u1; u++) s_unit[u] = (uint16_t)i;
     }
     __syncthreads();
-    const int cached_end = s_rel[ncache];             // tile-relative position where the cached pieces end
-    const int tile_len = (int)min((int64_t)MG_NUC_TILE, total - P0);
+    // text position (tile-relative) up to which the staged pieces are complete
+    const int covered = (p_hi - p_lo > NUC_CAP) ? (int)min((int64_t)MG_NUC_TILE, __ldg(piece_off + p_lo + NUC_CAP) - P0) : MG_NUC_TILE;
 
 #pragma unroll 1
     for (int cidx = 0; cidx < NUC_CHUNKS; cidx++) {
         const int p = (cidx * NUC_THREADS + (int)threadIdx.x) << 4;
         if (p >= tile_len) break;
-        if (p + 16 > cached_end && cached_end < tile_len) {      // piece list overflowed the cache: slow path
+        if (p + 16 > covered) {                        // staging overflowed: slow path
             const int64_t j = mg_search_le(piece_off, p_lo, n_piece, P0 + p);
-            nuc_chunk_generic(packed, piece_off, piece_src, n_piece, j, P0 + p, total, lit, exc_pos, exc_byte, n_exc, out);
+            nuc_chunk_generic(packed, piece_off, piece_src, j, P0 + p, total, T, exc_pos, exc_byte, n_exc, out);
             continue;
         }
-        int j = s_unit[p >> 6];
-        while (s_rel[j + 1] <= p) j++;
-        uint64_t nacc = 0;                             // nibble codes of the 16 output positions
-        uint32_t bw0 = 0, bw1 = 0, bw2 = 0, bw3 = 0;  // raw bytes (literals)
-        uint32_t bm = 0;                               // which of the 16 bytes are raw
-        const int end = min(16, tile_len - p);
-        int lo = 0;
-        for (;;) {
-            const int hi = min(s_rel[j + 1] - p, end);
-            const int kind = s_kind[j];
-            const int64_t base = s_base[j];
-            if (kind == KIND_LIT) {
-                uint32_t w[4];
-                ld_lit16(lit, base + p, w);
-                const uint32_t m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-                const uint32_t m0 = expand4(m), m1 = expand4(m >> 4), m2 = expand4(m >> 8), m3 = expand4(m >> 12);
-                bw0 |= w[0] & m0; bw1 |= w[1] & m1; bw2 |= w[2] & m2; bw3 |= w[3] & m3;
-                bm |= m;
-            } else {
-                uint64_t v = kind == KIND_FWD ? mg_ld_nib16(packed, base + p) : mg_rc_nib16(mg_ld_nib16(packed, base - p - 15));
-                if (hi - lo < 16) v &= nib_range_mask(lo, hi);
-                nacc |= v;
+        int A = s_unit[p >> 6];
+        while (c_end[A] <= p) A++;
+        // first two genome pieces of the chunk, branch-free
+        const int sA = c_start[A], eA = c_end[A], sB = c_start[A + 1], eB = c_end[A + 1];
+        const bool hasA = sA < p + 16, hasB = sB < p + 16;
+        const int64_t gA = hasA ? c_base[A] + p : MG_FRONT_PAD;
+        const int64_t gB = hasB ? c_base[A + 1] + p : MG_FRONT_PAD;
+        uint64_t vA = mg_ld_nib16(packed, gA);
+        uint64_t vB = mg_ld_nib16(packed, gB);
+        const int loA = max(sA - p, 0), hiA = min(eA - p, 16);
+        const int loB = max(sB - p, 0), hiB = min(eB - p, 16);
+        vA = hasA ? (vA & nib_range_mask(loA, hiA)) : 0ull;
+        vB = hasB ? (vB & nib_range_mask(loB, hiB)) : 0ull;
+        uint64_t nacc = vA | vB;
+        if (hasB && c_start[A + 2] < p + 16) {         // three or more genome pieces inside 16 bytes: rare
+            for (int j = A + 2; c_start[j] < p + 16; j++) {
+                const int lo = c_start[j] - p, hi = min(c_end[j] - p, 16);
+                nacc |= mg_ld_nib16(packed, c_base[j] + p) & nib_range_mask(lo, hi);
             }
-            if (hi >= end) break;
-            lo = hi;
-            do { j++; } while (s_rel[j + 1] <= p + lo);
         }
         uint32_t w0, w1, w2, w3;
         mg_decode8((uint32_t)nacc, w0, w1);
         mg_decode8((uint32_t)(nacc >> 32), w2, w3);
-        if (bm) {
-            const uint32_t m0 = expand4(bm), m1 = expand4(bm >> 4), m2 = expand4(bm >> 8), m3 = expand4(bm >> 12);
-            w0 = (w0 & ~m0) | bw0; w1 = (w1 & ~m1) | bw1; w2 = (w2 & ~m2) | bw2; w3 = (w3 & ~m3) | bw3;
-        }
-        // code 15 = byte outside the packed alphabet on a '+' piece (reverse pieces already turned it into 'n',
+        // code 15 = byte outside the packed alphabet on a '+' piece (the reverse plane already holds 'n',
         // genome.py:791-792): fetch the exact byte the FASTA had (genome.py:606 keeps it).  Rare.
         uint64_t e = nacc & (nacc >> 1) & (nacc >> 2) & (nacc >> 3) & 0x1111111111111111ull;
         if (e) {
@@ -181,10 +206,13 @@ __global__ void __launch_bounds__(NUC_THREADS) k_emit_nuc(
             while (e) {
                 const int t = (__ffsll((long long)e) - 1) >> 2;
                 e &= e - 1;
-                int jj = s_unit[p >> 6];
-                while (s_rel[jj + 1] <= p + t) jj++;
-                const uint32_t b = mg_exc_byte(exc_pos, exc_byte, n_exc, s_base[jj] + p + t);
-                w[t >> 2] = (w[t >> 2] & ~(0xFFu << ((t & 3) * 8))) | (b << ((t & 3) * 8));
+                int jj = A;
+                while (c_end[jj] <= p + t) jj++;
+                const int64_t gi = c_base[jj] + p + t;
+                if (gi < T) {
+                    const uint32_t b = mg_exc_byte(exc_pos, exc_byte, n_exc, gi);
+                    w[t >> 2] = (w[t >> 2] & ~(0xFFu << ((t & 3) * 8))) | (b << ((t & 3) * 8));
+                }
             }
             w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3];
         }
@@ -192,15 +220,41 @@ __global__ void __launch_bounds__(NUC_THREADS) k_emit_nuc(
     }
 }
 
+// ---- literal framing bytes (">ID\n" prefixes, "\n" suffixes): one thread per literal piece -------------------
+// Runs AFTER the main kernel on the same stream and overwrites the placeholder bytes it left there.
+// which = 0: nucleotide text (positions from piece_off); which = 1: protein text (positions from prot_off).
+__global__ void __launch_bounds__(256) k_emit_lit(int which, int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
+                                                  const int64_t *__restrict__ piece_off, const int64_t *__restrict__ prot_off,
+                                                  const int32_t *__restrict__ rec_aa, const int64_t *__restrict__ rec_lit_off,
+                                                  const int32_t *__restrict__ rec_pre, const int32_t *__restrict__ rec_suf,
+                                                  const uint8_t *__restrict__ lit, uint8_t *__restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= 2 * n_rec) return;
+    const int64_t r = i >> 1;
+    const bool suffix = i & 1;
+    const int pre = rec_pre[r];
+    const int n = suffix ? rec_suf[r] : pre;
+    if (n <= 0) return;
+    const uint8_t *src = lit + rec_lit_off[r] + (suffix ? pre : 0);
+    int64_t dst;
+    if (which == 0) {
+        const int64_t f0 = rec_seg_off[r] + 2 * r, f1 = rec_seg_off[r + 1] + 2 * (r + 1);
+        dst = suffix ? piece_off[f1 - 1] : piece_off[f0];
+    } else {
+        int32_t naa = rec_aa[r];
+        if (naa < 0) naa = 0;
+        dst = prot_off[r] + (suffix ? pre + naa : 0);
+    }
+    for (int k = 0; k < n; k++) out[dst + k] = __ldg(src + k);
+}
+
 // ---- K3 -------------------------------------------------------------------------------------------------------
-// generic fallback: one byte at a time from global memory
+// generic fallback: one residue at a time from global memory (literal positions skipped)
 __device__ __noinline__ void prot_chunk_generic(const uint32_t *__restrict__ packed, const int64_t *__restrict__ piece_off,
                                                 const int64_t *__restrict__ piece_src, const int64_t *__restrict__ rec_seg_off,
                                                 const int64_t *__restrict__ prot_off, const int32_t *__restrict__ rec_aa,
-                                                const int8_t *__restrict__ rec_skip, const int64_t *__restrict__ rec_lit_off,
-                                                const int32_t *__restrict__ rec_pre, int64_t r, int64_t P, int64_t total,
-                                                const uint8_t *__restrict__ lit, const uint8_t *__restrict__ aa4096,
-                                                uint8_t *__restrict__ out) {
+                                                const int8_t *__restrict__ rec_skip, const int32_t *__restrict__ rec_pre, int64_t r,
+                                                int64_t P, int64_t total, const uint8_t *__restrict__ aa4096, uint8_t *__restrict__ out) {
     uint32_t w[4] = {0, 0, 0, 0};
     int64_t off_r = __ldg(prot_off + r), off_n = __ldg(prot_off + r + 1);
     for (int t = 0; t < 16 && P + t < total; t++) {
@@ -209,17 +263,13 @@ __device__ __noinline__ void prot_chunk_generic(const uint32_t *__restrict__ pac
         const int64_t q = pos - off_r, pre = rec_pre[r];
         int64_t naa = rec_aa[r];
         if (naa < 0) naa = 0;
-        uint32_t b;
-        if (q < pre) b = __ldg(lit + rec_lit_off[r] + q);
-        else if (q < pre + naa) {
-            const int64_t f0 = __ldg(rec_seg_off + r) + 2 * r, f1 = __ldg(rec_seg_off + r + 1) + 2 * (r + 1);
-            const int64_t S = __ldg(piece_off + f0 + 1) + rec_skip[r] + 3 * (q - pre);
-            const int64_t j = mg_search_le(piece_off, f0 + 1, f1 - 1, S);
-            uint64_t acc[3];
-            mg_gather_nib(packed, piece_off, piece_src, j, S, 3, acc);
-            b = __ldg(aa4096 + ((uint32_t)acc[0] & 0xFFFu));
-        } else b = __ldg(lit + rec_lit_off[r] + pre + (q - pre - naa));
-        w[t >> 2] |= b << ((t & 3) * 8);
+        if (q < pre || q >= pre + naa) continue;
+        const int64_t f0 = __ldg(rec_seg_off + r) + 2 * r, f1 = __ldg(rec_seg_off + r + 1) + 2 * (r + 1);
+        const int64_t S = __ldg(piece_off + f0 + 1) + rec_skip[r] + 3 * (q - pre);
+        const int64_t j = mg_search_le(piece_off, f0 + 1, f1 - 1, S);
+        uint64_t acc[3];
+        mg_gather_nib(packed, piece_off, piece_src, j, S, 3, acc);
+        w[t >> 2] |= (uint32_t)__ldg(aa4096 + ((uint32_t)acc[0] & 0xFFFu)) << ((t & 3) * 8);
     }
     mg_st16(out + P, w[0], w[1], w[2], w[3]);
 }
@@ -230,21 +280,19 @@ __device__ __noinline__ void prot_chunk_generic(const uint32_t *__restrict__ pac
 __global__ void __launch_bounds__(PROT_THREADS) k_emit_prot(
     const uint32_t *__restrict__ packed, const int64_t *__restrict__ piece_off, const int64_t *__restrict__ piece_src,
     const int64_t *__restrict__ rec_seg_off, const int64_t *__restrict__ prot_off, const int32_t *__restrict__ rec_aa,
-    const int8_t *__restrict__ rec_skip, const int64_t *__restrict__ rec_lit_off, const int32_t *__restrict__ rec_pre,
-    int64_t n_rec, const int64_t *__restrict__ tile_first, int64_t total, const uint8_t *__restrict__ lit,
-    const uint8_t *__restrict__ aa4096, uint8_t *__restrict__ out) {
+    const int8_t *__restrict__ rec_skip, const int32_t *__restrict__ rec_pre, int64_t n_rec,
+    const int64_t *__restrict__ tile_first, int64_t total, const uint8_t *__restrict__ aa4096, uint8_t *__restrict__ out) {
     __shared__ __align__(16) uint8_t s_aa[4096];
-    // records of the tile
-    __shared__ int32_t s_pstart[PROT_RCAP + 1];       // record start in the protein text, relative to the tile (may be < 0)
-    __shared__ int32_t s_pre[PROT_RCAP], s_naa[PROT_RCAP];
-    __shared__ int32_t s_q0[PROT_RCAP];               // nucleotide-text position of the first codon, relative to origin O
-    __shared__ int16_t s_j0[PROT_RCAP], s_j1[PROT_RCAP];   // first / one-past-last segment piece (tile-local)
-    __shared__ int64_t s_lbase[PROT_RCAP];            // literal index of tile position 0 for the prefix
-    // pieces of those records
-    __shared__ int64_t s_base[PROT_PCAP];
-    __shared__ int32_t s_rel[PROT_PCAP + 1];          // relative to O = piece_off[first cached piece]
-    __shared__ uint8_t s_kind[PROT_PCAP];
+    // compacted records (those with residues inside the tile): residue range [r_s, r_e) in the protein text relative to
+    // the tile, nucleotide-text position (relative to O) of the codon of residue 0, first compacted piece
+    __shared__ int32_t r_s[PROT_RCAP + 2], r_e[PROT_RCAP + 2], r_q0[PROT_RCAP + 2];
+    __shared__ int16_t r_j0[PROT_RCAP + 2];
+    // compacted genome pieces of those records: nucleotide-text range relative to O, nibble index of position O
+    __shared__ int64_t c_base[PROT_PCAP + 2];
+    __shared__ int32_t c_start[PROT_PCAP + 2], c_end[PROT_PCAP + 2];
+    __shared__ int16_t s_cidx[PROT_PCAP + 1];         // raw piece -> compacted index
     __shared__ uint16_t s_unit[PROT_UNITS];
+    __shared__ int s_warp[8];
     reinterpret_cast<uint4 *>(s_aa)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(aa4096) + threadIdx.x);
     const int64_t P0 = (int64_t)blockIdx.x * MG_PROT_TILE;
     const int64_t r_lo = tile_first[blockIdx.x];
@@ -254,51 +302,101 @@ __global__ void __launch_bounds__(PROT_THREADS) k_emit_prot(
     const int64_t pc_lo = __ldg(rec_seg_off + r_lo) + 2 * r_lo;
     const int64_t pc_hi = __ldg(rec_seg_off + r_hi) + 2 * r_hi;
     const int64_t O = __ldg(piece_off + pc_lo);
-    const int npc = (int)min((int64_t)PROT_PCAP + 1, pc_hi - pc_lo);
-    const bool fits = nrec <= PROT_RCAP && npc <= PROT_PCAP && (__ldg(piece_off + pc_hi) - O) < 0x7fffffffll;
+    const int64_t nraw64 = pc_hi - pc_lo;
+    const bool fits = nrec <= PROT_RCAP && nraw64 <= PROT_PCAP && (__ldg(piece_off + pc_hi) - O) < (int64_t)BIG;
     const int tile_len = (int)min((int64_t)MG_PROT_TILE, total - P0);
     if (!fits) {                                      // rare: whole tile through the generic path
         for (int cidx = 0; cidx < PROT_CHUNKS; cidx++) {
             const int p = (cidx * PROT_THREADS + (int)threadIdx.x) << 4;
             if (p >= tile_len) break;
             const int64_t r = mg_search_le(prot_off, r_lo, n_rec, P0 + p);
-            prot_chunk_generic(packed, piece_off, piece_src, rec_seg_off, prot_off, rec_aa, rec_skip, rec_lit_off, rec_pre, r,
-                               P0 + p, total, lit, aa4096, out);
+            prot_chunk_generic(packed, piece_off, piece_src, rec_seg_off, prot_off, rec_aa, rec_skip, rec_pre, r, P0 + p, total,
+                               aa4096, out);
         }
         return;
     }
-    for (int i = threadIdx.x; i <= npc; i += PROT_THREADS) {
-        const int64_t off = __ldg(piece_off + pc_lo + i);
-        const int32_t rel = (int32_t)(off - O);
-        s_rel[i] = rel;
-        if (i < npc) {
-            const uint64_t sk = (uint64_t)__ldg(piece_src + pc_lo + i);
-            const int kind = (int)(sk >> MG_KIND_SHIFT);
-            const int64_t src = (int64_t)(sk & MG_SRC_MASK);
-            s_base[i] = kind == KIND_RC ? src + (__ldg(piece_off + pc_lo + i + 1) - off) - 1 + rel : src - rel;
-            s_kind[i] = (uint8_t)kind;
+    const int nraw = (int)nraw64;
+    // ---- stage genome pieces
+    int n_c;
+    {
+        int64_t kb[PROT_PPT];
+        int32_t ks[PROT_PPT], ke[PROT_PPT];
+        int nk = 0;
+        uint32_t kept = 0;                            // bit k: raw piece i0+k was kept
+        const int i0 = (int)threadIdx.x * PROT_PPT;
+        int64_t off = i0 < nraw ? __ldg(piece_off + pc_lo + i0) : 0;
+#pragma unroll
+        for (int k = 0; k < PROT_PPT; k++) {
+            const int i = i0 + k;
+            if (i < nraw) {
+                const int64_t nxt = __ldg(piece_off + pc_lo + i + 1);
+                const uint64_t sk = (uint64_t)__ldg(piece_src + pc_lo + i);
+                if ((sk >> MG_KIND_SHIFT) != MG_KIND_LIT && nxt > off) {
+                    const int32_t rs = (int32_t)(off - O);
+                    kb[nk] = (int64_t)(sk & MG_SRC_MASK) - rs;
+                    ks[nk] = rs;
+                    ke[nk] = (int32_t)(nxt - O);
+                    nk++;
+                    kept |= 1u << k;
+                }
+                off = nxt;
+            }
         }
-    }
-    for (int i = threadIdx.x; i <= nrec; i += PROT_THREADS) {
-        const int64_t r = r_lo + i;
-        const int64_t ps = __ldg(prot_off + r) - P0;
-        s_pstart[i] = ps > MG_PROT_TILE ? MG_PROT_TILE : (int32_t)ps;
-        if (i < nrec) {
-            const int64_t f0 = __ldg(rec_seg_off + r) + 2 * r, f1 = __ldg(rec_seg_off + r + 1) + 2 * (r + 1);
-            int32_t naa = rec_aa[r];
-            s_pre[i] = rec_pre[r];
-            s_naa[i] = naa < 0 ? 0 : naa;
-            s_q0[i] = (int32_t)(__ldg(piece_off + f0 + 1) - O) + rec_skip[r];
-            s_j0[i] = (int16_t)(f0 + 1 - pc_lo);
-            s_j1[i] = (int16_t)(f1 - 1 - pc_lo);
-            s_lbase[i] = rec_lit_off[r] - ps;
+        int c = block_excl_scan256(nk, s_warp, &n_c);
+        int kk = 0;
+#pragma unroll
+        for (int k = 0; k < PROT_PPT; k++) {
+            const int i = i0 + k;
+            if (i < nraw) {
+                s_cidx[i] = (int16_t)c;               // raw piece -> index of the first kept piece at or after it
+                if (kept & (1u << k)) {
+                    c_base[c] = kb[kk]; c_start[c] = ks[kk]; c_end[c] = ke[kk];
+                    c++; kk++;
+                }
+            }
         }
+        if (threadIdx.x == 0) s_cidx[nraw] = (int16_t)n_c;
+        if (threadIdx.x < 2) { c_start[n_c + threadIdx.x] = BIG; c_end[n_c + threadIdx.x] = BIG; c_base[n_c + threadIdx.x] = 0; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nrec; i += PROT_THREADS) {
-        const int r0 = s_pstart[i] < 0 ? 0 : s_pstart[i], r1 = s_pstart[i + 1] < 0 ? 0 : s_pstart[i + 1];
-        const int u1 = min((r1 + 63) >> 6, PROT_UNITS);
-        for (int u = (r0 + 63) >> 6; u < u1; u++) s_unit[u] = (uint16_t)i;
+    // ---- stage records
+    int n_r;
+    {
+        int32_t a_s[PROT_RPT], a_e[PROT_RPT], a_q[PROT_RPT];
+        int16_t a_j[PROT_RPT];
+        int nk = 0;
+#pragma unroll
+        for (int k = 0; k < PROT_RPT; k++) {
+            const int i = (int)threadIdx.x * PROT_RPT + k;
+            if (i < nrec) {
+                const int64_t r = r_lo + i;
+                int32_t naa = rec_aa[r];
+                if (naa > 0) {
+                    const int64_t rs = __ldg(prot_off + r) + rec_pre[r] - P0, re = rs + naa;
+                    if (re > 0 && rs < MG_PROT_TILE) {
+                        const int64_t f0 = __ldg(rec_seg_off + r) + 2 * r;
+                        a_s[nk] = rs < -BIG ? -BIG : (int32_t)rs;
+                        a_e[nk] = re > MG_PROT_TILE ? MG_PROT_TILE : (int32_t)re;
+                        // codon of the residue that would sit at tile position 0 (may be "before" the record)
+                        a_q[nk] = (int32_t)(__ldg(piece_off + f0 + 1) - O) + rec_skip[r] - 3 * (int32_t)rs;
+                        a_j[nk] = s_cidx[f0 + 1 - pc_lo];
+                        nk++;
+                    }
+                }
+            }
+        }
+        const int my0 = block_excl_scan256(nk, s_warp, &n_r);
+#pragma unroll
+        for (int k = 0; k < PROT_RPT; k++) {
+            if (k < nk) { r_s[my0 + k] = a_s[k]; r_e[my0 + k] = a_e[k]; r_q0[my0 + k] = a_q[k]; r_j0[my0 + k] = a_j[k]; }
+        }
+        if (threadIdx.x < 2) { r_s[n_r + threadIdx.x] = BIG; r_e[n_r + threadIdx.x] = BIG; r_q0[n_r + threadIdx.x] = 0; r_j0[n_r + threadIdx.x] = (int16_t)n_c; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= n_r; i += PROT_THREADS) {
+        const int e0 = i ? r_e[i - 1] : 0, e1 = i < n_r ? r_e[i] : MG_PROT_TILE;
+        const int u1 = min((e1 + 63) >> 6, PROT_UNITS);
+        for (int u = i ? ((e0 + 63) >> 6) : 0; u < u1; u++) s_unit[u] = (uint16_t)i;
     }
     __syncthreads();
 
@@ -306,76 +404,58 @@ __global__ void __launch_bounds__(PROT_THREADS) k_emit_prot(
     for (int cidx = 0; cidx < PROT_CHUNKS; cidx++) {
         const int p = (cidx * PROT_THREADS + (int)threadIdx.x) << 4;
         if (p >= tile_len) break;
-        int r = s_unit[p >> 6];
-        while (s_pstart[r + 1] <= p) r++;
+        int R = s_unit[p >> 6];
+        while (r_e[R] <= p) R++;
         uint32_t bw0 = 0, bw1 = 0, bw2 = 0, bw3 = 0;
-        const int end = min(16, tile_len - p);
-        int lo = 0;
-        for (;;) {                                    // pieces of this chunk: prefix | residues | suffix of record r, ...
-            const int qq = p + lo - s_pstart[r];      // position inside the record's text
-            const int pre = s_pre[r], naa = s_naa[r];
-            int hi;
-            uint32_t w[4];
-            if (qq < pre) {                           // literal prefix
-                hi = min(end, lo + (pre - qq));
-                ld_lit16(lit, s_lbase[r] + p, w);
-            } else if (qq < pre + naa) {              // residues: position t of the chunk is amino acid (p+t-pstart-pre)
-                hi = min(end, lo + (pre + naa - qq));
-                // nucleotide-text position (relative to O) of the codon that lands on chunk position 0
-                const int q = s_q0[r] + 3 * (p - s_pstart[r] - pre);
-                uint64_t acc[3] = {0, 0, 0};
-                int j = s_j0[r];
-                const int j1 = s_j1[r];
-                {   // locate the segment holding the first needed nibble
-                    const int first = q + 3 * lo;
-                    int a = j, b = j1;
-                    while (b - a > 1) {
-                        const int mid = (a + b) >> 1;
-                        if (s_rel[mid] <= first) a = mid; else b = mid;
-                    }
-                    j = a;
+        for (; r_s[R] < p + 16; R++) {                // records with residues inside this chunk (usually one)
+            const int lo = max(r_s[R] - p, 0), hi = min(r_e[R] - p, 16);
+            // nucleotide-text position (relative to O) of the codon that lands on chunk position 0
+            const int q = r_q0[R] + 3 * p;
+            const int need_lo = q + 3 * lo, need_hi = q + 3 * hi;        // nibbles [need_lo, need_hi)
+            int j = r_j0[R];
+            {   // first piece of the record that ends after need_lo (pieces of a record are contiguous)
+                int a = j, b = r_j0[R + 1];
+                while (b - a > 1) {
+                    const int mid = (a + b) >> 1;
+                    if (c_start[mid] <= need_lo) a = mid; else b = mid;
                 }
-                const int need_lo = 3 * lo, need_hi = 3 * hi;           // nibbles [need_lo, need_hi) of the 48
+                j = a;
+            }
+            uint64_t acc[3];
 #pragma unroll
-                for (int g = 0; g < 3; g++) {
-                    int nlo = max(need_lo - 16 * g, 0);
-                    const int nend = min(need_hi - 16 * g, 16);
-                    if (nend <= nlo) continue;
-                    const int qg = q + 16 * g;        // position of nibble 0 of this group
-                    while (s_rel[j + 1] <= qg + nlo) j++;
-                    uint64_t a = 0;
-                    for (;;) {
-                        const int nhi = min(s_rel[j + 1] - qg, nend);
-                        const int64_t base = s_base[j];
-                        uint64_t v = s_kind[j] == KIND_FWD ? mg_ld_nib16(packed, base + qg) : mg_rc_nib16(mg_ld_nib16(packed, base - qg - 15));
-                        if (nhi - nlo < 16) v &= nib_range_mask(nlo, nhi);
-                        a |= v;
-                        if (nhi >= nend) break;
-                        nlo = nhi;
-                        do { j++; } while (s_rel[j + 1] <= qg + nlo);
+            for (int g = 0; g < 3; g++) {
+                const int w_lo = max(q + 16 * g, need_lo), w_hi = min(q + 16 * g + 16, need_hi);
+                uint64_t a = 0;
+                if (w_hi > w_lo) {
+                    while (c_end[j] <= w_lo) j++;
+                    const int qg = q + 16 * g;
+                    // first two pieces of this 16-nibble group, branch-free
+                    const int sA = c_start[j], eA = c_end[j], sB = c_start[j + 1], eB = c_end[j + 1];
+                    const bool hasB = sB < w_hi;
+                    const uint64_t vA = mg_ld_nib16(packed, c_base[j] + qg);
+                    const uint64_t vB = mg_ld_nib16(packed, hasB ? c_base[j + 1] + qg : (int64_t)MG_FRONT_PAD);
+                    a = vA & nib_range_mask(max(sA, w_lo) - qg, min(eA, w_hi) - qg);
+                    if (hasB) a |= vB & nib_range_mask(sB - qg, min(eB, w_hi) - qg);
+                    if (hasB && c_start[j + 2] < w_hi) {
+                        for (int jj = j + 2; c_start[jj] < w_hi; jj++)
+                            a |= mg_ld_nib16(packed, c_base[jj] + qg) & nib_range_mask(c_start[jj] - qg, min(c_end[jj], w_hi) - qg);
                     }
-                    acc[g] = a;
                 }
-                w[0] = w[1] = w[2] = w[3] = 0;
+                acc[g] = a;
+            }
+            uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-                for (int k = 0; k < 16; k++) {        // codon k sits at bit 12k of acc[2]:acc[1]:acc[0]
-                    const int bit = 12 * k, ww = bit >> 6, sh = bit & 63;
-                    uint32_t idx = (uint32_t)(acc[ww] >> sh);
-                    if (sh > 52) idx |= (uint32_t)(acc[ww + 1] << (64 - sh));
-                    w[k >> 2] |= (uint32_t)s_aa[idx & 0xFFFu] << ((k & 3) * 8);
-                }
-            } else {                                  // literal suffix
-                hi = min(end, s_pstart[r + 1] - p);
-                ld_lit16(lit, s_lbase[r] - naa + p, w);
+            for (int k = 0; k < 16; k++) {            // codon k sits at bit 12k of acc[2]:acc[1]:acc[0]
+                const int bit = 12 * k, ww = bit >> 6, sh = bit & 63;
+                uint32_t idx = (uint32_t)(acc[ww] >> sh);
+                if (sh > 52) idx |= (uint32_t)(acc[ww + 1] << (64 - sh));
+                w[k >> 2] |= (uint32_t)s_aa[idx & 0xFFFu] << ((k & 3) * 8);
             }
             const uint32_t m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
             if (m == 0xFFFFu) { bw0 = w[0]; bw1 = w[1]; bw2 = w[2]; bw3 = w[3]; }
             else {
                 bw0 |= w[0] & expand4(m); bw1 |= w[1] & expand4(m >> 4); bw2 |= w[2] & expand4(m >> 8); bw3 |= w[3] & expand4(m >> 12);
             }
-            if (hi >= end) break;
-            lo = hi;
-            while (s_pstart[r + 1] <= p + lo) r++;
         }
         mg_st16(out + P0 + p, bw0, bw1, bw2, bw3);
     }
@@ -400,11 +480,16 @@ extern "C" int mg_emit_nuc_device(mg_plan *p, uint8_t *out_dev, void *stream) {
     MG_REQUIRE(out_dev != nullptr && ((uintptr_t)out_dev & 15) == 0, "out_dev must be a 16-byte aligned device pointer");
     MG_CUDA(cudaSetDevice(p->device));
     mg_genome *g = p->g;
-    p->last_stream = (cudaStream_t)stream;
-    k_emit_nuc<<<(unsigned)p->n_nuc_tile, NUC_THREADS, 0, (cudaStream_t)stream>>>(
-        g->d_packed, p->d_piece_off, p->d_piece_src, p->n_piece, p->d_nuc_tile, p->nuc_total, p->d_lit, g->d_exc_pos,
-        g->d_exc_byte, g->n_exc, out_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    p->last_stream = st;
+    k_emit_nuc<<<(unsigned)p->n_nuc_tile, NUC_THREADS, 0, st>>>(g->d_packed, p->d_piece_off, p->d_piece_src, p->n_piece, p->d_nuc_tile,
+                                                              p->nuc_total, g->total_bases, g->d_exc_pos, g->d_exc_byte, g->n_exc, out_dev);
     MG_LAUNCH_CHECK();
+    if (p->n_lit > 0) {
+        k_emit_lit<<<(unsigned)((2 * p->n_rec + 255) / 256), 256, 0, st>>>(0, p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_prot_off,
+                                                                         p->d_rec_aa, p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, p->d_lit, out_dev);
+        MG_LAUNCH_CHECK();
+    }
     return MG_OK;
 }
 
@@ -415,11 +500,17 @@ extern "C" int mg_emit_prot_device(mg_plan *p, uint8_t *out_dev, void *stream) {
     MG_REQUIRE(out_dev != nullptr && ((uintptr_t)out_dev & 15) == 0, "out_dev must be a 16-byte aligned device pointer");
     MG_CUDA(cudaSetDevice(p->device));
     mg_genome *g = p->g;
-    p->last_stream = (cudaStream_t)stream;
-    k_emit_prot<<<(unsigned)p->n_prot_tile, PROT_THREADS, 0, (cudaStream_t)stream>>>(
-        g->d_packed, p->d_piece_off, p->d_piece_src, p->d_rec_seg_off, p->d_prot_off, p->d_rec_aa, p->d_rec_skip,
-        p->d_rec_lit_off, p->d_rec_pre, p->n_rec, p->d_prot_tile, p->prot_total, p->d_lit, g->d_aa4096, out_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    p->last_stream = st;
+    k_emit_prot<<<(unsigned)p->n_prot_tile, PROT_THREADS, 0, st>>>(g->d_packed, p->d_piece_off, p->d_piece_src, p->d_rec_seg_off,
+                                                                 p->d_prot_off, p->d_rec_aa, p->d_rec_skip, p->d_rec_pre, p->n_rec,
+                                                                 p->d_prot_tile, p->prot_total, g->d_aa4096, out_dev);
     MG_LAUNCH_CHECK();
+    if (p->n_lit > 0) {
+        k_emit_lit<<<(unsigned)((2 * p->n_rec + 255) / 256), 256, 0, st>>>(1, p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_prot_off,
+                                                                         p->d_rec_aa, p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, p->d_lit, out_dev);
+        MG_LAUNCH_CHECK();
+    }
     return MG_OK;
 }
 

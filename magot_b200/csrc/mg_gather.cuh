@@ -7,8 +7,8 @@
 // Gather nb (<= 48) nibbles of the spliced sequence starting at nucleotide-text offset S, which lies in
 // piece j (piece_off[j] <= S < piece_off[j+1]).  Following pieces are walked as needed; the caller
 // guarantees that [S, S+nb) stays inside genome-segment pieces.  Result: nibble k in bits [4k,4k+4)
-// of the 192-bit value acc[2]:acc[1]:acc[0]; reverse-strand pieces arrive already reverse-complemented
-// in code space, so the consumer never needs to know the strand.
+// of the 192-bit value acc[2]:acc[1]:acc[0]; reverse-strand pieces are forward reads of the genome's
+// reverse-complement plane, so the consumer never needs to know the strand.
 __device__ __forceinline__ void mg_gather_nib(const uint32_t *__restrict__ packed, const int64_t *__restrict__ piece_off,
                                               const int64_t *__restrict__ piece_src, int64_t j, int64_t S, int nb,
                                               uint64_t acc[3]) {
@@ -28,12 +28,7 @@ __device__ __forceinline__ void mg_gather_nib(const uint32_t *__restrict__ packe
         int c = nb - f;
         if (c > 16) c = 16;
         if (rem < c) c = (int)rem;
-        uint64_t v;
-        if ((sk >> MG_KIND_SHIFT) == MG_KIND_FWD) {
-            v = mg_ld_nib16(packed, src + o);
-        } else {
-            v = mg_rc_nib16(mg_ld_nib16(packed, src + (off_n - off_j) - o - 16));
-        }
+        uint64_t v = mg_ld_nib16(packed, src + o);     // '-' pieces already point into the reverse plane
         if (c < 16) v &= (1ull << (4 * c)) - 1ull;
         const int w = f >> 4, sh = (f & 15) << 2;
         if (w == 0) {

@@ -85,7 +85,7 @@ extern "C" int mg_genome_create(int device, int64_t n_contigs, const int64_t *co
     }
     g->h_contig_base[n_contigs] = base;
     g->total_bases = base;
-    const int64_t words = base / 8 + MG_TAIL_WORDS;
+    const int64_t words = 2 * base / 8 + MG_TAIL_WORDS;           // forward plane + reverse-complement plane
     MG_CUDA(cudaMalloc(&g->d_packed, words * sizeof(uint32_t)));
     // padding decodes as 'N' (0x8 per nibble) so that stray reads are harmless and deterministic
     MG_CUDA(cudaMemset(g->d_packed, 0x88, words * sizeof(uint32_t)));
@@ -157,7 +157,7 @@ int mg_ensure_pin(mg_genome *g, int64_t bytes) {
 // One thread packs 16 ASCII bytes (one 16-byte load) into 2 words (one 8-byte store).  HBM traffic:
 // 1 B/base read + 0.5 B/base written.  Bytes outside the 15-symbol alphabet become code 15 and are
 // appended to the exception list (rare in real assemblies; dense lists still work, only slower).
-__global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ ascii, int64_t n, int64_t g0,
+__global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ ascii, int64_t n, int64_t g0, int64_t two_T,
                                               uint32_t *__restrict__ packed, int64_t *__restrict__ exc_pos,
                                               uint8_t *__restrict__ exc_byte, int64_t exc_cap,
                                               unsigned long long *__restrict__ exc_count) {
@@ -190,6 +190,9 @@ __global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ ascii,
             }
         }
         *reinterpret_cast<uint2 *>(packed + ((g0 + b0) >> 3)) = make_uint2(o[0], o[1]);
+        // reverse-complement plane: forward bases [G, G+16) are bases [2T-16-G, 2T-G) of the second plane
+        const uint64_t rc = mg_rc_nib16(((uint64_t)o[1] << 32) | o[0]);
+        *reinterpret_cast<uint2 *>(packed + ((two_T - 16 - (g0 + b0)) >> 3)) = make_uint2((uint32_t)rc, (uint32_t)(rc >> 32));
     }
 }
 
@@ -198,7 +201,7 @@ static int pack_device_chunk(mg_genome *g, int64_t gbase, const uint8_t *d_ascii
         MG_CUDA(cudaMemsetAsync(g->d_exc_count, 0, sizeof(unsigned long long), st));
         const int64_t nchunk = (n + 15) / 16;
         const int blocks = (int)std::min<int64_t>((nchunk + 255) / 256, 148 * 16);
-        k_pack<<<std::max(blocks, 1), 256, 0, st>>>(d_ascii, n, gbase, g->d_packed, g->d_exc_pos, g->d_exc_byte,
+        k_pack<<<std::max(blocks, 1), 256, 0, st>>>(d_ascii, n, gbase, 2 * g->total_bases, g->d_packed, g->d_exc_pos, g->d_exc_byte,
                                                    g->exc_cap, g->d_exc_count);
         MG_LAUNCH_CHECK();
         unsigned long long cnt = 0;
@@ -300,19 +303,14 @@ extern "C" int mg_genome_finalize(mg_genome *g, int64_t *n_exceptions_out) {
 }
 
 // ---- range decode -----------------------------------------------------------------------------------
-// out[i] for i in [0, n): forward = base g_lo+i; minus = complement of base g_hi-1-i.  16 bytes / thread.
+// out[i] for i in [0, n) = base g_lo+i of whichever plane g_lo points into.  16 bytes / thread.
 __global__ void __launch_bounds__(256) k_fetch(const uint32_t *__restrict__ packed, int64_t g_lo, int64_t n, int minus,
                                                const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte,
                                                int64_t n_exc, uint8_t *__restrict__ out) {
     const int64_t nchunk = (n + 15) >> 4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nchunk; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t o = i << 4;
-        uint64_t v;
-        if (!minus) {
-            v = mg_ld_nib16(packed, g_lo + o);
-        } else {
-            v = mg_rc_nib16(mg_ld_nib16(packed, g_lo + n - o - 16));
-        }
+        const uint64_t v = mg_ld_nib16(packed, g_lo + o);       // g_lo already points into the right plane
         uint32_t b0, b1, b2, b3;
         mg_decode8((uint32_t)v, b0, b1);
         mg_decode8((uint32_t)(v >> 32), b2, b3);
@@ -348,7 +346,8 @@ extern "C" int mg_genome_fetch(mg_genome *g, int64_t contig, int64_t lo, int64_t
     for (int64_t done = 0; done < n;) {
         const int64_t m = std::min<int64_t>(step, n - done);
         // forward: output [done, done+m) = bases gl+done ..; minus: output [done, done+m) = rc of bases [gl+n-done-m, gl+n-done)
-        const int64_t sub_lo = minus ? gl + n - done - m : gl + done;
+        // minus: output byte i is the complement of base gl+n-1-i, i.e. base (2T - gl - n) + i of the reverse plane
+        const int64_t sub_lo = minus ? 2 * g->total_bases - gl - n + done : gl + done;
         const int blocks = (int)std::min<int64_t>(((m + 15) / 16 + 255) / 256, 148 * 16);
         k_fetch<<<std::max(blocks, 1), 256, 0, st>>>(g->d_packed, sub_lo, m, minus, g->d_exc_pos, g->d_exc_byte, g->n_exc, g->d_stage);
         MG_LAUNCH_CHECK();

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) k_plan_pieces(int64_t n_piece, int64_t n_
                                                      const int64_t *__restrict__ seg_end, const int8_t *__restrict__ seg_strand,
                                                      const int64_t *__restrict__ rec_lit_off, const int32_t *__restrict__ rec_pre,
                                                      const int32_t *__restrict__ rec_suf, const int64_t *__restrict__ contig_len,
-                                                     const int64_t *__restrict__ contig_base, int64_t n_contigs,
+                                                     const int64_t *__restrict__ contig_base, int64_t n_contigs, int64_t two_T,
                                                      int32_t *__restrict__ piece_len, int64_t *__restrict__ piece_src) {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n_piece) return;
@@ -59,8 +59,9 @@ __global__ void __launch_bounds__(256) k_plan_pieces(int64_t n_piece, int64_t n_
             src = contig_base[c] + i;
         }
         piece_len[p] = (int32_t)len;
-        const uint64_t kind = seg_strand[e] ? MG_KIND_RC : MG_KIND_FWD;
-        piece_src[p] = src | (int64_t)(kind << MG_KIND_SHIFT);
+        // '-' strand: forward bases [src, src+len) are bases [2T-src-len, 2T-src) of the reverse-complement plane,
+        // in exactly the order Sequence.reverse_compliment emits them (genome.py:784-793)
+        piece_src[p] = seg_strand[e] ? two_T - src - len : src;
     }
 }
 
@@ -215,7 +216,7 @@ extern "C" int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, i
     if (p->n_rec > 0) {
         k_plan_pieces<<<(unsigned)((p->n_piece + 255) / 256), 256, 0, st>>>(
             p->n_piece, p->n_rec, p->d_rec_seg_off, p->d_seg_contig, p->d_seg_start, p->d_seg_end, p->d_seg_strand,
-            p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, g->d_contig_len, g->d_contig_base, g->n_contigs,
+            p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, g->d_contig_len, g->d_contig_base, g->n_contigs, 2 * g->total_bases,
             p->d_piece_len, p->d_piece_src);
         MG_LAUNCH_CHECK();
         int rc = mg_scan_i32(p->d_piece_len, p->d_piece_off, p->n_piece, p->d_scan_tmp, p->scan_tmp_cap, st);

@@ -41,7 +41,7 @@ struct mg_sixframe_state {
     mg_orf *d_recs = nullptr;
     int32_t *d_len = nullptr;
     int64_t *d_aa_off = nullptr;                     // [n_orf+1]
-    int64_t *d_src = nullptr;                        // [n_orf] first base (plus) / one past last base | 1<<62 (minus)
+    int64_t *d_src = nullptr;                        // [n_orf] index of the ORF's first base (forward or reverse plane)
     int64_t *d_aa_tile = nullptr;
     int64_t n_aa_tile = 0;
     uint8_t *d_aa = nullptr;                         // library-owned residue buffer for the host variant
@@ -324,7 +324,7 @@ __device__ __forceinline__ int64_t layout_index(const TileInfo &ti, const int64_
 // WRITE == true: k-th kept ORF (ascending position) goes to slot0 + k ('+') or slot0 + (n_mine-1-k) ('-').
 template <bool WRITE>
 __device__ __forceinline__ int enumerate_stream(const TileInfo &ti, const SixMasks &sm, int s, int64_t x0, int64_t prev,
-                                                bool is_end_thread, int64_t min_aa, int64_t slot0, int n_mine,
+                                                bool is_end_thread, int64_t min_aa, int64_t two_T, int64_t slot0, int n_mine,
                                                 mg_orf *__restrict__ recs, int32_t *__restrict__ lens, int64_t *__restrict__ srcs) {
     if (ti.m[s] <= 0) return 0;                       // `if translated_seq:` (genome.py:832)
     const int plus = s & 1;
@@ -351,7 +351,7 @@ __device__ __forceinline__ int enumerate_stream(const TileInfo &ti, const SixMas
                     recs[slot] = o;
                     lens[slot] = (int32_t)ln;
                     const int64_t q = ti.cs[s] + 3 * st;            // oriented offset of the ORF's first base
-                    srcs[slot] = plus ? (ti.gb + q) : ((ti.gb + ti.L - q) | (int64_t)(1ull << MG_KIND_SHIFT));
+                    srcs[slot] = plus ? (ti.gb + q) : (two_T - ti.gb - ti.L + q);      // '-': forward read of the reverse plane
                 }
                 k++;
             }
@@ -392,7 +392,7 @@ template <bool EMIT>
 __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
     const uint32_t *__restrict__ packed, const int64_t *__restrict__ tile_base, int64_t nc, int64_t contig_lo,
     const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
-    const int64_t *__restrict__ m, int64_t n_tiles, const int64_t *__restrict__ carry, int64_t min_aa,
+    const int64_t *__restrict__ m, int64_t n_tiles, const int64_t *__restrict__ carry, int64_t min_aa, int64_t two_T,
     int32_t *__restrict__ cnt, const int64_t *__restrict__ cnt_off, mg_orf *__restrict__ recs, int32_t *__restrict__ lens,
     int64_t *__restrict__ srcs) {
     __shared__ TileInfo ti;
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
     int my_cnt[6];
 #pragma unroll
     for (int s = 0; s < 6; s++)
-        my_cnt[s] = active ? enumerate_stream<false>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, 0, 0, nullptr, nullptr, nullptr) : 0;
+        my_cnt[s] = active ? enumerate_stream<false>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, 0, 0, nullptr, nullptr, nullptr) : 0;
 
     if (!EMIT) {
 #pragma unroll
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
                 // '+': ascending, my first ORF has rank = exclusive prefix; '-': descending, ranks count from the top
                 const int64_t rank0 = (s & 1) ? inc - my_cnt[s] : tot - inc;
                 const int64_t slot0 = cnt_off[layout_index(ti, tile_base, contig_lo, s)] + rank0;
-                enumerate_stream<true>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, slot0, my_cnt[s], recs, lens, srcs);
+                enumerate_stream<true>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, slot0, my_cnt[s], recs, lens, srcs);
             }
         }
     }
@@ -532,20 +532,11 @@ __global__ void __launch_bounds__(AA_THREADS) k_six_aa(const uint32_t *__restric
             const int64_t a = pos - off_o;
             int c = 16 - filled;
             if (off_n - pos < c) c = (int)(off_n - pos);
-            const uint64_t sk = (uint64_t)__ldg(srcs + o);
-            const int64_t src = (int64_t)(sk & MG_SRC_MASK);
-            uint64_t acc[3] = {0, 0, 0};
-            if ((sk >> MG_KIND_SHIFT) == 0) {
-                const int64_t g0 = src + 3 * a;
-                acc[0] = mg_ld_nib16(packed, g0);
-                if (3 * c > 16) acc[1] = mg_ld_nib16(packed, g0 + 16);
-                if (3 * c > 32) acc[2] = mg_ld_nib16(packed, g0 + 32);
-            } else {
-                const int64_t e = src - 3 * a;               // one past the last (genome) base of the first codon
-                acc[0] = mg_rc_nib16(mg_ld_nib16(packed, e - 16));
-                if (3 * c > 16) acc[1] = mg_rc_nib16(mg_ld_nib16(packed, e - 32));
-                if (3 * c > 32) acc[2] = mg_rc_nib16(mg_ld_nib16(packed, e - 48));
-            }
+            const int64_t g0 = __ldg(srcs + o) + 3 * a;      // either plane, always a forward read
+            uint64_t acc[3];
+            acc[0] = mg_ld_nib16(packed, g0);
+            acc[1] = mg_ld_nib16(packed, g0 + 16);
+            acc[2] = mg_ld_nib16(packed, g0 + 32);
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 if (k < c) {
@@ -642,7 +633,7 @@ extern "C" int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig
     k_ms_apply<<<dim3((unsigned)nb, 6), MS_THREADS, 0, st>>>(s->d_tile_last, s->n_tiles, nb, s->d_chunk, s->d_carry);
     MG_LAUNCH_CHECK();
     k_six_orfs<false><<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, contig_lo, g->d_contig_len,
-                                                                   g->d_contig_base, s->d_cs, s->d_m, s->n_tiles, s->d_carry, min_aa,
+                                                                   g->d_contig_base, s->d_cs, s->d_m, s->n_tiles, s->d_carry, min_aa, 2 * g->total_bases,
                                                                    s->d_cnt, nullptr, nullptr, nullptr, nullptr);
     MG_LAUNCH_CHECK();
     s->scan_tmp_cap = mg_scan_tmp_elems(s->n_tiles * 6) + 2;
@@ -656,7 +647,7 @@ extern "C" int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig
         TRY(six_alloc(s, &s->d_src, s->n_orf));
         TRY(six_alloc(s, &s->d_aa_off, s->n_orf + 1));
         k_six_orfs<true><<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, contig_lo, g->d_contig_len,
-                                                                      g->d_contig_base, s->d_cs, s->d_m, s->n_tiles, s->d_carry, min_aa,
+                                                                      g->d_contig_base, s->d_cs, s->d_m, s->n_tiles, s->d_carry, min_aa, 2 * g->total_bases,
                                                                       nullptr, s->d_cnt_off, s->d_recs, s->d_len, s->d_src);
         MG_LAUNCH_CHECK();
         const int64_t need = mg_scan_tmp_elems(s->n_orf) + 2;
