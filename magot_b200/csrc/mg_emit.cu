@@ -20,9 +20,9 @@
 //        2 lanes, literal bytes by 1 lane) and the strand branch.
 //   r1c  (this file) * the genome keeps a second, reverse-complemented plane, so a '-' interval is a plain
 //        forward read: no strand branch, no register reversal (mg_common.cuh);
-//        * per tile, the GENOME pieces are compacted into shared memory (literal pieces and clamped-away
-//          empty ones dropped) so the first two pieces of every chunk are handled branch-free by all lanes;
-//          a third piece in 16 bytes is rare and takes a loop;
+//        * the first two GENOME pieces of every chunk are handled branch-free by all lanes (literal and
+//          clamped-away empty pieces are skipped by flag: at most two sit between two genome pieces in the
+//          common case); anything else in 16 bytes is rare and takes a loop;
 //        * literal bytes (">ID\n", "\n") are not touched here at all: a tiny second kernel writes them
 //          afterwards, one thread per record.
 #include <algorithm>
@@ -31,19 +31,19 @@
 
 #define NUC_THREADS 256
 #define NUC_CHUNKS (MG_NUC_TILE / 16 / NUC_THREADS)     // 4 chunks of 16 B per thread
-#define NUC_PPT 4                                        // raw pieces examined per thread while staging
-#define NUC_CAP (NUC_THREADS * NUC_PPT)                  // raw pieces staged per tile
+#define NUC_CAP 1024                                     // pieces staged per tile
 #define NUC_UNITS (MG_NUC_TILE / 64)
 
 #define PROT_THREADS 256
-#define PROT_CHUNKS (MG_PROT_TILE / 16 / PROT_THREADS)  // 2
-#define PROT_RPT 2
-#define PROT_RCAP (PROT_THREADS * PROT_RPT)              // records staged per tile
-#define PROT_PPT 6
-#define PROT_PCAP (PROT_THREADS * PROT_PPT)              // raw pieces staged per tile
+#define PROT_CHUNKS (MG_PROT_TILE / 16 / PROT_THREADS)  // 4
+#define PROT_RCAP 512                                    // records staged per tile
+#define PROT_PCAP 2048                                   // pieces staged per tile
 #define PROT_UNITS (MG_PROT_TILE / 64)
 
 #define BIG 0x7fffffff
+// 1: K2 patches literal bytes itself (1 lane, ~1.5 chunks per record); 0: k_emit_lit writes them afterwards.
+// Measured on B200 (config 4): inline 0.300 ms vs separate 0.204 + 0.027 ms per exon launch -> separate.
+#define MG_NUC_INLINE_LIT 0
 
 // expand the low 4 bits of x into a byte mask (bit k -> byte k = 0xFF)
 __device__ __forceinline__ uint32_t expand4(uint32_t x) {
@@ -55,39 +55,22 @@ __device__ __forceinline__ uint64_t nib_range_mask(int lo, int hi) {
     return ((~0ull) >> (64 - 4 * (hi - lo))) << (4 * lo);
 }
 
-// exclusive prefix sum of one int per thread across a 256-thread block; *total = block sum
-__device__ __forceinline__ int block_excl_scan256(int v, int *s_warp, int *total) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    if (lane == 31) s_warp[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        int w = lane < 8 ? s_warp[lane] : 0;
-#pragma unroll
-        for (int d = 1; d < 8; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, w, d);
-            if (lane >= d) w += t;
-        }
-        if (lane < 8) s_warp[lane] = w;
-    }
-    __syncthreads();
-    const int off = wid ? s_warp[wid - 1] : 0;
-    *total = s_warp[7];
-    __syncthreads();
-    return off + inc - v;
+// 16 bytes starting at byte index a of `lit` (a may be unaligned; the buffer is padded on both sides)
+__device__ __forceinline__ void ld_lit16(const uint8_t *__restrict__ lit, int64_t a, uint32_t w[4]) {
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(lit) + (a >> 2);
+    const uint32_t sh = ((uint32_t)a & 3u) << 3;
+    const uint32_t x0 = __ldg(p), x1 = __ldg(p + 1), x2 = __ldg(p + 2), x3 = __ldg(p + 3), x4 = __ldg(p + 4);
+    w[0] = __funnelshift_r(x0, x1, sh);
+    w[1] = __funnelshift_r(x1, x2, sh);
+    w[2] = __funnelshift_r(x2, x3, sh);
+    w[3] = __funnelshift_r(x3, x4, sh);
 }
 
 // ---- generic (slow, always correct) chunk assembly straight from global memory ------------------------------
 // Used for tiles whose piece list does not fit the shared-memory staging (thousands of tiny pieces per tile).
-// Writes genome bytes only; literal positions are left to k_emit_lit like in the fast path.
 __device__ __noinline__ void nuc_chunk_generic(const uint32_t *__restrict__ packed, const int64_t *__restrict__ piece_off,
                                                const int64_t *__restrict__ piece_src, int64_t j, int64_t P, int64_t total,
-                                               int64_t T, const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte,
+                                               int64_t T, const uint8_t *__restrict__ lit, const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte,
                                                int64_t n_exc, uint8_t *__restrict__ out) {
     uint32_t w[4] = {0, 0, 0, 0};
     int64_t off_j = __ldg(piece_off + j), off_n = __ldg(piece_off + j + 1);
@@ -95,7 +78,10 @@ __device__ __noinline__ void nuc_chunk_generic(const uint32_t *__restrict__ pack
         const int64_t pos = P + t;
         while (off_n <= pos) { j++; off_j = off_n; off_n = __ldg(piece_off + j + 1); }
         const uint64_t sk = (uint64_t)__ldg(piece_src + j);
-        if ((sk >> MG_KIND_SHIFT) == MG_KIND_LIT) continue;
+        if ((sk >> MG_KIND_SHIFT) == MG_KIND_LIT) {
+            w[t >> 2] |= (uint32_t)__ldg(lit + (int64_t)(sk & MG_SRC_MASK) + (pos - off_j)) << ((t & 3) * 8);
+            continue;
+        }
         const int64_t gi = (int64_t)(sk & MG_SRC_MASK) + (pos - off_j);
         const uint32_t code = (__ldg(packed + (gi >> 3)) >> (((uint32_t)gi & 7u) * 4)) & 15u;
         uint32_t d0, d1;
@@ -110,94 +96,102 @@ __device__ __noinline__ void nuc_chunk_generic(const uint32_t *__restrict__ pack
 // ---- K2 ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NUC_THREADS) k_emit_nuc(
     const uint32_t *__restrict__ packed, const int64_t *__restrict__ piece_off, const int64_t *__restrict__ piece_src,
-    int64_t n_piece, const int64_t *__restrict__ tile_first, int64_t total, int64_t T,
+    int64_t n_piece, const int64_t *__restrict__ tile_first, int64_t total, int64_t T, const uint8_t *__restrict__ lit,
     const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte, int64_t n_exc, uint8_t *__restrict__ out) {
-    // compacted genome pieces of the tile: text range [c_start, c_end) relative to the tile, and the nibble
-    // index that tile position 0 would have (index of position q = c_base + q)
-    __shared__ int64_t c_base[NUC_CAP + 2];
-    __shared__ int32_t c_start[NUC_CAP + 2], c_end[NUC_CAP + 2];
-    __shared__ uint16_t s_unit[NUC_UNITS];            // first compacted piece that ends after byte 64*u
-    __shared__ int s_warp[8];
+    // pieces of the tile: piece i covers text [s_rel[i], s_rel[i+1]) relative to the tile; the nibble index of
+    // tile position q is s_base[i] + q (byte index into lit[] for a literal piece); s_skip[i] = 1 for clamped-away
+    // empty pieces, 3 for literal pieces (bit 0 = "not a genome piece", bit 1 = literal)
+    __shared__ int64_t s_base[NUC_CAP + 4];
+    __shared__ int32_t s_rel[NUC_CAP + 5];
+    __shared__ uint8_t s_skip[NUC_CAP + 4];
+    __shared__ uint16_t s_unit[NUC_UNITS];            // piece holding byte 64*u of the tile
     const int64_t P0 = (int64_t)blockIdx.x * MG_NUC_TILE;
     const int64_t p_lo = tile_first[blockIdx.x];
     int64_t p_hi = tile_first[blockIdx.x + 1] + 1;    // one past the last piece this tile can touch
     if (p_hi > n_piece) p_hi = n_piece;
-    const int nraw = (int)min((int64_t)NUC_CAP, p_hi - p_lo);
+    const int ncache = (int)min((int64_t)NUC_CAP, p_hi - p_lo);
     const int tile_len = (int)min((int64_t)MG_NUC_TILE, total - P0);
-
-    // ---- stage: each thread examines NUC_PPT consecutive raw pieces, keeps the non-empty genome ones
-    int64_t kb[NUC_PPT];
-    int32_t ks[NUC_PPT], ke[NUC_PPT];
-    int nk = 0;
-    {
-        const int i0 = (int)threadIdx.x * NUC_PPT;
-        int64_t off = i0 < nraw ? __ldg(piece_off + p_lo + i0) : 0;
-#pragma unroll
-        for (int k = 0; k < NUC_PPT; k++) {
-            const int i = i0 + k;
-            if (i < nraw) {
-                const int64_t nxt = __ldg(piece_off + p_lo + i + 1);
-                const uint64_t sk = (uint64_t)__ldg(piece_src + p_lo + i);
-                const int64_t rs = off - P0, re = nxt - P0;
-                if ((sk >> MG_KIND_SHIFT) != MG_KIND_LIT && re > rs && re > 0 && rs < MG_NUC_TILE) {
-                    kb[nk] = (int64_t)(sk & MG_SRC_MASK) - rs;
-                    ks[nk] = rs < -BIG ? -BIG : (int32_t)rs;
-                    ke[nk] = re > MG_NUC_TILE ? MG_NUC_TILE : (int32_t)re;
-                    nk++;
-                }
-                off = nxt;
-            }
+    for (int i = threadIdx.x; i < ncache + 4; i += NUC_THREADS) {
+        if (i <= ncache) {
+            const int64_t rel = __ldg(piece_off + p_lo + i) - P0;      // > -2^31: piece lengths are int32
+            s_rel[i] = rel > MG_NUC_TILE ? MG_NUC_TILE : (int32_t)rel;
+        } else {
+            s_rel[i] = BIG;
+        }
+        if (i < ncache) {
+            const int64_t rel = __ldg(piece_off + p_lo + i) - P0;
+            const uint64_t sk = (uint64_t)__ldg(piece_src + p_lo + i);
+            s_base[i] = (int64_t)(sk & MG_SRC_MASK) - rel;
+            s_skip[i] = (sk >> MG_KIND_SHIFT) == MG_KIND_LIT ? 3 : (__ldg(piece_off + p_lo + i + 1) - P0 == rel ? 1 : 0);
+        } else {
+            s_base[i] = 0;
+            s_skip[i] = 1;                            // nothing beyond the staged pieces may be selected as A or B
         }
     }
-    int n_c;
-    const int my0 = block_excl_scan256(nk, s_warp, &n_c);
-#pragma unroll
-    for (int k = 0; k < NUC_PPT; k++) {
-        if (k < nk) { c_base[my0 + k] = kb[k]; c_start[my0 + k] = ks[k]; c_end[my0 + k] = ke[k]; }
-    }
-    if (threadIdx.x < 2) { c_start[n_c + threadIdx.x] = BIG; c_end[n_c + threadIdx.x] = BIG; c_base[n_c + threadIdx.x] = 0; }
+    if (threadIdx.x == 0) s_rel[ncache + 4] = BIG;
     __syncthreads();
-    for (int i = threadIdx.x; i <= n_c; i += NUC_THREADS) {
-        const int e0 = i ? c_end[i - 1] : 0, e1 = i < n_c ? c_end[i] : MG_NUC_TILE;
-        const int u1 = min((e1 + 63) >> 6, NUC_UNITS);
-        for (int u = i ? ((e0 + 63) >> 6) : 0; u < u1; u++) s_unit[u] = (uint16_t)i;
+    for (int i = threadIdx.x; i < ncache; i += NUC_THREADS) {
+        const int r0 = s_rel[i] < 0 ? 0 : s_rel[i], r1 = s_rel[i + 1] < 0 ? 0 : s_rel[i + 1];
+        const int u1 = min((r1 + 63) >> 6, NUC_UNITS);
+        for (int u = (r0 + 63) >> 6; u < u1; u++) s_unit[u] = (uint16_t)i;
     }
     __syncthreads();
-    // text position (tile-relative) up to which the staged pieces are complete
-    const int covered = (p_hi - p_lo > NUC_CAP) ? (int)min((int64_t)MG_NUC_TILE, __ldg(piece_off + p_lo + NUC_CAP) - P0) : MG_NUC_TILE;
+    const int covered = s_rel[ncache];                // tile-relative position where the staged pieces end
 
 #pragma unroll 1
     for (int cidx = 0; cidx < NUC_CHUNKS; cidx++) {
         const int p = (cidx * NUC_THREADS + (int)threadIdx.x) << 4;
         if (p >= tile_len) break;
-        if (p + 16 > covered) {                        // staging overflowed: slow path
+        if (p + 16 > covered && covered < tile_len) {  // staging overflowed: slow path
             const int64_t j = mg_search_le(piece_off, p_lo, n_piece, P0 + p);
-            nuc_chunk_generic(packed, piece_off, piece_src, j, P0 + p, total, T, exc_pos, exc_byte, n_exc, out);
+            nuc_chunk_generic(packed, piece_off, piece_src, j, P0 + p, total, T, lit, exc_pos, exc_byte, n_exc, out);
             continue;
         }
-        int A = s_unit[p >> 6];
-        while (c_end[A] <= p) A++;
-        // first two genome pieces of the chunk, branch-free
-        const int sA = c_start[A], eA = c_end[A], sB = c_start[A + 1], eB = c_end[A + 1];
-        const bool hasA = sA < p + 16, hasB = sB < p + 16;
-        const int64_t gA = hasA ? c_base[A] + p : MG_FRONT_PAD;
-        const int64_t gB = hasB ? c_base[A + 1] + p : MG_FRONT_PAD;
-        uint64_t vA = mg_ld_nib16(packed, gA);
-        uint64_t vB = mg_ld_nib16(packed, gB);
-        const int loA = max(sA - p, 0), hiA = min(eA - p, 16);
-        const int loB = max(sB - p, 0), hiB = min(eB - p, 16);
-        vA = hasA ? (vA & nib_range_mask(loA, hiA)) : 0ull;
-        vB = hasB ? (vB & nib_range_mask(loB, hiB)) : 0ull;
-        uint64_t nacc = vA | vB;
-        if (hasB && c_start[A + 2] < p + 16) {         // three or more genome pieces inside 16 bytes: rare
-            for (int j = A + 2; c_start[j] < p + 16; j++) {
-                const int lo = c_start[j] - p, hi = min(c_end[j] - p, 16);
-                nacc |= mg_ld_nib16(packed, c_base[j] + p) & nib_range_mask(lo, hi);
+        int j = s_unit[p >> 6];
+        while (s_rel[j + 1] <= p) j++;
+        // first two genome pieces of the chunk, branch-free; up to two skippable pieces (suffix + prefix literal)
+        // may sit in front of each
+        int A = j;
+        A += s_skip[A] & 1;
+        A += s_skip[A] & 1;
+        int B = A + 1;
+        B += s_skip[B] & 1;
+        B += s_skip[B] & 1;
+        const int sA = s_rel[A], eA = s_rel[A + 1], sB = s_rel[B], eB = s_rel[B + 1];
+        const bool okA = !s_skip[A] && sA < p + 16, okB = okA && !s_skip[B] && sB < p + 16;
+        const uint64_t vA = mg_ld_nib16(packed, okA ? s_base[A] + p : (int64_t)MG_FRONT_PAD);
+        const uint64_t vB = mg_ld_nib16(packed, okB ? s_base[B] + p : (int64_t)MG_FRONT_PAD);
+        uint64_t nacc = 0;
+        if (okA) nacc = vA & nib_range_mask(max(sA - p, 0), min(eA - p, 16));   // literal positions stay 0 and are patched below
+        if (okB) nacc |= vB & nib_range_mask(sB - p, min(eB - p, 16));
+        // anything beyond that inside these 16 bytes (a third genome piece, chains of blank records): rare
+        const bool more = (s_skip[A] && sA < p + 16) || (okA && s_skip[B] && sB < p + 16) || (okB && eB < p + 16);
+        if (more) {
+            nacc = 0;
+            for (int k = j; k < ncache && s_rel[k] < p + 16; k++) {
+                if (!s_skip[k]) nacc |= mg_ld_nib16(packed, s_base[k] + p) & nib_range_mask(max(s_rel[k] - p, 0), min(s_rel[k + 1] - p, 16));
             }
         }
         uint32_t w0, w1, w2, w3;
         mg_decode8((uint32_t)nacc, w0, w1);
         mg_decode8((uint32_t)(nacc >> 32), w2, w3);
+        // literal bytes (">ID\n", "\n") inside this chunk: skipped pieces in front of A, or right behind A inside the
+        // chunk.  About 1.5 chunks per record take this path; a suffix and the following prefix that are adjacent in
+        // lit[] share one 16-byte window load.
+        if (MG_NUC_INLINE_LIT && (A != j || (okA && B != A + 1 && eA < p + 16) || more)) {
+            uint32_t lw[4] = {0, 0, 0, 0};
+            int64_t last = INT64_MIN;
+            for (int k = j; k < ncache && s_rel[k] < p + 16; k++) {
+                if ((s_skip[k] & 2) && s_rel[k + 1] > s_rel[k]) {
+                    if (s_base[k] != last) { ld_lit16(lit, s_base[k] + p, lw); last = s_base[k]; }
+                    const int lo = max(s_rel[k] - p, 0), hi = min(s_rel[k + 1] - p, 16);
+                    const uint32_t m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+                    const uint32_t m0 = expand4(m), m1 = expand4(m >> 4), m2 = expand4(m >> 8), m3 = expand4(m >> 12);
+                    w0 = (w0 & ~m0) | (lw[0] & m0); w1 = (w1 & ~m1) | (lw[1] & m1);
+                    w2 = (w2 & ~m2) | (lw[2] & m2); w3 = (w3 & ~m3) | (lw[3] & m3);
+                }
+            }
+        }
         // code 15 = byte outside the packed alphabet on a '+' piece (the reverse plane already holds 'n',
         // genome.py:791-792): fetch the exact byte the FASTA had (genome.py:606 keeps it).  Rare.
         uint64_t e = nacc & (nacc >> 1) & (nacc >> 2) & (nacc >> 3) & 0x1111111111111111ull;
@@ -206,9 +200,9 @@ __global__ void __launch_bounds__(NUC_THREADS) k_emit_nuc(
             while (e) {
                 const int t = (__ffsll((long long)e) - 1) >> 2;
                 e &= e - 1;
-                int jj = A;
-                while (c_end[jj] <= p + t) jj++;
-                const int64_t gi = c_base[jj] + p + t;
+                int jj = j;
+                while (s_rel[jj + 1] <= p + t) jj++;
+                const int64_t gi = s_base[jj] + p + t;
                 if (gi < T) {
                     const uint32_t b = mg_exc_byte(exc_pos, exc_byte, n_exc, gi);
                     w[t >> 2] = (w[t >> 2] & ~(0xFFu << ((t & 3) * 8))) | (b << ((t & 3) * 8));
@@ -220,8 +214,8 @@ __global__ void __launch_bounds__(NUC_THREADS) k_emit_nuc(
     }
 }
 
-// ---- literal framing bytes (">ID\n" prefixes, "\n" suffixes): one thread per literal piece -------------------
-// Runs AFTER the main kernel on the same stream and overwrites the placeholder bytes it left there.
+// ---- literal framing bytes of the PROTEIN text (">ID\n" prefixes, "\n" suffixes): one thread per literal piece ---
+// Runs AFTER k_emit_prot on the same stream and overwrites the placeholder bytes it left there (K2 writes its own).
 // which = 0: nucleotide text (positions from piece_off); which = 1: protein text (positions from prot_off).
 __global__ void __launch_bounds__(256) k_emit_lit(int which, int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
                                                   const int64_t *__restrict__ piece_off, const int64_t *__restrict__ prot_off,
@@ -283,16 +277,15 @@ __global__ void __launch_bounds__(PROT_THREADS) k_emit_prot(
     const int8_t *__restrict__ rec_skip, const int32_t *__restrict__ rec_pre, int64_t n_rec,
     const int64_t *__restrict__ tile_first, int64_t total, const uint8_t *__restrict__ aa4096, uint8_t *__restrict__ out) {
     __shared__ __align__(16) uint8_t s_aa[4096];
-    // compacted records (those with residues inside the tile): residue range [r_s, r_e) in the protein text relative to
-    // the tile, nucleotide-text position (relative to O) of the codon of residue 0, first compacted piece
+    // records of the tile: residues occupy protein-text positions [r_s[i], r_e[i]) relative to the tile (empty when the
+    // record has none); r_q0 = nucleotide-text position (relative to O) of the codon that would land on tile position 0;
+    // r_j0 = first segment piece of the record (tile-local index)
     __shared__ int32_t r_s[PROT_RCAP + 2], r_e[PROT_RCAP + 2], r_q0[PROT_RCAP + 2];
     __shared__ int16_t r_j0[PROT_RCAP + 2];
-    // compacted genome pieces of those records: nucleotide-text range relative to O, nibble index of position O
-    __shared__ int64_t c_base[PROT_PCAP + 2];
-    __shared__ int32_t c_start[PROT_PCAP + 2], c_end[PROT_PCAP + 2];
-    __shared__ int16_t s_cidx[PROT_PCAP + 1];         // raw piece -> compacted index
+    // pieces of those records: piece i covers nucleotide-text [s_rel[i], s_rel[i+1]) relative to O
+    __shared__ int64_t s_base[PROT_PCAP + 4];
+    __shared__ int32_t s_rel[PROT_PCAP + 5];
     __shared__ uint16_t s_unit[PROT_UNITS];
-    __shared__ int s_warp[8];
     reinterpret_cast<uint4 *>(s_aa)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(aa4096) + threadIdx.x);
     const int64_t P0 = (int64_t)blockIdx.x * MG_PROT_TILE;
     const int64_t r_lo = tile_first[blockIdx.x];
@@ -316,85 +309,39 @@ __global__ void __launch_bounds__(PROT_THREADS) k_emit_prot(
         return;
     }
     const int nraw = (int)nraw64;
-    // ---- stage genome pieces
-    int n_c;
-    {
-        int64_t kb[PROT_PPT];
-        int32_t ks[PROT_PPT], ke[PROT_PPT];
-        int nk = 0;
-        uint32_t kept = 0;                            // bit k: raw piece i0+k was kept
-        const int i0 = (int)threadIdx.x * PROT_PPT;
-        int64_t off = i0 < nraw ? __ldg(piece_off + pc_lo + i0) : 0;
-#pragma unroll
-        for (int k = 0; k < PROT_PPT; k++) {
-            const int i = i0 + k;
-            if (i < nraw) {
-                const int64_t nxt = __ldg(piece_off + pc_lo + i + 1);
-                const uint64_t sk = (uint64_t)__ldg(piece_src + pc_lo + i);
-                if ((sk >> MG_KIND_SHIFT) != MG_KIND_LIT && nxt > off) {
-                    const int32_t rs = (int32_t)(off - O);
-                    kb[nk] = (int64_t)(sk & MG_SRC_MASK) - rs;
-                    ks[nk] = rs;
-                    ke[nk] = (int32_t)(nxt - O);
-                    nk++;
-                    kept |= 1u << k;
-                }
-                off = nxt;
-            }
+    for (int i = threadIdx.x; i < nraw + 4; i += PROT_THREADS) {
+        if (i <= nraw) {
+            const int32_t rel = (int32_t)(__ldg(piece_off + pc_lo + i) - O);
+            s_rel[i] = rel;
+            s_base[i] = i < nraw ? (int64_t)((uint64_t)__ldg(piece_src + pc_lo + i) & MG_SRC_MASK) - rel : 0;
+        } else {
+            s_rel[i] = BIG;
+            s_base[i] = 0;
         }
-        int c = block_excl_scan256(nk, s_warp, &n_c);
-        int kk = 0;
-#pragma unroll
-        for (int k = 0; k < PROT_PPT; k++) {
-            const int i = i0 + k;
-            if (i < nraw) {
-                s_cidx[i] = (int16_t)c;               // raw piece -> index of the first kept piece at or after it
-                if (kept & (1u << k)) {
-                    c_base[c] = kb[kk]; c_start[c] = ks[kk]; c_end[c] = ke[kk];
-                    c++; kk++;
-                }
-            }
+    }
+    if (threadIdx.x == 0) s_rel[nraw + 4] = BIG;
+    for (int i = threadIdx.x; i < nrec + 2; i += PROT_THREADS) {
+        if (i < nrec) {
+            const int64_t r = r_lo + i;
+            int32_t naa = rec_aa[r];
+            if (naa < 0) naa = 0;
+            const int64_t rs = __ldg(prot_off + r) + rec_pre[r] - P0, re = rs + naa;
+            const int64_t f0 = __ldg(rec_seg_off + r) + 2 * r;
+            r_s[i] = rs < -BIG ? -BIG : (rs > MG_PROT_TILE ? MG_PROT_TILE : (int32_t)rs);
+            r_e[i] = re < -BIG ? -BIG : (re > MG_PROT_TILE ? MG_PROT_TILE : (int32_t)re);
+            r_q0[i] = (int32_t)(__ldg(piece_off + f0 + 1) - O) + rec_skip[r] - 3 * (int32_t)rs;
+            r_j0[i] = (int16_t)(f0 + 1 - pc_lo);
+        } else {
+            r_s[i] = BIG; r_e[i] = BIG; r_q0[i] = 0; r_j0[i] = (int16_t)(nraw + 1);   // so that r_j0[R+1]-2 is the last record's suffix piece
         }
-        if (threadIdx.x == 0) s_cidx[nraw] = (int16_t)n_c;
-        if (threadIdx.x < 2) { c_start[n_c + threadIdx.x] = BIG; c_end[n_c + threadIdx.x] = BIG; c_base[n_c + threadIdx.x] = 0; }
     }
     __syncthreads();
-    // ---- stage records
-    int n_r;
-    {
-        int32_t a_s[PROT_RPT], a_e[PROT_RPT], a_q[PROT_RPT];
-        int16_t a_j[PROT_RPT];
-        int nk = 0;
-#pragma unroll
-        for (int k = 0; k < PROT_RPT; k++) {
-            const int i = (int)threadIdx.x * PROT_RPT + k;
-            if (i < nrec) {
-                const int64_t r = r_lo + i;
-                int32_t naa = rec_aa[r];
-                if (naa > 0) {
-                    const int64_t rs = __ldg(prot_off + r) + rec_pre[r] - P0, re = rs + naa;
-                    if (re > 0 && rs < MG_PROT_TILE) {
-                        const int64_t f0 = __ldg(rec_seg_off + r) + 2 * r;
-                        a_s[nk] = rs < -BIG ? -BIG : (int32_t)rs;
-                        a_e[nk] = re > MG_PROT_TILE ? MG_PROT_TILE : (int32_t)re;
-                        // codon of the residue that would sit at tile position 0 (may be "before" the record)
-                        a_q[nk] = (int32_t)(__ldg(piece_off + f0 + 1) - O) + rec_skip[r] - 3 * (int32_t)rs;
-                        a_j[nk] = s_cidx[f0 + 1 - pc_lo];
-                        nk++;
-                    }
-                }
-            }
-        }
-        const int my0 = block_excl_scan256(nk, s_warp, &n_r);
-#pragma unroll
-        for (int k = 0; k < PROT_RPT; k++) {
-            if (k < nk) { r_s[my0 + k] = a_s[k]; r_e[my0 + k] = a_e[k]; r_q0[my0 + k] = a_q[k]; r_j0[my0 + k] = a_j[k]; }
-        }
-        if (threadIdx.x < 2) { r_s[n_r + threadIdx.x] = BIG; r_e[n_r + threadIdx.x] = BIG; r_q0[n_r + threadIdx.x] = 0; r_j0[n_r + threadIdx.x] = (int16_t)n_c; }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i <= n_r; i += PROT_THREADS) {
-        const int e0 = i ? r_e[i - 1] : 0, e1 = i < n_r ? r_e[i] : MG_PROT_TILE;
+    // unit u -> first record whose residues end after byte 64*u
+    for (int i = threadIdx.x; i <= nrec; i += PROT_THREADS) {
+        int e0 = 0;
+        if (i) { e0 = r_e[i - 1]; if (e0 < 0) e0 = 0; }
+        int e1 = i < nrec ? r_e[i] : MG_PROT_TILE;
+        if (e1 < 0) e1 = 0;
         const int u1 = min((e1 + 63) >> 6, PROT_UNITS);
         for (int u = i ? ((e0 + 63) >> 6) : 0; u < u1; u++) s_unit[u] = (uint16_t)i;
     }
@@ -409,36 +356,39 @@ __global__ void __launch_bounds__(PROT_THREADS) k_emit_prot(
         uint32_t bw0 = 0, bw1 = 0, bw2 = 0, bw3 = 0;
         for (; r_s[R] < p + 16; R++) {                // records with residues inside this chunk (usually one)
             const int lo = max(r_s[R] - p, 0), hi = min(r_e[R] - p, 16);
+            if (hi <= lo) continue;                   // record without residues
             // nucleotide-text position (relative to O) of the codon that lands on chunk position 0
             const int q = r_q0[R] + 3 * p;
             const int need_lo = q + 3 * lo, need_hi = q + 3 * hi;        // nibbles [need_lo, need_hi)
             int j = r_j0[R];
-            {   // first piece of the record that ends after need_lo (pieces of a record are contiguous)
-                int a = j, b = r_j0[R + 1];
+            {   // last piece of the record that starts at or before need_lo (its pieces are contiguous)
+                int a = j, b = r_j0[R + 1] - 2;       // one past the record's last segment piece
                 while (b - a > 1) {
                     const int mid = (a + b) >> 1;
-                    if (c_start[mid] <= need_lo) a = mid; else b = mid;
+                    if (s_rel[mid] <= need_lo) a = mid; else b = mid;
                 }
                 j = a;
             }
             uint64_t acc[3];
 #pragma unroll
             for (int g = 0; g < 3; g++) {
-                const int w_lo = max(q + 16 * g, need_lo), w_hi = min(q + 16 * g + 16, need_hi);
+                const int qg = q + 16 * g;
+                const int w_lo = max(qg, need_lo), w_hi = min(qg + 16, need_hi);
                 uint64_t a = 0;
                 if (w_hi > w_lo) {
-                    while (c_end[j] <= w_lo) j++;
-                    const int qg = q + 16 * g;
-                    // first two pieces of this 16-nibble group, branch-free
-                    const int sA = c_start[j], eA = c_end[j], sB = c_start[j + 1], eB = c_end[j + 1];
-                    const bool hasB = sB < w_hi;
-                    const uint64_t vA = mg_ld_nib16(packed, c_base[j] + qg);
-                    const uint64_t vB = mg_ld_nib16(packed, hasB ? c_base[j + 1] + qg : (int64_t)MG_FRONT_PAD);
+                    while (s_rel[j + 1] <= w_lo) j++;
+                    // first two pieces of this 16-nibble group, branch-free (segment pieces of a record are adjacent)
+                    const int sA = s_rel[j], eA = s_rel[j + 1], eB = s_rel[j + 2];
+                    const bool hasB = eA < w_hi && eB > eA;
+                    const uint64_t vA = mg_ld_nib16(packed, s_base[j] + qg);
+                    const uint64_t vB = mg_ld_nib16(packed, hasB ? s_base[j + 1] + qg : (int64_t)MG_FRONT_PAD);
                     a = vA & nib_range_mask(max(sA, w_lo) - qg, min(eA, w_hi) - qg);
-                    if (hasB) a |= vB & nib_range_mask(sB - qg, min(eB, w_hi) - qg);
-                    if (hasB && c_start[j + 2] < w_hi) {
-                        for (int jj = j + 2; c_start[jj] < w_hi; jj++)
-                            a |= mg_ld_nib16(packed, c_base[jj] + qg) & nib_range_mask(c_start[jj] - qg, min(c_end[jj], w_hi) - qg);
+                    if (hasB) a |= vB & nib_range_mask(eA - qg, min(eB, w_hi) - qg);
+                    if (eA < w_hi && (!hasB || eB < w_hi)) {           // more than two pieces in 16 nibbles: rare
+                        for (int jj = j + 1; s_rel[jj] < w_hi; jj++) {
+                            if (s_rel[jj + 1] > s_rel[jj] && (jj > j + 1 || !hasB))
+                                a |= mg_ld_nib16(packed, s_base[jj] + qg) & nib_range_mask(s_rel[jj] - qg, min(s_rel[jj + 1], w_hi) - qg);
+                        }
                     }
                 }
                 acc[g] = a;
@@ -483,9 +433,9 @@ extern "C" int mg_emit_nuc_device(mg_plan *p, uint8_t *out_dev, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     p->last_stream = st;
     k_emit_nuc<<<(unsigned)p->n_nuc_tile, NUC_THREADS, 0, st>>>(g->d_packed, p->d_piece_off, p->d_piece_src, p->n_piece, p->d_nuc_tile,
-                                                              p->nuc_total, g->total_bases, g->d_exc_pos, g->d_exc_byte, g->n_exc, out_dev);
+                                                              p->nuc_total, g->total_bases, p->d_lit, g->d_exc_pos, g->d_exc_byte, g->n_exc, out_dev);
     MG_LAUNCH_CHECK();
-    if (p->n_lit > 0) {
+    if (!MG_NUC_INLINE_LIT && p->n_lit > 0) {
         k_emit_lit<<<(unsigned)((2 * p->n_rec + 255) / 256), 256, 0, st>>>(0, p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_prot_off,
                                                                          p->d_rec_aa, p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, p->d_lit, out_dev);
         MG_LAUNCH_CHECK();
