@@ -330,9 +330,9 @@ def gpu_arm(args):
     # ---- device-resident plans + output buffers
     plans = {k: create_plan(k) for k in tables}
     sizes = {k: prepare(plans[k]) for k in tables}
-    out_cds_n = torch.empty((sizes["cds"][0] + 15) // 16 * 16, dtype=torch.uint8, device=dev)
-    out_cds_p = torch.empty((sizes["cds"][1] + 15) // 16 * 16, dtype=torch.uint8, device=dev)
-    out_exon_n = torch.empty((sizes["exon"][0] + 15) // 16 * 16, dtype=torch.uint8, device=dev)
+    out_cds_n = torch.empty((sizes["cds"][0] + 31) // 32 * 32, dtype=torch.uint8, device=dev)
+    out_cds_p = torch.empty((sizes["cds"][1] + 31) // 32 * 32, dtype=torch.uint8, device=dev)
+    out_exon_n = torch.empty((sizes["exon"][0] + 31) // 32 * 32, dtype=torch.uint8, device=dev)
     d2h_bytes = sizes["cds"][0] + sizes["cds"][1] + sizes["exon"][0]
     ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
     nuc_events = []

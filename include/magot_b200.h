@@ -99,8 +99,8 @@ int mg_plan_lengths(mg_plan *p, int64_t *nuc_len, int64_t *aa_len, void *stream)
 
 /* ---- K2: spliced nucleotides (+ per-segment reverse complement, + literal framing) ---------
  * replaces ParentAnnotation.get_fasta seq_type="nucleotide" (genome.py:687-710) and
- * Sequence.reverse_compliment (genome.py:784-793).  `out_dev` must be 16-byte aligned and hold
- * nuc_total rounded up to a multiple of 16 bytes.                                            */
+ * Sequence.reverse_compliment (genome.py:784-793).  `out_dev` must be 32-byte aligned and hold
+ * nuc_total rounded up to a multiple of 32 bytes (each lane issues one 256-bit store).                                            */
 int mg_emit_nuc_device(mg_plan *p, uint8_t *out_dev, void *stream);
 /* ---- K3: protein -- replaces Sequence.translate(frame=0,strand='+') (genome.py:795-822) on the
  * spliced sequence (genome.py:707).  Same buffer rules with prot_total.                     */

@@ -30,7 +30,7 @@
 #include "mg_gather.cuh"
 
 #define NUC_THREADS 256
-#define NUC_CHUNKS (MG_NUC_TILE / 16 / NUC_THREADS)     // 4 chunks of 16 B per thread
+#define NUC_CHUNKS (MG_NUC_TILE / 32 / NUC_THREADS)     // 2 chunks of 32 B per thread
 #define NUC_CAP 1024                                     // pieces staged per tile
 #define NUC_UNITS (MG_NUC_TILE / 64)
 
@@ -41,9 +41,6 @@
 #define PROT_UNITS (MG_PROT_TILE / 64)
 
 #define BIG 0x7fffffff
-// 1: K2 patches literal bytes itself (1 lane, ~1.5 chunks per record); 0: k_emit_lit writes them afterwards.
-// Measured on B200 (config 4): inline 0.300 ms vs separate 0.204 + 0.027 ms per exon launch -> separate.
-#define MG_NUC_INLINE_LIT 0
 
 // expand the low 4 bits of x into a byte mask (bit k -> byte k = 0xFF)
 __device__ __forceinline__ uint32_t expand4(uint32_t x) {
@@ -66,44 +63,124 @@ __device__ __forceinline__ void ld_lit16(const uint8_t *__restrict__ lit, int64_
     w[3] = __funnelshift_r(x3, x4, sh);
 }
 
-// ---- generic (slow, always correct) chunk assembly straight from global memory ------------------------------
-// Used for tiles whose piece list does not fit the shared-memory staging (thousands of tiny pieces per tile).
+// 32 consecutive nibbles starting at global base index g, as four words
+__device__ __forceinline__ void ld_nib32(const uint32_t *__restrict__ pk, int64_t g, uint32_t n[4]) {
+    const uint32_t *q = pk + (g >> 3);
+    const uint32_t sh = ((uint32_t)g & 7u) << 2;
+    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3), w4 = __ldg(q + 4);
+    n[0] = __funnelshift_r(w0, w1, sh);
+    n[1] = __funnelshift_r(w1, w2, sh);
+    n[2] = __funnelshift_r(w2, w3, sh);
+    n[3] = __funnelshift_r(w3, w4, sh);
+}
+
+__device__ __forceinline__ void st32(uint8_t *p, const uint32_t w[8]) {          // one 256-bit store (STG.E.ENL2.256)
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
+// ---- generic (slow, always correct) assembly of one 32-byte chunk straight from global memory -------------------
+// Walks the piece table from piece j (piece_off[j] <= P), genome and literal pieces alike.  Used by the literal-chunk
+// kernel (every chunk that contains framing bytes) and by K2 for tiles whose piece list overflows its staging.
 __device__ __noinline__ void nuc_chunk_generic(const uint32_t *__restrict__ packed, const int64_t *__restrict__ piece_off,
                                                const int64_t *__restrict__ piece_src, int64_t j, int64_t P, int64_t total,
-                                               int64_t T, const uint8_t *__restrict__ lit, const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte,
-                                               int64_t n_exc, uint8_t *__restrict__ out) {
-    uint32_t w[4] = {0, 0, 0, 0};
+                                               int64_t T, const uint8_t *__restrict__ lit, const int64_t *__restrict__ exc_pos,
+                                               const uint8_t *__restrict__ exc_byte, int64_t n_exc, uint8_t *__restrict__ out) {
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t off_j = __ldg(piece_off + j), off_n = __ldg(piece_off + j + 1);
-    for (int t = 0; t < 16 && P + t < total; t++) {
-        const int64_t pos = P + t;
-        while (off_n <= pos) { j++; off_j = off_n; off_n = __ldg(piece_off + j + 1); }
+    const int end = (int)min((int64_t)32, total - P);
+    int t = 0;
+    while (t < end) {
+        while (off_n <= P + t) { j++; off_j = off_n; off_n = __ldg(piece_off + j + 1); }
         const uint64_t sk = (uint64_t)__ldg(piece_src + j);
+        const int64_t src = (int64_t)(sk & MG_SRC_MASK) + (P - off_j);           // source index of chunk position 0
+        const int hi = (int)min((int64_t)end, off_n - P);
+        const uint32_t m = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << t) - 1u);   // chunk positions [t, hi)
+        uint32_t b[8];
         if ((sk >> MG_KIND_SHIFT) == MG_KIND_LIT) {
-            w[t >> 2] |= (uint32_t)__ldg(lit + (int64_t)(sk & MG_SRC_MASK) + (pos - off_j)) << ((t & 3) * 8);
-            continue;
+            ld_lit16(lit, src, b);
+            ld_lit16(lit, src + 16, b + 4);
+        } else {
+            uint32_t n[4];
+            ld_nib32(packed, src, n);
+#pragma unroll
+            for (int k = 0; k < 4; k++) mg_decode8(n[k], b[2 * k], b[2 * k + 1]);
+            if (n_exc > 0 && src < T) {
+                for (int q = t; q < hi; q++) {
+                    if (((n[q >> 3] >> ((q & 7) * 4)) & 15u) == MG_CODE_EXC) {
+                        const uint32_t c = mg_exc_byte(exc_pos, exc_byte, n_exc, src + q);
+                        b[q >> 2] = (b[q >> 2] & ~(0xFFu << ((q & 3) * 8))) | (c << ((q & 3) * 8));
+                    }
+                }
+            }
         }
-        const int64_t gi = (int64_t)(sk & MG_SRC_MASK) + (pos - off_j);
-        const uint32_t code = (__ldg(packed + (gi >> 3)) >> (((uint32_t)gi & 7u) * 4)) & 15u;
-        uint32_t d0, d1;
-        mg_decode8(code, d0, d1);
-        uint32_t b = d0 & 0xFFu;
-        if (code == MG_CODE_EXC && gi < T) b = mg_exc_byte(exc_pos, exc_byte, n_exc, gi);
-        w[t >> 2] |= b << ((t & 3) * 8);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t mk = expand4(m >> (4 * k));
+            w[k] = (w[k] & ~mk) | (b[k] & mk);
+        }
+        t = hi;
     }
-    mg_st16(out + P, w[0], w[1], w[2], w[3]);
+    st32(out + P, w);
+}
+
+
+// rare path of K2: three or more pieces, or framing bytes, inside one 32-byte chunk: walk every staged piece.
+// Literal positions are left as placeholders (k_emit_lit writes them).
+__device__ __noinline__ void nuc_chunk_many(const uint32_t *__restrict__ packed, const int64_t *s_base, const int32_t *s_rel,
+                                            const uint8_t *s_kind, int A, int ncache, int p, int end, uint32_t n[4]) {
+    n[0] = n[1] = n[2] = n[3] = 0;
+    int lo = max(s_rel[A] - p, 0);
+    for (int k = A; k < ncache && s_rel[k] - p < end; k++) {
+        if (s_kind[k] == 1) continue;
+        const int hi = min(s_rel[k + 1] - p, end);
+        if (s_kind[k] == 2) { lo = hi; continue; }
+        uint32_t v[4];
+        ld_nib32(packed, s_base[k] + p, v);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int a = min(max(lo - 8 * q, 0), 8), b = min(max(hi - 8 * q, 0), 8);
+            const uint32_t m = b > a ? ((0xFFFFFFFFu >> (32 - 4 * (b - a))) << (4 * a)) : 0u;
+            n[q] |= v[q] & m;
+        }
+        lo = hi;
+    }
+}
+
+// rare path of K2: replace the placeholder of every code-15 nibble by the byte the FASTA had
+__device__ __noinline__ void nuc_patch_exceptions(const int64_t *s_base, const int32_t *s_rel, const uint8_t *s_kind, int A, int p,
+                                                  int end, int64_t T,
+                                                  const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte,
+                                                  int64_t n_exc, const uint32_t n[4], uint32_t w[8]) {
+    for (int t = 0; t < end; t++) {
+        if (((n[t >> 3] >> ((t & 7) * 4)) & 15u) != MG_CODE_EXC) continue;
+        int jj = A;
+        while (s_rel[jj + 1] - p <= t) jj++;
+        if (s_kind[jj] != 0) continue;                 // literal position: placeholder nibble, not a genome base
+        const int64_t gi = s_base[jj] + p + t;
+        if (gi < T) {
+            const uint32_t b = mg_exc_byte(exc_pos, exc_byte, n_exc, gi);
+            w[t >> 2] = (w[t >> 2] & ~(0xFFu << ((t & 3) * 8))) | (b << ((t & 3) * 8));
+        }
+    }
 }
 
 // ---- K2 ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NUC_THREADS) k_emit_nuc(
+// One lane = 32 output bytes = one 256-bit store.  A chunk normally lies inside a run of adjacent genome pieces: piece A holds its first byte, piece B (if A ends
+// inside the chunk) follows immediately; both are fetched branch-free and merged with one boundary mask.
+#define PIECE_G 0
+#define PIECE_E 1        // empty (clamped-away segment, empty literal)
+#define PIECE_L 2        // non-empty literal
+__global__ void __launch_bounds__(NUC_THREADS, 6) k_emit_nuc(
     const uint32_t *__restrict__ packed, const int64_t *__restrict__ piece_off, const int64_t *__restrict__ piece_src,
     int64_t n_piece, const int64_t *__restrict__ tile_first, int64_t total, int64_t T, const uint8_t *__restrict__ lit,
     const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte, int64_t n_exc, uint8_t *__restrict__ out) {
-    // pieces of the tile: piece i covers text [s_rel[i], s_rel[i+1]) relative to the tile; the nibble index of
-    // tile position q is s_base[i] + q (byte index into lit[] for a literal piece); s_skip[i] = 1 for clamped-away
-    // empty pieces, 3 for literal pieces (bit 0 = "not a genome piece", bit 1 = literal)
-    __shared__ int64_t s_base[NUC_CAP + 4];
-    __shared__ int32_t s_rel[NUC_CAP + 5];
-    __shared__ uint8_t s_skip[NUC_CAP + 4];
+    // pieces of the tile: piece i covers text [s_rel[i], s_rel[i+1]) relative to the tile; the nibble index of tile
+    // position q is s_base[i] + q; s_ng[i] = first non-empty GENOME piece at or after i
+    __shared__ int64_t s_base[NUC_CAP + 2];
+    __shared__ int32_t s_rel[NUC_CAP + 3];
+    __shared__ uint16_t s_ng[NUC_CAP + 2];
+    __shared__ uint8_t s_kind[NUC_CAP + 2];
     __shared__ uint16_t s_unit[NUC_UNITS];            // piece holding byte 64*u of the tile
     const int64_t P0 = (int64_t)blockIdx.x * MG_NUC_TILE;
     const int64_t p_lo = tile_first[blockIdx.x];
@@ -111,111 +188,93 @@ __global__ void __launch_bounds__(NUC_THREADS) k_emit_nuc(
     if (p_hi > n_piece) p_hi = n_piece;
     const int ncache = (int)min((int64_t)NUC_CAP, p_hi - p_lo);
     const int tile_len = (int)min((int64_t)MG_NUC_TILE, total - P0);
-    for (int i = threadIdx.x; i < ncache + 4; i += NUC_THREADS) {
-        if (i <= ncache) {
-            const int64_t rel = __ldg(piece_off + p_lo + i) - P0;      // > -2^31: piece lengths are int32
-            s_rel[i] = rel > MG_NUC_TILE ? MG_NUC_TILE : (int32_t)rel;
-        } else {
-            s_rel[i] = BIG;
-        }
+    for (int i = threadIdx.x; i < ncache + 2; i += NUC_THREADS) {
         if (i < ncache) {
-            const int64_t rel = __ldg(piece_off + p_lo + i) - P0;
+            const int64_t rel = __ldg(piece_off + p_lo + i) - P0;      // > -2^31: piece lengths are int32
+            const int64_t nxt = __ldg(piece_off + p_lo + i + 1) - P0;
             const uint64_t sk = (uint64_t)__ldg(piece_src + p_lo + i);
+            s_rel[i] = rel > MG_NUC_TILE ? MG_NUC_TILE : (int32_t)rel;
             s_base[i] = (int64_t)(sk & MG_SRC_MASK) - rel;
-            s_skip[i] = (sk >> MG_KIND_SHIFT) == MG_KIND_LIT ? 3 : (__ldg(piece_off + p_lo + i + 1) - P0 == rel ? 1 : 0);
+            s_kind[i] = nxt == rel ? PIECE_E : ((sk >> MG_KIND_SHIFT) == MG_KIND_LIT ? PIECE_L : PIECE_G);
         } else {
+            const int64_t rel = i == ncache ? __ldg(piece_off + p_lo + ncache) - P0 : (int64_t)BIG;
+            s_rel[i] = rel > MG_NUC_TILE ? (i == ncache ? MG_NUC_TILE : BIG) : (int32_t)rel;
             s_base[i] = 0;
-            s_skip[i] = 1;                            // nothing beyond the staged pieces may be selected as A or B
+            s_kind[i] = PIECE_G;
         }
     }
-    if (threadIdx.x == 0) s_rel[ncache + 4] = BIG;
+    if (threadIdx.x == 0) s_rel[ncache + 2] = BIG;
     __syncthreads();
-    for (int i = threadIdx.x; i < ncache; i += NUC_THREADS) {
-        const int r0 = s_rel[i] < 0 ? 0 : s_rel[i], r1 = s_rel[i + 1] < 0 ? 0 : s_rel[i + 1];
-        const int u1 = min((r1 + 63) >> 6, NUC_UNITS);
-        for (int u = (r0 + 63) >> 6; u < u1; u++) s_unit[u] = (uint16_t)i;
+    for (int i = threadIdx.x; i < ncache + 2; i += NUC_THREADS) {
+        int k = i;
+        while (k < ncache && s_kind[k] != PIECE_G) k++;               // runs of literal / empty pieces are short
+        s_ng[i] = (uint16_t)k;
+        if (i < ncache) {
+            const int r0 = s_rel[i] < 0 ? 0 : s_rel[i], r1 = s_rel[i + 1] < 0 ? 0 : s_rel[i + 1];
+            const int u1 = min((r1 + 63) >> 6, NUC_UNITS);
+            for (int u = (r0 + 63) >> 6; u < u1; u++) s_unit[u] = (uint16_t)i;
+        }
     }
     __syncthreads();
     const int covered = s_rel[ncache];                // tile-relative position where the staged pieces end
 
 #pragma unroll 1
     for (int cidx = 0; cidx < NUC_CHUNKS; cidx++) {
-        const int p = (cidx * NUC_THREADS + (int)threadIdx.x) << 4;
+        const int p = (cidx * NUC_THREADS + (int)threadIdx.x) << 5;
         if (p >= tile_len) break;
-        if (p + 16 > covered && covered < tile_len) {  // staging overflowed: slow path
+        if (p + 32 > covered && covered < tile_len) {  // staging overflowed: slow path straight from global memory
             const int64_t j = mg_search_le(piece_off, p_lo, n_piece, P0 + p);
             nuc_chunk_generic(packed, piece_off, piece_src, j, P0 + p, total, T, lit, exc_pos, exc_byte, n_exc, out);
             continue;
         }
-        int j = s_unit[p >> 6];
-        while (s_rel[j + 1] <= p) j++;
-        // first two genome pieces of the chunk, branch-free; up to two skippable pieces (suffix + prefix literal)
-        // may sit in front of each
-        int A = j;
-        A += s_skip[A] & 1;
-        A += s_skip[A] & 1;
-        int B = A + 1;
-        B += s_skip[B] & 1;
-        B += s_skip[B] & 1;
-        const int sA = s_rel[A], eA = s_rel[A + 1], sB = s_rel[B], eB = s_rel[B + 1];
-        const bool okA = !s_skip[A] && sA < p + 16, okB = okA && !s_skip[B] && sB < p + 16;
-        const uint64_t vA = mg_ld_nib16(packed, okA ? s_base[A] + p : (int64_t)MG_FRONT_PAD);
-        const uint64_t vB = mg_ld_nib16(packed, okB ? s_base[B] + p : (int64_t)MG_FRONT_PAD);
-        uint64_t nacc = 0;
-        if (okA) nacc = vA & nib_range_mask(max(sA - p, 0), min(eA - p, 16));   // literal positions stay 0 and are patched below
-        if (okB) nacc |= vB & nib_range_mask(sB - p, min(eB - p, 16));
-        // anything beyond that inside these 16 bytes (a third genome piece, chains of blank records): rare
-        const bool more = (s_skip[A] && sA < p + 16) || (okA && s_skip[B] && sB < p + 16) || (okB && eB < p + 16);
-        if (more) {
-            nacc = 0;
-            for (int k = j; k < ncache && s_rel[k] < p + 16; k++) {
-                if (!s_skip[k]) nacc |= mg_ld_nib16(packed, s_base[k] + p) & nib_range_mask(max(s_rel[k] - p, 0), min(s_rel[k + 1] - p, 16));
+        int A = s_unit[p >> 6];
+        while (s_rel[A + 1] <= p) A++;                 // the (non-empty) piece that holds byte p
+        const int end = min(32, tile_len - p);
+        // the first two GENOME pieces that reach into the chunk.  Literal positions before, between or after them get
+        // whatever nibbles happen to be there: k_emit_lit overwrites those bytes afterwards, so no lane ever branches
+        // on "is there framing in my chunk".
+        const int X = s_ng[A];
+        const bool hasX = s_rel[X] - p < end;
+        const int hiX = s_rel[X + 1] - p;              // X covers chunk positions [.., hiX)
+        const int Y = s_ng[X + 1];
+        const bool hasY = hasX && hiX < end && s_rel[Y] - p < end;
+        const bool third = hasY && s_rel[Y + 1] - p < end;             // a third genome piece inside 32 bytes: rare
+        uint32_t nX[4], nY[4];
+        ld_nib32(packed, hasX ? s_base[X] + p : (int64_t)MG_FRONT_PAD, nX);
+        ld_nib32(packed, hasY ? s_base[Y] + p : (int64_t)MG_FRONT_PAD, nY);
+        uint32_t n[4];
+        {   // positions < hiX come from X, the rest from Y
+            const int c = hiX > 32 ? 32 : hiX;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int t = c - 8 * k;
+                const uint32_t m = t >= 8 ? 0xFFFFFFFFu : (t <= 0 ? 0u : ((1u << (4 * t)) - 1u));
+                n[k] = (nX[k] & m) | (nY[k] & ~m);
             }
         }
-        uint32_t w0, w1, w2, w3;
-        mg_decode8((uint32_t)nacc, w0, w1);
-        mg_decode8((uint32_t)(nacc >> 32), w2, w3);
-        // literal bytes (">ID\n", "\n") inside this chunk: skipped pieces in front of A, or right behind A inside the
-        // chunk.  About 1.5 chunks per record take this path; a suffix and the following prefix that are adjacent in
-        // lit[] share one 16-byte window load.
-        if (MG_NUC_INLINE_LIT && (A != j || (okA && B != A + 1 && eA < p + 16) || more)) {
-            uint32_t lw[4] = {0, 0, 0, 0};
-            int64_t last = INT64_MIN;
-            for (int k = j; k < ncache && s_rel[k] < p + 16; k++) {
-                if ((s_skip[k] & 2) && s_rel[k + 1] > s_rel[k]) {
-                    if (s_base[k] != last) { ld_lit16(lit, s_base[k] + p, lw); last = s_base[k]; }
-                    const int lo = max(s_rel[k] - p, 0), hi = min(s_rel[k + 1] - p, 16);
-                    const uint32_t m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-                    const uint32_t m0 = expand4(m), m1 = expand4(m >> 4), m2 = expand4(m >> 8), m3 = expand4(m >> 12);
-                    w0 = (w0 & ~m0) | (lw[0] & m0); w1 = (w1 & ~m1) | (lw[1] & m1);
-                    w2 = (w2 & ~m2) | (lw[2] & m2); w3 = (w3 & ~m3) | (lw[3] & m3);
-                }
-            }
-        }
+        if (third) nuc_chunk_many(packed, s_base, s_rel, s_kind, A, ncache, p, end, n);   // rare: generic walk
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) mg_decode8(n[k], w[2 * k], w[2 * k + 1]);
         // code 15 = byte outside the packed alphabet on a '+' piece (the reverse plane already holds 'n',
         // genome.py:791-792): fetch the exact byte the FASTA had (genome.py:606 keeps it).  Rare.
-        uint64_t e = nacc & (nacc >> 1) & (nacc >> 2) & (nacc >> 3) & 0x1111111111111111ull;
-        if (e) {
-            uint32_t w[4] = {w0, w1, w2, w3};
-            while (e) {
-                const int t = (__ffsll((long long)e) - 1) >> 2;
-                e &= e - 1;
-                int jj = j;
-                while (s_rel[jj + 1] <= p + t) jj++;
-                const int64_t gi = s_base[jj] + p + t;
-                if (gi < T) {
-                    const uint32_t b = mg_exc_byte(exc_pos, exc_byte, n_exc, gi);
-                    w[t >> 2] = (w[t >> 2] & ~(0xFFu << ((t & 3) * 8))) | (b << ((t & 3) * 8));
-                }
+        if (n_exc > 0) {
+            uint32_t any = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t e = n[k] & (n[k] >> 1);
+                any |= e & (e >> 2) & 0x11111111u;
             }
-            w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3];
+            if (any) nuc_patch_exceptions(s_base, s_rel, s_kind, A, p, end, T, exc_pos, exc_byte, n_exc, n, w);
         }
-        mg_st16(out + P0 + p, w0, w1, w2, w3);
+        st32(out + P0 + p, w);
     }
 }
 
-// ---- literal framing bytes of the PROTEIN text (">ID\n" prefixes, "\n" suffixes): one thread per literal piece ---
-// Runs AFTER k_emit_prot on the same stream and overwrites the placeholder bytes it left there (K2 writes its own).
+// ---- literal framing bytes (">ID\n" prefixes, "\n" suffixes): one thread per literal piece ------------------------
+// Runs AFTER K2 / K3 on the same stream and overwrites the placeholder bytes they left at those positions.  Folding
+// this into K2 (1 lane active, ~1.5 chunks per record) or writing whole literal chunks from a second kernel were both
+// measured slower on B200 (0.300 / 0.251 ms vs 0.204 + 0.027 ms per exon launch of config 4).
 // which = 0: nucleotide text (positions from piece_off); which = 1: protein text (positions from prot_off).
 __global__ void __launch_bounds__(256) k_emit_lit(int which, int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
                                                   const int64_t *__restrict__ piece_off, const int64_t *__restrict__ prot_off,
@@ -427,7 +486,7 @@ extern "C" int mg_emit_nuc_device(mg_plan *p, uint8_t *out_dev, void *stream) {
     MG_REQUIRE(p != nullptr, "plan handle is NULL");
     if (!p->prepared) { mg_set_error("mg_plan_prepare has not been called"); return MG_ESTATE; }
     if (p->nuc_total == 0) return MG_OK;
-    MG_REQUIRE(out_dev != nullptr && ((uintptr_t)out_dev & 15) == 0, "out_dev must be a 16-byte aligned device pointer");
+    MG_REQUIRE(out_dev != nullptr && ((uintptr_t)out_dev & 31) == 0, "out_dev must be a 32-byte aligned device pointer");
     MG_CUDA(cudaSetDevice(p->device));
     mg_genome *g = p->g;
     cudaStream_t st = (cudaStream_t)stream;
@@ -435,7 +494,7 @@ extern "C" int mg_emit_nuc_device(mg_plan *p, uint8_t *out_dev, void *stream) {
     k_emit_nuc<<<(unsigned)p->n_nuc_tile, NUC_THREADS, 0, st>>>(g->d_packed, p->d_piece_off, p->d_piece_src, p->n_piece, p->d_nuc_tile,
                                                               p->nuc_total, g->total_bases, p->d_lit, g->d_exc_pos, g->d_exc_byte, g->n_exc, out_dev);
     MG_LAUNCH_CHECK();
-    if (!MG_NUC_INLINE_LIT && p->n_lit > 0) {
+    if (p->n_lit > 0) {
         k_emit_lit<<<(unsigned)((2 * p->n_rec + 255) / 256), 256, 0, st>>>(0, p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_prot_off,
                                                                          p->d_rec_aa, p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, p->d_lit, out_dev);
         MG_LAUNCH_CHECK();
@@ -471,7 +530,7 @@ extern "C" int mg_emit_nuc_host(mg_plan *p, uint8_t *out_host, void *stream) {
     MG_REQUIRE(out_host != nullptr, "out_host is NULL");
     MG_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = ensure_out(p, (p->nuc_total + 15) / 16 * 16, st);
+    int rc = ensure_out(p, (p->nuc_total + 31) / 32 * 32, st);
     if (rc) return rc;
     rc = mg_emit_nuc_device(p, p->d_out, stream);
     if (rc) return rc;
@@ -486,7 +545,7 @@ extern "C" int mg_emit_prot_host(mg_plan *p, uint8_t *out_host, void *stream) {
     MG_REQUIRE(out_host != nullptr, "out_host is NULL");
     MG_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = ensure_out(p, (p->prot_total + 15) / 16 * 16, st);
+    int rc = ensure_out(p, (p->prot_total + 31) / 32 * 32, st);
     if (rc) return rc;
     rc = mg_emit_prot_device(p, p->d_out, stream);
     if (rc) return rc;
