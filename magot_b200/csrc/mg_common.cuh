@@ -102,6 +102,7 @@ struct mg_plan {
     int8_t *d_rec_phase = nullptr;
     uint8_t *d_lit = nullptr;
     // derived (device)
+    int64_t *d_blk_r0 = nullptr;              // [n_piece/256] record owning the first piece of each 256-piece block
     int32_t *d_piece_len = nullptr;           // [n_piece]
     int64_t *d_piece_src = nullptr;           // [n_piece]  src | kind<<62
     int64_t *d_piece_off = nullptr;           // [n_piece+1] exclusive prefix = offsets in the nucleotide text

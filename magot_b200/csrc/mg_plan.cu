@@ -19,24 +19,49 @@
 
 // ---- kernels ----------------------------------------------------------------------------------------
 
-// thread per piece: find its record (binary search over F), clamp like a Python slice, write len + src
+// thread per 256-piece block: record that owns the block's first piece (largest r with F(r) = rec_seg_off[r]+2r <= 256*b)
+__global__ void __launch_bounds__(256) k_plan_block_rec(int64_t n_block, int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
+                                                        int64_t *__restrict__ blk_r0) {
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= n_block) return;
+    const int64_t pb = b * 256;
+    int64_t lo = 0, hi = n_rec;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(rec_seg_off + mid) + 2 * mid <= pb) lo = mid; else hi = mid;
+    }
+    blk_r0[b] = lo;
+}
+
+// thread per piece: find its record, clamp like a Python slice, write len + src
 __global__ void __launch_bounds__(256) k_plan_pieces(int64_t n_piece, int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
+                                                     const int64_t *__restrict__ blk_r0,
                                                      const int32_t *__restrict__ seg_contig, const int64_t *__restrict__ seg_start,
                                                      const int64_t *__restrict__ seg_end, const int8_t *__restrict__ seg_strand,
                                                      const int64_t *__restrict__ rec_lit_off, const int32_t *__restrict__ rec_pre,
                                                      const int32_t *__restrict__ rec_suf, const int64_t *__restrict__ contig_len,
                                                      const int64_t *__restrict__ contig_base, int64_t n_contigs, int64_t two_T,
                                                      int32_t *__restrict__ piece_len, int64_t *__restrict__ piece_src) {
-    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= n_piece) return;
-    // largest r with F(r) = rec_seg_off[r] + 2r <= p
-    int64_t lo = 0, hi = n_rec;
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(rec_seg_off + mid) + 2 * mid <= p) lo = mid; else hi = mid;
+    // The 256 pieces of a block belong to at most 129 consecutive records starting at blk_r0[block] (found by
+    // k_plan_block_rec, 35 global searches per SM instead of one per thread): F(r) = rec_seg_off[r] + 2r of those
+    // records is staged in shared memory and every thread searches there.
+    __shared__ int64_t s_F[258];
+    const int64_t pb = blockIdx.x * (int64_t)blockDim.x;
+    const int64_t r0 = blk_r0[blockIdx.x];
+    for (int i = threadIdx.x; i < 258; i += blockDim.x) {
+        const int64_t r = r0 + i;
+        s_F[i] = r <= n_rec ? __ldg(rec_seg_off + r) + 2 * r : INT64_MAX;
     }
-    const int64_t r = lo;
-    const int64_t s0 = __ldg(rec_seg_off + r), s1 = __ldg(rec_seg_off + r + 1);
+    __syncthreads();
+    const int64_t p = pb + threadIdx.x;
+    if (p >= n_piece) return;
+    int lo = 0, hi = 257;                              // F(r0) <= p < F(r0 + 257) because F grows by >= 2 per record
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_F[mid] <= p) lo = mid; else hi = mid;
+    }
+    const int64_t r = r0 + lo;
+    const int64_t s0 = s_F[lo] - 2 * r, s1 = s_F[lo + 1] - 2 * (r + 1);
     const int64_t local = p - (s0 + 2 * r);
     if (local == 0) {                                   // literal prefix
         piece_len[p] = rec_pre[r];
@@ -182,6 +207,7 @@ extern "C" int mg_plan_create(mg_genome *g, int64_t n_rec, const int64_t *rec_se
         p->d_lit = d + 16;
     }
     if (rec_phase) TRY(upload(p, &p->d_rec_phase, rec_phase, n_rec, st));
+    TRY(dalloc(p, &p->d_blk_r0, (p->n_piece + 255) / 256 + 1, st));
     TRY(dalloc(p, &p->d_piece_len, p->n_piece, st));
     TRY(dalloc(p, &p->d_piece_src, p->n_piece, st));
     TRY(dalloc(p, &p->d_piece_off, p->n_piece + 1, st));
@@ -214,8 +240,11 @@ extern "C" int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, i
     p->last_stream = st;
     int64_t totals[2] = {0, 0};
     if (p->n_rec > 0) {
-        k_plan_pieces<<<(unsigned)((p->n_piece + 255) / 256), 256, 0, st>>>(
-            p->n_piece, p->n_rec, p->d_rec_seg_off, p->d_seg_contig, p->d_seg_start, p->d_seg_end, p->d_seg_strand,
+        const int64_t n_block = (p->n_piece + 255) / 256;
+        k_plan_block_rec<<<(unsigned)((n_block + 255) / 256), 256, 0, st>>>(n_block, p->n_rec, p->d_rec_seg_off, p->d_blk_r0);
+        MG_LAUNCH_CHECK();
+        k_plan_pieces<<<(unsigned)n_block, 256, 0, st>>>(
+            p->n_piece, p->n_rec, p->d_rec_seg_off, p->d_blk_r0, p->d_seg_contig, p->d_seg_start, p->d_seg_end, p->d_seg_strand,
             p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, g->d_contig_len, g->d_contig_base, g->n_contigs, 2 * g->total_bases,
             p->d_piece_len, p->d_piece_src);
         MG_LAUNCH_CHECK();

@@ -269,3 +269,84 @@ def test_edge_records(mg):
     empty = engine.RecordTable([0], [], [], [], [], [], [], [], np.zeros(0, np.uint8))
     assert engine.run_table(g, empty)[0] == b""
     g.close()
+
+
+# ---- K4: six-frame translation + ORF scan -------------------------------------------------------------------------
+
+def _sixframe_case(mg, contigs, min_aa):
+    from magot_b200 import engine, orfs
+    g = engine.DeviceGenome([len(c) for c in contigs], device=0)
+    for i, c in enumerate(contigs):
+        g.pack(i, np.frombuffer(c, dtype=np.uint8))
+    g.finalize()
+    recs, aa = orfs.sixframe(g, 0, len(contigs), min_aa)
+    g.close()
+    want_aa, want_rec = [], []
+    off = 0
+    for ci, c in enumerate(contigs):
+        a, r = coracle.sixframe(c, min_aa)
+        for row in r:
+            want_rec.append((ci, int(row[0]), int(row[1]), int(row[2]), int(row[3]), off))
+            off += int(row[3])
+        want_aa.append(a)
+    got_rec = [(int(r["contig"]), int(r["frame"]), int(r["minus"]), int(r["start"]), int(r["len"]), int(r["aa_off"])) for r in recs]
+    assert got_rec == want_rec
+    assert aa == b"".join(want_aa)
+
+
+def test_sixframe_matches_reference_get_orfs(mg, kat):
+    """Sequence.get_orfs (genome.py:824-851) known answers produced by the reference, via the device ORF scan."""
+    from magot_b200 import engine, orfs
+    for s, mode, r in kat["get_orfs"]:
+        if mode is not False or len(s) < 1:
+            continue
+        g = engine.DeviceGenome([len(s)], device=0)
+        g.pack(0, np.frombuffer(s.encode("latin-1"), dtype=np.uint8))
+        g.finalize()
+        recs, aa = orfs.sixframe(g, 0, 1, 0)
+        g.close()
+        text = aa.decode("latin-1")
+        got = [text[int(x["aa_off"]):int(x["aa_off"]) + int(x["len"])] for x in recs]
+        assert got == r, (len(s), s[:40])
+
+
+@pytest.mark.parametrize("min_aa", [0, 1, 15, 16, 30, 100])
+def test_sixframe_random_contigs(mg, min_aa):
+    rng = np.random.default_rng(100 + min_aa)
+    alpha = np.frombuffer(b"ACGTacgtNnR", dtype=np.uint8)
+    p = np.array([30, 30, 30, 30, 10, 10, 10, 10, 2, 1, 1], dtype=float)
+    contigs = []
+    for n in [0, 1, 2, 3, 4, 5, 6, 7, 8, 47, 48, 49, 95, 96, 97, 12287, 12288, 12289, 12290, 30000, 200001]:
+        contigs.append(alpha[rng.choice(alpha.size, size=n, p=p / p.sum())].tobytes())
+    # stop-poor contig (long ORFs crossing many tiles) and an N run in the middle of a contig
+    contigs.append(np.frombuffer(b"ACG", dtype=np.uint8)[rng.integers(0, 3, size=60000)].tobytes())
+    c = bytearray(alpha[rng.integers(0, 4, size=50000)].tobytes())
+    c[20000:33000] = b"N" * 13000
+    contigs.append(bytes(c))
+    _sixframe_case(mg, contigs, min_aa)
+
+
+def test_dna2orfs_entry_point(mg, tmp_path):
+    """dna2orfs (genome_tools.py:145-180) as intended: ORF strings are get_orfs', positions follow its own formula."""
+    from magot_b200 import genome_tools as gt
+    rng = np.random.default_rng(7)
+    seqs = {"s1": "".join(rng.choice(list("ACGT"), size=900)), "s2 extra words": "".join(rng.choice(list("ACGTN"), size=301))}
+    fa = tmp_path / "in.fa"
+    fa.write_text("".join(">%s\n%s\n" % kv for kv in seqs.items()))
+    out = tmp_path / "orfs.fa"
+    gt.dna2orfs(str(fa), str(out))
+    got = out.read_text()
+    import py2dict
+    want = []
+    for name in py2dict.py2_order(list(seqs)):
+        s = seqs[name]
+        for frame in (0, 1, 2):
+            for strand in "-+":
+                t = mo.translate(s, frame=frame, strand=strand)
+                if not t:
+                    continue
+                pos = frame if strand == '+' else len(s) - frame
+                for orf in t.split('*'):
+                    want.append(">%s-pos:%d\n%s\n" % (name, pos, orf))
+                    pos += 3 * (1 + len(orf))
+    assert got == "".join(want)
