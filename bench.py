@@ -5,7 +5,7 @@
   python bench.py --impl reference --gpus N --steps K --warmup W
 
 Workload (config.workload): synthetic 3.1 Gbp human-scale genome (24 chromosomes + 170 scaffolds,
-5 % N, 50 % soft-masked) resident on the GPU as 0.5 B/base, and a GTF-shaped annotation of 200k
+5 % N, 50 % soft-masked) resident on the GPU as two strand planes of 0.5 B/base each, and a GTF-shaped annotation of 200k
 transcripts per GPU (weak scaling: every rank owns its own 200k-transcript batch over a replicated
 genome; the path has no cross-shard exchange, so there is no collective on the data path).
 One STEP = one pass of the hot path over one batch, producing all three products of config 4:
@@ -302,7 +302,7 @@ def gpu_arm(args):
 
     # pinned copies of the host tables for the e2e path
     def pin(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        t = torch.from_numpy(np.array(a, copy=True)).pin_memory()
         return t
     pinned = {}
     for k, t in tables.items():
@@ -451,7 +451,7 @@ def gpu_arm(args):
             "metric": METRIC, "value": bp_all / (dev_ms * 1e-3) / 1e9, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "config 4: synthetic %.2f Gbp human-scale genome (replicated per GPU, 0.5 B/base resident) + %d-transcript GTF-shaped batch per GPU; products: CDS nucleotide FASTA + CDS protein FASTA + exon-based transcript FASTA" % (GENOME_BP / 1e9, N_TX),
+            "config": {"workload": "config 4: synthetic %.2f Gbp human-scale genome (replicated per GPU; forward + reverse-complement planes, 0.5 B/base each) + %d-transcript GTF-shaped batch per GPU; products: CDS nucleotide FASTA + CDS protein FASTA + exon-based transcript FASTA" % (GENOME_BP / 1e9, N_TX),
                        "genome_bp": GENOME_BP, "transcripts_per_gpu": N_TX, "cds_segments": int(tables["cds"].n_seg),
                        "exons": int(tables["exon"].n_seg), "spliced_cds_bp": S_cds, "spliced_exon_bp": S_exon,
                        "bp_per_step_per_gpu": bp_step, "parallelism": "transcript batches per GPU, genome replicated, no collective",
