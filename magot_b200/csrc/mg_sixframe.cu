@@ -48,6 +48,7 @@ struct mg_sixframe_state {
     int64_t aa_cap = 0;
     std::vector<void *> owned;
     bool counted = false;
+    cudaStream_t stream = 0;
 };
 
 // ---- per-stream geometry ------------------------------------------------------------------------------
@@ -328,33 +329,58 @@ __device__ __forceinline__ int enumerate_stream(const TileInfo &ti, const SixMas
                                                 mg_orf *__restrict__ recs, int32_t *__restrict__ lens, int64_t *__restrict__ srcs) {
     if (ti.m[s] <= 0) return 0;                       // `if translated_seq:` (genome.py:832)
     const int plus = s & 1;
+    int k = 0;
+    // one candidate ORF: between stops xl (lower) and xh (higher, !real = virtual stop at the contig's high end)
+    // Contig offsets fit 32 bits (mg_sixframe_count rejects longer contigs).  The length test needs no division:
+    // both stops are congruent to cs modulo 3, so len = span/3 - 1; the divisions of orf_of run for kept ORFs only.
+    const int32_t L32 = (int32_t)ti.L, cs32 = ti.cs[s], m32 = (int32_t)ti.m[s];
+    const int64_t need3 = 3 * min_aa;                       // residues * 3
+    auto visit = [&](int64_t xl, bool xl_real, int64_t xh, bool real) {
+        // span3 = 3 * (number of residues of the candidate)
+        const int32_t ql = plus ? (int32_t)xl - cs32 : L32 - 3 - cs32 - (int32_t)xl;   // 3 * residue index of the lower stop
+        const int32_t qh = plus ? (int32_t)xh - cs32 : L32 - 3 - cs32 - (int32_t)xh;
+        int64_t span3;
+        if (plus) span3 = (int64_t)(real ? qh : 3 * m32) - (xl_real ? ql : -3) - 3;
+        else span3 = (int64_t)(xl_real ? ql : 3 * m32) - (real ? qh : -3) - 3;
+        if (span3 >= need3) {
+            if (WRITE) {
+                int64_t st, ln;
+                orf_of(plus, ti.L, ti.cs[s], ti.m[s], xl, xh, xl_real, real, st, ln);
+                const int64_t slot = slot0 + (plus ? k : n_mine - 1 - k);
+                mg_orf o;
+                o.contig = (int32_t)ti.c; o.frame = (int8_t)(s >> 1); o.minus = (int8_t)(!plus); o.pad = 0;
+                o.start = st; o.len = ln; o.aa_off = 0;
+                recs[slot] = o;
+                lens[slot] = (int32_t)ln;
+                const int64_t q = ti.cs[s] + 3 * st;                // oriented offset of the ORF's first base
+                srcs[slot] = plus ? (ti.gb + q) : (two_T - ti.gb - ti.L + q);      // '-': forward read of the reverse plane
+            }
+            k++;
+        }
+    };
+    if (min_aa >= 16) {
+        // Two stops of one stream inside a thread's 48 bases are < 16 codons apart, so only the FIRST stop of the thread
+        // (and the virtual stop at the contig end) can close an ORF of >= 16 residues: no loop over stops.
+        int first, last;
+        stream_first_last(sm, s, ti.Lm3, first, last);
+        if (first >= 0) visit(prev, prev >= 0, x0 + first, true);
+        if (is_end_thread) {
+            const int64_t xl = last >= 0 ? x0 + last : prev;
+            visit(xl, xl >= 0, 0, false);
+        }
+        return k;
+    }
     const int r = stream_res(s, ti.Lm3);
     const uint64_t *msk = plus ? sm.pm : sm.mm;
     int64_t xl = prev;
     bool xl_real = prev >= 0;
-    int k = 0;
     for (int g = 0; g <= 3; g++) {
         uint64_t x = g < 3 ? (msk[g] & res_mask((r - g + 3) % 3)) : (is_end_thread ? 1ull : 0ull);
         while (x) {
             const int t = 16 * g + ((__ffsll((long long)x) - 1) >> 2);
             x &= x - 1;
-            const bool real = g < 3;
             const int64_t xh = x0 + t;
-            int64_t st, ln;
-            orf_of(plus, ti.L, ti.cs[s], ti.m[s], xl, xh, xl_real, real, st, ln);
-            if (ln >= min_aa) {
-                if (WRITE) {
-                    const int64_t slot = slot0 + (plus ? k : n_mine - 1 - k);
-                    mg_orf o;
-                    o.contig = (int32_t)ti.c; o.frame = (int8_t)(s >> 1); o.minus = (int8_t)(!plus); o.pad = 0;
-                    o.start = st; o.len = ln; o.aa_off = 0;
-                    recs[slot] = o;
-                    lens[slot] = (int32_t)ln;
-                    const int64_t q = ti.cs[s] + 3 * st;            // oriented offset of the ORF's first base
-                    srcs[slot] = plus ? (ti.gb + q) : (two_T - ti.gb - ti.L + q);      // '-': forward read of the reverse plane
-                }
-                k++;
-            }
+            visit(xl, xl_real, xh, g < 3);
             xl = xh;
             xl_real = true;
         }
@@ -557,7 +583,7 @@ __global__ void __launch_bounds__(AA_THREADS) k_six_aa(const uint32_t *__restric
 
 // ---- host API -------------------------------------------------------------------------------------------------
 static void six_release(mg_sixframe_state *s) {
-    for (void *d : s->owned) cudaFree(d);
+    for (void *d : s->owned) cudaFreeAsync(d, s->stream);
     s->owned.clear();
     if (s->d_aa) cudaFree(s->d_aa);
     s->d_aa = nullptr;
@@ -574,8 +600,8 @@ void mg_sixframe_free(mg_genome *g) {
 
 template <typename T>
 static int six_alloc(mg_sixframe_state *s, T **p, int64_t n) {
-    void *d = nullptr;
-    MG_CUDA(cudaMalloc(&d, std::max<int64_t>(1, n) * sizeof(T)));
+    void *d = nullptr;                               // stream-ordered pool: no device-wide sync per allocation
+    MG_CUDA(cudaMallocAsync(&d, std::max<int64_t>(1, n) * sizeof(T), s->stream));
     s->owned.push_back(d);
     *p = (T *)d;
     return MG_OK;
@@ -592,6 +618,7 @@ extern "C" int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig
     mg_sixframe_free(g);
     mg_sixframe_state *s = new mg_sixframe_state();
     g->six = s;
+    s->stream = st;
     s->contig_lo = contig_lo;
     s->contig_hi = contig_hi;
     s->min_aa = min_aa;
