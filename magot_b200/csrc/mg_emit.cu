@@ -30,8 +30,8 @@
 #include "mg_gather.cuh"
 
 #define NUC_THREADS 256
-#define NUC_CHUNKS (MG_NUC_TILE / 32 / NUC_THREADS)     // 2 chunks of 32 B per thread
-#define NUC_CAP 1024                                     // pieces staged per tile
+#define NUC_CHUNKS (MG_NUC_TILE / 32 / NUC_THREADS)     // 4 chunks of 32 B per thread
+#define NUC_CAP 2048                                     // pieces staged per tile
 #define NUC_UNITS (MG_NUC_TILE / 64)
 
 #define PROT_THREADS 256
