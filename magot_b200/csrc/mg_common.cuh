@@ -7,7 +7,7 @@
 //               complement of codes 0..7 is code ^ 3 (case bit 2 is preserved), which is what makes the
 //               reverse complement (genome.py:784-793) three register ops per 8 bases.
 //   contigs are laid back to back in one global base index space; contig c starts at contig_base[c],
-//   a multiple of 32 bases (16 bytes); index 0..31 is front padding so that a 16-base window that
+//   a multiple of 32 bases (16 bytes); index 0..63 is front padding so that a window that
 //   starts a little before the first base of the genome can still be loaded with non-negative addresses.
 //   TWO PLANES: indices [0, T) hold the forward strand, indices [T, 2T) hold the reverse complement of
 //   the whole index space (base g of the forward plane is base 2T-1-g of the reverse plane, complemented
@@ -24,7 +24,7 @@
 #include <vector>
 #include "../../include/magot_b200.h"
 
-#define MG_FRONT_PAD 32            // bases of padding before contig 0
+#define MG_FRONT_PAD 64            // bases of padding before contig 0 (K3 may start a 48-nibble window 45 bases early)
 #define MG_TAIL_WORDS 8            // readable slack words after the last contig
 #define MG_CODE_EXC 15u
 

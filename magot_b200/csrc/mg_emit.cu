@@ -327,6 +327,29 @@ __device__ __noinline__ void prot_chunk_generic(const uint32_t *__restrict__ pac
     mg_st16(out + P, w[0], w[1], w[2], w[3]);
 }
 
+// rare path of K3: the 48 nibbles of a chunk's codons spread over three or more segment pieces
+__device__ __noinline__ void prot_gather_many(const uint32_t *__restrict__ packed, const int64_t *s_base, const int32_t *s_rel,
+                                              int j, int q, int need_lo, int need_hi, uint32_t n[6]) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) n[k] = 0;
+    for (; s_rel[j] < need_hi; j++) {
+        const int lo = max(s_rel[j], need_lo) - q, hi = min(s_rel[j + 1], need_hi) - q;     // nibble range of this piece
+        if (hi <= lo) continue;
+        const int64_t g = s_base[j] + q;
+        const uint32_t *pp = packed + (g >> 3);
+        const uint32_t sh = ((uint32_t)g & 7u) << 2;
+        uint32_t w[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) w[k] = __ldg(pp + k);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int a = min(max(lo - 8 * k, 0), 8), b = min(max(hi - 8 * k, 0), 8);
+            const uint32_t m = b > a ? ((0xFFFFFFFFu >> (32 - 4 * (b - a))) << (4 * a)) : 0u;
+            n[k] |= __funnelshift_r(w[k], w[k + 1], sh) & m;
+        }
+    }
+}
+
 // Output chunk = 16 bytes of protein text.  Amino acid a of record r is the codon at spliced offset
 // skip[r] + 3a; the 4096-entry nibble-triplet table (case-insensitive, anything non-ACGT -> 'X') sits in
 // shared memory.  Stop codons are emitted as '*' and translation continues (genome.py:811-818).
@@ -411,62 +434,65 @@ __global__ void __launch_bounds__(PROT_THREADS) k_emit_prot(
         const int p = (cidx * PROT_THREADS + (int)threadIdx.x) << 4;
         if (p >= tile_len) break;
         int R = s_unit[p >> 6];
-        while (r_e[R] <= p) R++;
-        uint32_t bw0 = 0, bw1 = 0, bw2 = 0, bw3 = 0;
-        for (; r_s[R] < p + 16; R++) {                // records with residues inside this chunk (usually one)
+        while (r_e[R] <= p) R++;                      // first record whose residues end after byte p
+        uint32_t bw[4] = {0, 0, 0, 0};
+        // Usually ONE record has residues in the chunk: 16 codons = 48 spliced nibbles, taken from at most two
+        // adjacent segment pieces and merged with one boundary mask, branch-free.  A second record in the same 16 bytes
+        // needs >= 11 framing bytes in between, i.e. it happens for ~1 % of chunks, and takes another trip of the loop.
+        for (; r_s[R] < p + 16; R++) {
             const int lo = max(r_s[R] - p, 0), hi = min(r_e[R] - p, 16);
             if (hi <= lo) continue;                   // record without residues
             // nucleotide-text position (relative to O) of the codon that lands on chunk position 0
             const int q = r_q0[R] + 3 * p;
             const int need_lo = q + 3 * lo, need_hi = q + 3 * hi;        // nibbles [need_lo, need_hi)
-            int j = r_j0[R];
-            {   // last piece of the record that starts at or before need_lo (its pieces are contiguous)
-                int a = j, b = r_j0[R + 1] - 2;       // one past the record's last segment piece
+            int X;
+            {   // last segment piece of the record that starts at or before need_lo (its pieces are adjacent)
+                int a = r_j0[R], b = r_j0[R + 1] - 2; // b = one past the record's last segment piece
                 while (b - a > 1) {
                     const int mid = (a + b) >> 1;
                     if (s_rel[mid] <= need_lo) a = mid; else b = mid;
                 }
-                j = a;
+                X = a;
             }
-            uint64_t acc[3];
+            const int eX = s_rel[X + 1];              // X covers nibbles [.., eX)
+            const bool hasY = eX < need_hi;
+            const int Y = X + 1;                      // next segment piece of the same record (may be empty)
+            const bool many = hasY && s_rel[Y + 1] < need_hi;           // three or more pieces in 48 nibbles: rare
+            uint32_t n[6];
+            if (!many) {
+                const int64_t gx = s_base[X] + q;
+                const int64_t gy = hasY ? s_base[Y] + q : (int64_t)MG_FRONT_PAD;
+                const uint32_t *px = packed + (gx >> 3), *py = packed + (gy >> 3);
+                const uint32_t shx = ((uint32_t)gx & 7u) << 2, shy = ((uint32_t)gy & 7u) << 2;
+                uint32_t wx[7], wy[7];
 #pragma unroll
-            for (int g = 0; g < 3; g++) {
-                const int qg = q + 16 * g;
-                const int w_lo = max(qg, need_lo), w_hi = min(qg + 16, need_hi);
-                uint64_t a = 0;
-                if (w_hi > w_lo) {
-                    while (s_rel[j + 1] <= w_lo) j++;
-                    // first two pieces of this 16-nibble group, branch-free (segment pieces of a record are adjacent)
-                    const int sA = s_rel[j], eA = s_rel[j + 1], eB = s_rel[j + 2];
-                    const bool hasB = eA < w_hi && eB > eA;
-                    const uint64_t vA = mg_ld_nib16(packed, s_base[j] + qg);
-                    const uint64_t vB = mg_ld_nib16(packed, hasB ? s_base[j + 1] + qg : (int64_t)MG_FRONT_PAD);
-                    a = vA & nib_range_mask(max(sA, w_lo) - qg, min(eA, w_hi) - qg);
-                    if (hasB) a |= vB & nib_range_mask(eA - qg, min(eB, w_hi) - qg);
-                    if (eA < w_hi && (!hasB || eB < w_hi)) {           // more than two pieces in 16 nibbles: rare
-                        for (int jj = j + 1; s_rel[jj] < w_hi; jj++) {
-                            if (s_rel[jj + 1] > s_rel[jj] && (jj > j + 1 || !hasB))
-                                a |= mg_ld_nib16(packed, s_base[jj] + qg) & nib_range_mask(s_rel[jj] - qg, min(s_rel[jj + 1], w_hi) - qg);
-                        }
-                    }
+                for (int k = 0; k < 7; k++) { wx[k] = __ldg(px + k); wy[k] = __ldg(py + k); }
+                const int c = eX - q;                 // nibbles [0, c) of the 48 come from X, the rest from Y
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    const int t = c - 8 * k;
+                    const uint32_t m = t >= 8 ? 0xFFFFFFFFu : (t <= 0 ? 0u : ((1u << (4 * t)) - 1u));
+                    n[k] = (__funnelshift_r(wx[k], wx[k + 1], shx) & m) | (__funnelshift_r(wy[k], wy[k + 1], shy) & ~m);
                 }
-                acc[g] = a;
+            } else {
+                prot_gather_many(packed, s_base, s_rel, X, q, need_lo, need_hi, n);
             }
             uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int k = 0; k < 16; k++) {            // codon k sits at bit 12k of acc[2]:acc[1]:acc[0]
-                const int bit = 12 * k, ww = bit >> 6, sh = bit & 63;
-                uint32_t idx = (uint32_t)(acc[ww] >> sh);
-                if (sh > 52) idx |= (uint32_t)(acc[ww + 1] << (64 - sh));
+            for (int k = 0; k < 16; k++) {            // codon k = nibbles 3k..3k+2 = bits 12k.. of n[5]:..:n[0]
+                const int bit = 12 * k, ww = bit >> 5, sh = bit & 31;
+                uint32_t idx = n[ww] >> sh;
+                if (sh > 20) idx |= n[ww + 1] << (32 - sh);
                 w[k >> 2] |= (uint32_t)s_aa[idx & 0xFFFu] << ((k & 3) * 8);
             }
             const uint32_t m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-            if (m == 0xFFFFu) { bw0 = w[0]; bw1 = w[1]; bw2 = w[2]; bw3 = w[3]; }
+            if (m == 0xFFFFu) { bw[0] = w[0]; bw[1] = w[1]; bw[2] = w[2]; bw[3] = w[3]; }
             else {
-                bw0 |= w[0] & expand4(m); bw1 |= w[1] & expand4(m >> 4); bw2 |= w[2] & expand4(m >> 8); bw3 |= w[3] & expand4(m >> 12);
+#pragma unroll
+                for (int k = 0; k < 4; k++) { const uint32_t mk = expand4(m >> (4 * k)); bw[k] = (bw[k] & ~mk) | (w[k] & mk); }
             }
         }
-        mg_st16(out + P0 + p, bw0, bw1, bw2, bw3);
+        mg_st16(out + P0 + p, bw[0], bw[1], bw[2], bw[3]);
     }
 }
 
