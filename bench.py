@@ -380,15 +380,30 @@ def gpu_arm(args):
     host_cds_p = torch.empty(sizes["cds"][1], dtype=torch.uint8, pin_memory=True)
     host_exon_n = torch.empty(sizes["exon"][0], dtype=torch.uint8, pin_memory=True)
 
+    # The two plans are independent, so the exon plan goes to a second stream: its table upload (H2D engine) and its
+    # kernels overlap the device->host copy of the CDS texts (D2H engine), which is what bounds the step.
+    stream_b = torch.cuda.Stream(device=dev)
+    spb = ctypes.c_void_p(stream_b.cuda_stream)
+
+    def create_plan_on(k, s):
+        p = pinned[k]
+        h = ctypes.c_void_p()
+        _lib.check(lib.mg_plan_create(g.handle, tables[k].n_rec, P(p["rec_seg_off"]), tables[k].n_seg, P(p["seg_contig"]), P(p["seg_start"]),
+                                      P(p["seg_end"]), P(p["seg_strand"]), P(p["rec_lit_off"]), P(p["rec_pre_len"]), P(p["rec_suf_len"]),
+                                      P(p["lit"]), p["lit"].numel(), None, s, ctypes.byref(h)))
+        return h
+
     def e2e_step():
-        hc = create_plan("cds")
-        prepare(hc)
+        hc = create_plan_on("cds", sp)
+        he = create_plan_on("exon", spb)
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.check(lib.mg_plan_prepare(hc, _lib.MG_PROT_TRIMX, ctypes.byref(a), ctypes.byref(b), sp))
         _lib.check(lib.mg_emit_nuc_host(hc, P(host_cds_n), sp))
         _lib.check(lib.mg_emit_prot_host(hc, P(host_cds_p), sp))
-        he = create_plan("exon")
-        prepare(he)
-        _lib.check(lib.mg_emit_nuc_host(he, P(host_exon_n), sp))
+        _lib.check(lib.mg_plan_prepare(he, _lib.MG_PROT_TRIMX, ctypes.byref(a), ctypes.byref(b), spb))
+        _lib.check(lib.mg_emit_nuc_host(he, P(host_exon_n), spb))
         _lib.check(lib.mg_stream_sync(local, sp))
+        _lib.check(lib.mg_stream_sync(local, spb))
         lib.mg_plan_destroy(hc)
         lib.mg_plan_destroy(he)
 
@@ -400,6 +415,7 @@ def gpu_arm(args):
     s2.record(stream)
     for _ in range(args.steps):
         e2e_step()
+    stream.wait_stream(stream_b)
     e2.record(stream)
     barrier()
     e2e_ms = max(s2.elapsed_time(e2), (time.perf_counter() - t0) * 1e3) / args.steps

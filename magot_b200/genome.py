@@ -306,24 +306,12 @@ class GenomeSequence(dict):
 def _parse_fasta(data, truncate_names):
     """genome.py:856-877 on a bytes buffer.  Lines end at '\\n' only; '\\r' and '\\n' are removed from
     sequence lines, every other byte is kept; records with an empty sequence are dropped; text
-    before the first header belongs to seqid ''; a repeated header replaces the earlier record."""
-    arr = np.frombuffer(data, dtype=np.uint8)
-    n = arr.size
+    before the first header belongs to seqid ''; a repeated header replaces the earlier record.
+    Headers are located with bytes.find and newlines stripped with bytes.translate (both run at
+    memory speed in C), so a human-size FASTA parses in seconds."""
+    n = len(data)
     names = []
     arrays = {}
-    if n == 0:
-        return names, arrays
-    nl = np.flatnonzero(arr == 10)
-    line_starts = np.concatenate(([0], nl + 1))
-    line_starts = line_starts[line_starts < n]
-    is_hdr = arr[line_starts] == 62
-    hdr_starts = line_starts[is_hdr]
-    # end (exclusive, at the '\n' or EOF) of each header line
-    if hdr_starts.size and nl.size:
-        pos = np.searchsorted(nl, hdr_starts)
-        hdr_ends = np.where(pos < nl.size, nl[np.minimum(pos, nl.size - 1)], n)
-    else:
-        hdr_ends = np.full(hdr_starts.size, n, dtype=np.int64)
 
     def put(name, lo, hi):
         if hi <= lo:
@@ -335,15 +323,24 @@ def _parse_fasta(data, truncate_names):
             names.append(name)
         arrays[name] = np.frombuffer(seq, dtype=np.uint8)
 
-    first = int(hdr_starts[0]) if hdr_starts.size else n
-    put("", 0, first)
-    for k in range(hdr_starts.size):
-        hs, he = int(hdr_starts[k]), int(hdr_ends[k])
-        raw = data[hs + 1:he].replace(b"\r", b"").decode("latin-1")
+    # a header is a '>' at the very start of the buffer or right after a '\n'
+    pos = 0 if data[:1] == b">" else data.find(b"\n>")
+    if pos < 0:
+        put("", 0, n)
+        return names, arrays
+    if pos > 0 or data[:1] != b">":
+        put("", 0, pos + 1)
+        pos += 1                                   # index of the '>'
+    while pos < n:
+        eol = data.find(b"\n", pos)
+        if eol < 0:
+            eol = n
+        raw = data[pos + 1:eol].replace(b"\r", b"").decode("latin-1")
         seqid = raw.split()[0] if truncate_names is True else raw
-        body_lo = min(he + 1, n)
-        body_hi = int(hdr_starts[k + 1]) if k + 1 < hdr_starts.size else n
-        put(seqid, body_lo, body_hi)
+        nxt = data.find(b"\n>", eol)
+        body_hi = n if nxt < 0 else nxt + 1
+        put(seqid, min(eol + 1, n), body_hi)
+        pos = n if nxt < 0 else nxt + 1
     return names, arrays
 
 

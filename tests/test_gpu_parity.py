@@ -350,3 +350,36 @@ def test_dna2orfs_entry_point(mg, tmp_path):
                     want.append(">%s-pos:%d\n%s\n" % (name, pos, orf))
                     pos += 3 * (1 + len(orf))
     assert got == "".join(want)
+
+
+# ---- configs 3 / 4 end to end through the API: synthetic FASTA + GFF3 / GTF text --------------------------------
+
+@pytest.mark.parametrize("flavour", ["gff3", "gtf"])
+def test_synthetic_annotation_text_through_api(mg, tmp_path, flavour):
+    """Scaled twins of config 3 (GFF3, gene->mRNA->exon+CDS, CDS rows of one mRNA share an ID: de-dup naming) and
+    config 4 (GTF with transcript_id/gene_id): FASTA text + annotation text -> Genome/read_gff/get_fasta vs the oracle."""
+    from magot_b200 import synth
+    from magot_b200 import genome_tools as gt
+    kind = "insect" if flavour == "gff3" else "human"
+    layout = synth.contig_layout(kind, 1_500_000, 3)
+    contigs = synth.synth_genome_host(layout, 3, n_mean=300)
+    ann = synth.synth_annotation(layout, 250, 3)
+    names = [n for n, _ in layout]
+    fa = tmp_path / "g.fa"
+    with open(fa, "wb") as fh:
+        for n, a in zip(names, contigs):
+            fh.write(b">" + n.encode() + b"\n")
+            for k in range(0, a.size, 60):
+                fh.write(a[k:k + 60].tobytes() + b"\n")
+    gff = tmp_path / ("a." + flavour)
+    gff.write_text(ann.to_gff3(names) if flavour == "gff3" else ann.to_gtf(names))
+    for kw in ({}, {"seq_type": "protein"}):
+        assert _stdout_of(gt.gff2fasta, str(fa), str(gff), **kw) == mo.gff2fasta(str(fa), str(gff), **kw)
+    # exon-based transcripts through the library call (base_features=['exon'], CDS ignored)
+    g = mg.Genome(str(fa))
+    g.read_gff(str(gff), base_features=['exon', 'match_part', 'similarity', 'region'], features_to_ignore=['CDS'])
+    seqs, _ = mo.read_fasta(str(fa))
+    aset = mo.read_gff(str(gff), base_features=['exon', 'match_part', 'similarity', 'region'], features_to_ignore=['CDS'])
+    aset.genome = seqs
+    assert g.annotations.get_fasta('gene') == mo.annotation_set_get_fasta(aset, 'gene')
+    assert g.annotations.get_fasta('gene', longest=True) == mo.annotation_set_get_fasta(aset, 'gene', longest=True)
