@@ -177,16 +177,20 @@ __device__ __forceinline__ uint64_t mg_rc_nib16(uint64_t v) {
 }
 
 // 8 nibbles -> 8 ASCII bytes.  Code 15 decodes to '?' and must be patched by the caller.
+// Branch-free: two 8-entry byte tables per half (PRMT), chosen per byte by bit 3 of the nibble.  The byte mask for
+// "bit 3 set" is one PRMT in sign-replicate mode: for the 16 bits n3 n2 n1 n0 of four nibbles, bit 3 of n1/n3 is the
+// sign bit of byte 0/1 of x, and bit 3 of n0/n2 is the sign bit of byte 0/1 of x << 4.
 __device__ __forceinline__ void mg_decode8(uint32_t x, uint32_t &o0, uint32_t &o1) {
     const uint32_t LA = 0x54474341u;  // "ACGT"
     const uint32_t LB = 0x74676361u;  // "acgt"
+    const uint32_t LC = 0x522D6E4Eu;  // "Nn-R"
+    const uint32_t LD = 0x3F4D4B59u;  // "YKM?"
+#ifdef MG_DECODE_BRANCHY
     const uint32_t s = x & 0x77777777u;
     o0 = __byte_perm(LA, LB, s & 0xFFFFu);
     o1 = __byte_perm(LA, LB, s >> 16);
     const uint32_t h = x & 0x88888888u;
     if (h) {
-        const uint32_t LC = 0x522D6E4Eu;  // "Nn-R"
-        const uint32_t LD = 0x3F4D4B59u;  // "YKM?"
         const uint32_t h0 = __byte_perm(LC, LD, s & 0xFFFFu);
         const uint32_t h1 = __byte_perm(LC, LD, s >> 16);
         uint32_t t = h & 0xFFFFu;
@@ -198,6 +202,17 @@ __device__ __forceinline__ void mg_decode8(uint32_t x, uint32_t &o0, uint32_t &o
         o0 = (o0 & ~m0) | (h0 & m0);
         o1 = (o1 & ~m1) | (h1 & m1);
     }
+#else
+    const uint32_t s = x & 0x77777777u, s1 = s >> 16;
+    const uint32_t x4 = x << 4;
+    uint32_t m0, m1;                                      // (__byte_perm drops selector bit 3, the sign-replicate flag)
+    asm("prmt.b32 %0, %1, %2, 0xD9C8;" : "=r"(m0) : "r"(x4), "r"(x));   // sign(x4.b0), sign(x.b0), sign(x4.b1), sign(x.b1)
+    asm("prmt.b32 %0, %1, %2, 0xFBEA;" : "=r"(m1) : "r"(x4), "r"(x));   // same for bytes 2, 3
+    const uint32_t a0 = __byte_perm(LA, LB, s), a1 = __byte_perm(LA, LB, s1);
+    const uint32_t h0 = __byte_perm(LC, LD, s), h1 = __byte_perm(LC, LD, s1);
+    o0 = (a0 & ~m0) | (h0 & m0);
+    o1 = (a1 & ~m1) | (h1 & m1);
+#endif
 }
 
 // ASCII -> nibble code (pack side)

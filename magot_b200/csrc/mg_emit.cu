@@ -30,9 +30,10 @@
 #include "mg_gather.cuh"
 
 #define NUC_THREADS 256
-#define NUC_CHUNKS (MG_NUC_TILE / 32 / NUC_THREADS)     // 4 chunks of 32 B per thread
 #define NUC_CAP 2048                                     // pieces staged per tile
 #define NUC_UNITS (MG_NUC_TILE / 64)
+#define NUC_ITERS (MG_NUC_TILE / 1024)                   // warp-iterations per tile (32 lanes x 32 bytes each)
+#define NUC_DEFER 512                                    // framing chunks listed per tile (a 32 KB tile of config 4 has ~40)
 
 #define PROT_THREADS 256
 #define PROT_CHUNKS (MG_PROT_TILE / 16 / PROT_THREADS)  // 4
@@ -72,6 +73,14 @@ __device__ __forceinline__ void ld_nib32(const uint32_t *__restrict__ pk, int64_
     n[1] = __funnelshift_r(w1, w2, sh);
     n[2] = __funnelshift_r(w2, w3, sh);
     n[3] = __funnelshift_r(w3, w4, sh);
+}
+
+// one word of the packed genome.  L2::64B: a piece is ~100 packed bytes at a random address; without the hint L2 fills
+// whole 128-byte lines from DRAM on a sector miss (measured: 1.6 x the sectors the SMs asked for), with it 64-byte halves.
+__device__ __forceinline__ uint32_t ld_pk(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
 }
 
 __device__ __forceinline__ void st32(uint8_t *p, const uint32_t w[8]) {          // one 256-bit store (STG.E.ENL2.256)
@@ -125,49 +134,56 @@ __device__ __noinline__ void nuc_chunk_generic(const uint32_t *__restrict__ pack
 }
 
 
-// rare path of K2: three or more pieces, or framing bytes, inside one 32-byte chunk: walk every staged piece.
-// Literal positions are left as placeholders (k_emit_lit writes them).
-__device__ __noinline__ void nuc_chunk_many(const uint32_t *__restrict__ packed, const int64_t *s_base, const int32_t *s_rel,
-                                            const uint8_t *s_kind, int A, int ncache, int p, int end, uint32_t n[4]) {
-    n[0] = n[1] = n[2] = n[3] = 0;
-    int lo = max(s_rel[A] - p, 0);
-    for (int k = A; k < ncache && s_rel[k] - p < end; k++) {
-        if (s_kind[k] == 1) continue;
-        const int hi = min(s_rel[k + 1] - p, end);
-        if (s_kind[k] == 2) { lo = hi; continue; }
-        uint32_t v[4];
-        ld_nib32(packed, s_base[k] + p, v);
+// Slow path of K2, one 32-byte chunk assembled from EVERY staged piece that reaches into it, genome and literal alike:
+// chunks that contain framing bytes (">ID\n", "\n"; ~1.5 per record), three or more pieces, or a byte outside the
+// packed alphabet.  Takes scalars only, so the fast path keeps its words in registers.
+__device__ __noinline__ void nuc_chunk_slow(const uint32_t *__restrict__ packed, const int64_t *s_base, const int32_t *s_rel,
+                                            const uint8_t *s_kind, const uint16_t *s_unit, int ncache, int p, int end, int64_t T,
+                                            const uint8_t *__restrict__ lit, const int64_t *__restrict__ exc_pos,
+                                            const uint8_t *__restrict__ exc_byte, int64_t n_exc, uint8_t *__restrict__ dst) {
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int k = s_unit[p >> 6];
+    while (s_rel[k + 1] <= p) k++;
+    for (; k < ncache && s_rel[k] - p < end; k++) {
+        const int lo = max(s_rel[k] - p, 0), hi = min(s_rel[k + 1] - p, end);
+        if (hi <= lo) continue;
+        const uint32_t m = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+        uint32_t b[8];
+        if (s_kind[k] == 2) {
+            ld_lit16(lit, s_base[k] + p, b);
+            ld_lit16(lit, s_base[k] + p + 16, b + 4);
+        } else {
+            uint32_t n[4];
+            const int64_t g = s_base[k] + p;
+            ld_nib32(packed, g, n);
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int a = min(max(lo - 8 * q, 0), 8), b = min(max(hi - 8 * q, 0), 8);
-            const uint32_t m = b > a ? ((0xFFFFFFFFu >> (32 - 4 * (b - a))) << (4 * a)) : 0u;
-            n[q] |= v[q] & m;
+            for (int q = 0; q < 4; q++) mg_decode8(n[q], b[2 * q], b[2 * q + 1]);
+            if (n_exc > 0 && g < T) {
+                for (int q = lo; q < hi; q++) {
+                    if (((n[q >> 3] >> ((q & 7) * 4)) & 15u) == MG_CODE_EXC) {
+                        const uint32_t c = mg_exc_byte(exc_pos, exc_byte, n_exc, g + q);
+                        b[q >> 2] = (b[q >> 2] & ~(0xFFu << ((q & 3) * 8))) | (c << ((q & 3) * 8));
+                    }
+                }
+            }
         }
-        lo = hi;
-    }
-}
-
-// rare path of K2: replace the placeholder of every code-15 nibble by the byte the FASTA had
-__device__ __noinline__ void nuc_patch_exceptions(const int64_t *s_base, const int32_t *s_rel, const uint8_t *s_kind, int A, int p,
-                                                  int end, int64_t T,
-                                                  const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte,
-                                                  int64_t n_exc, const uint32_t n[4], uint32_t w[8]) {
-    for (int t = 0; t < end; t++) {
-        if (((n[t >> 3] >> ((t & 7) * 4)) & 15u) != MG_CODE_EXC) continue;
-        int jj = A;
-        while (s_rel[jj + 1] - p <= t) jj++;
-        if (s_kind[jj] != 0) continue;                 // literal position: placeholder nibble, not a genome base
-        const int64_t gi = s_base[jj] + p + t;
-        if (gi < T) {
-            const uint32_t b = mg_exc_byte(exc_pos, exc_byte, n_exc, gi);
-            w[t >> 2] = (w[t >> 2] & ~(0xFFu << ((t & 3) * 8))) | (b << ((t & 3) * 8));
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t mk = expand4(m >> (4 * q));
+            w[q] = (w[q] & ~mk) | (b[q] & mk);
         }
     }
+    st32(dst, w);
 }
 
 // ---- K2 ---------------------------------------------------------------------------------------------------------
-// One lane = 32 output bytes = one 256-bit store.  A chunk normally lies inside a run of adjacent genome pieces: piece A holds its first byte, piece B (if A ends
-// inside the chunk) follows immediately; both are fetched branch-free and merged with one boundary mask.
+// One lane = 32 output bytes = one 256-bit store; every byte of the text is written exactly once, framing included.
+//  * fast path (a chunk of genome bases only): piece A holds its first byte, piece Y (if A ends inside the chunk) is the
+//    next non-empty genome piece; both are fetched branch-free and merged with one boundary mask.
+//  * chunks with framing bytes are known after staging (one bit per chunk); they are collected in a list and done FIRST,
+//    32 of them per warp, by the slow path -- instead of one lane per warp diverging into it in every iteration
+//    (measured 0.300 ms vs 0.20 ms for the exon launch of config 4).
+//  * the 32 warp-iterations of a tile are claimed from a shared counter, which evens out the warps that did slow chunks.
 #define PIECE_G 0
 #define PIECE_E 1        // empty (clamped-away segment, empty literal)
 #define PIECE_L 2        // non-empty literal
@@ -175,19 +191,24 @@ __global__ void __launch_bounds__(NUC_THREADS, 6) k_emit_nuc(
     const uint32_t *__restrict__ packed, const int64_t *__restrict__ piece_off, const int64_t *__restrict__ piece_src,
     int64_t n_piece, const int64_t *__restrict__ tile_first, int64_t total, int64_t T, const uint8_t *__restrict__ lit,
     const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte, int64_t n_exc, uint8_t *__restrict__ out) {
-    // pieces of the tile: piece i covers text [s_rel[i], s_rel[i+1]) relative to the tile; the nibble index of tile
-    // position q is s_base[i] + q; s_ng[i] = first non-empty GENOME piece at or after i
+    // pieces of the tile: piece i covers text [s_rel[i], s_rel[i+1]) relative to the tile; the nibble index (literal: byte
+    // index) of tile position q is s_base[i] + q; s_ng[i] = first non-empty GENOME piece at or after i
     __shared__ int64_t s_base[NUC_CAP + 2];
     __shared__ int32_t s_rel[NUC_CAP + 3];
     __shared__ uint16_t s_ng[NUC_CAP + 2];
     __shared__ uint8_t s_kind[NUC_CAP + 2];
     __shared__ uint16_t s_unit[NUC_UNITS];            // piece holding byte 64*u of the tile
+    __shared__ uint32_t s_litmap[NUC_ITERS];          // bit l of word w: chunk 32*w + l contains framing bytes
+    __shared__ uint16_t s_defer[NUC_DEFER];           // those chunks
+    __shared__ int s_ndefer, s_next;
     const int64_t P0 = (int64_t)blockIdx.x * MG_NUC_TILE;
     const int64_t p_lo = tile_first[blockIdx.x];
     int64_t p_hi = tile_first[blockIdx.x + 1] + 1;    // one past the last piece this tile can touch
     if (p_hi > n_piece) p_hi = n_piece;
     const int ncache = (int)min((int64_t)NUC_CAP, p_hi - p_lo);
     const int tile_len = (int)min((int64_t)MG_NUC_TILE, total - P0);
+    if (threadIdx.x < NUC_ITERS) s_litmap[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s_ndefer = 0; s_next = 0; }
     for (int i = threadIdx.x; i < ncache + 2; i += NUC_THREADS) {
         if (i < ncache) {
             const int64_t rel = __ldg(piece_off + p_lo + i) - P0;      // > -2^31: piece lengths are int32
@@ -213,60 +234,87 @@ __global__ void __launch_bounds__(NUC_THREADS, 6) k_emit_nuc(
             const int r0 = s_rel[i] < 0 ? 0 : s_rel[i], r1 = s_rel[i + 1] < 0 ? 0 : s_rel[i + 1];
             const int u1 = min((r1 + 63) >> 6, NUC_UNITS);
             for (int u = (r0 + 63) >> 6; u < u1; u++) s_unit[u] = (uint16_t)i;
+            if (s_kind[i] == PIECE_L && r1 > r0) {
+                for (int c = r0 >> 5; c <= (r1 - 1) >> 5; c++) {
+                    const uint32_t bit = 1u << (c & 31);
+                    if (!(atomicOr(&s_litmap[c >> 5], bit) & bit)) {
+                        const int slot = atomicAdd(&s_ndefer, 1);
+                        if (slot < NUC_DEFER) s_defer[slot] = (uint16_t)c;
+                    }
+                }
+            }
         }
     }
     __syncthreads();
     const int covered = s_rel[ncache];                // tile-relative position where the staged pieces end
+    const int lane = threadIdx.x & 31;
 
-#pragma unroll 1
-    for (int cidx = 0; cidx < NUC_CHUNKS; cidx++) {
-        const int p = (cidx * NUC_THREADS + (int)threadIdx.x) << 5;
-        if (p >= tile_len) break;
+    {   // chunks with framing bytes first (the list overflows only when records are shorter than ~64 bytes: then scan the map)
+        const int nd = s_ndefer;
+        const int n = nd <= NUC_DEFER ? nd : MG_NUC_TILE / 32;
+        for (int d = threadIdx.x; d < n; d += NUC_THREADS) {
+            int c = d;
+            if (nd <= NUC_DEFER) c = s_defer[d];
+            else if (!((s_litmap[d >> 5] >> (d & 31)) & 1u)) continue;
+            const int p = c << 5;
+            if (p + 32 > covered && covered < tile_len) continue;     // beyond the staged pieces: main loop, generic path
+            nuc_chunk_slow(packed, s_base, s_rel, s_kind, s_unit, ncache, p, min(32, tile_len - p), T, lit, exc_pos, exc_byte, n_exc,
+                           out + P0 + p);
+        }
+    }
+
+    const int n_iter = (tile_len + 1023) >> 10;
+    for (;;) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(&s_next, 1);
+        it = __shfl_sync(0xFFFFFFFFu, it, 0);
+        if (it >= n_iter) break;
+        const int p = (it * 32 + lane) << 5;
+        if (p >= tile_len) continue;
         if (p + 32 > covered && covered < tile_len) {  // staging overflowed: slow path straight from global memory
             const int64_t j = mg_search_le(piece_off, p_lo, n_piece, P0 + p);
             nuc_chunk_generic(packed, piece_off, piece_src, j, P0 + p, total, T, lit, exc_pos, exc_byte, n_exc, out);
             continue;
         }
+        if ((s_litmap[it] >> lane) & 1u) continue;     // done above
         int A = s_unit[p >> 6];
-        while (s_rel[A + 1] <= p) A++;                 // the (non-empty) piece that holds byte p
+        while (s_rel[A + 1] <= p) A++;                 // the non-empty piece that holds byte p: a genome piece
         const int end = min(32, tile_len - p);
-        // the first two GENOME pieces that reach into the chunk.  Literal positions before, between or after them get
-        // whatever nibbles happen to be there: k_emit_lit overwrites those bytes afterwards, so no lane ever branches
-        // on "is there framing in my chunk".
-        const int X = s_ng[A];
-        const bool hasX = s_rel[X] - p < end;
-        const int hiX = s_rel[X + 1] - p;              // X covers chunk positions [.., hiX)
-        const int Y = s_ng[X + 1];
-        const bool hasY = hasX && hiX < end && s_rel[Y] - p < end;
-        const bool third = hasY && s_rel[Y + 1] - p < end;             // a third genome piece inside 32 bytes: rare
-        uint32_t nX[4], nY[4];
-        ld_nib32(packed, hasX ? s_base[X] + p : (int64_t)MG_FRONT_PAD, nX);
-        ld_nib32(packed, hasY ? s_base[Y] + p : (int64_t)MG_FRONT_PAD, nY);
+        const int hiA = s_rel[A + 1] - p;              // A covers chunk positions [0, hiA)
+        const int Y = s_ng[A + 1];
+        const bool hasY = hiA < end && s_rel[Y] - p < end;
+        uint32_t rare = hasY && s_rel[Y + 1] - p < end;                // a third genome piece inside 32 bytes
+        const int64_t ga = s_base[A] + p;
+        const int64_t gy = hasY ? s_base[Y] + p : (int64_t)MG_FRONT_PAD;
+        const uint32_t *qa = packed + (ga >> 3), *qy = packed + (gy >> 3);
+        uint32_t ra[5], ry[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) { ra[k] = ld_pk(qa + k); ry[k] = ld_pk(qy + k); }
+        const uint32_t sha = ((uint32_t)ga & 7u) << 2, shy = ((uint32_t)gy & 7u) << 2;
+        const int c = hiA > 32 ? 32 : hiA;
         uint32_t n[4];
-        {   // positions < hiX come from X, the rest from Y
-            const int c = hiX > 32 ? 32 : hiX;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int t = c - 8 * k;
-                const uint32_t m = t >= 8 ? 0xFFFFFFFFu : (t <= 0 ? 0u : ((1u << (4 * t)) - 1u));
-                n[k] = (nX[k] & m) | (nY[k] & ~m);
-            }
+        for (int k = 0; k < 4; k++) {                  // positions < hiA come from A, the rest from Y
+            const int t = c - 8 * k;
+            const uint32_t m = t >= 8 ? 0xFFFFFFFFu : (t <= 0 ? 0u : ((1u << (4 * t)) - 1u));
+            n[k] = (__funnelshift_r(ra[k], ra[k + 1], sha) & m) | (__funnelshift_r(ry[k], ry[k + 1], shy) & ~m);
         }
-        if (third) nuc_chunk_many(packed, s_base, s_rel, s_kind, A, ncache, p, end, n);   // rare: generic walk
-        uint32_t w[8];
-#pragma unroll
-        for (int k = 0; k < 4; k++) mg_decode8(n[k], w[2 * k], w[2 * k + 1]);
         // code 15 = byte outside the packed alphabet on a '+' piece (the reverse plane already holds 'n',
-        // genome.py:791-792): fetch the exact byte the FASTA had (genome.py:606 keeps it).  Rare.
+        // genome.py:791-792): the exact byte the FASTA had must come out (genome.py:606 keeps it).  Rare.
         if (n_exc > 0) {
-            uint32_t any = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const uint32_t e = n[k] & (n[k] >> 1);
-                any |= e & (e >> 2) & 0x11111111u;
+                rare |= e & (e >> 2) & 0x11111111u;
             }
-            if (any) nuc_patch_exceptions(s_base, s_rel, s_kind, A, p, end, T, exc_pos, exc_byte, n_exc, n, w);
         }
+        if (rare) {
+            nuc_chunk_slow(packed, s_base, s_rel, s_kind, s_unit, ncache, p, end, T, lit, exc_pos, exc_byte, n_exc, out + P0 + p);
+            continue;
+        }
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) mg_decode8(n[k], w[2 * k], w[2 * k + 1]);
         st32(out + P0 + p, w);
     }
 }
@@ -520,11 +568,6 @@ extern "C" int mg_emit_nuc_device(mg_plan *p, uint8_t *out_dev, void *stream) {
     k_emit_nuc<<<(unsigned)p->n_nuc_tile, NUC_THREADS, 0, st>>>(g->d_packed, p->d_piece_off, p->d_piece_src, p->n_piece, p->d_nuc_tile,
                                                               p->nuc_total, g->total_bases, p->d_lit, g->d_exc_pos, g->d_exc_byte, g->n_exc, out_dev);
     MG_LAUNCH_CHECK();
-    if (p->n_lit > 0) {
-        k_emit_lit<<<(unsigned)((2 * p->n_rec + 255) / 256), 256, 0, st>>>(0, p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_prot_off,
-                                                                         p->d_rec_aa, p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, p->d_lit, out_dev);
-        MG_LAUNCH_CHECK();
-    }
     return MG_OK;
 }
 

@@ -197,14 +197,14 @@ extern "C" int mg_plan_create(mg_genome *g, int64_t n_rec, const int64_t *rec_se
     TRY(upload(p, &p->d_rec_lit_off, rec_lit_off, n_rec, st));
     TRY(upload(p, &p->d_rec_pre, rec_pre_len, n_rec, st));
     TRY(upload(p, &p->d_rec_suf, rec_suf_len, n_rec, st));
-    {   // literal bytes sit 16 bytes into a zeroed, padded buffer: the emit kernels fetch 16-byte windows that
-        // may start up to 15 bytes before / end up to 19 bytes after the literal they need
+    {   // literal bytes sit 64 bytes into a zeroed, padded buffer: the emit kernels fetch 32-byte windows (as aligned
+        // words) that may start up to 35 bytes before / end up to 39 bytes after the literal they need
         uint8_t *d = nullptr;
-        TRY(dalloc(p, &d, n_lit + 64, st));
-        rc = cudaMemsetAsync(d, 0, n_lit + 64, st) == cudaSuccess ? MG_OK : MG_ECUDA;
-        if (rc == MG_OK && n_lit > 0 && cudaMemcpyAsync(d + 16, lit, n_lit, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = MG_ECUDA;
+        TRY(dalloc(p, &d, n_lit + 128, st));
+        rc = cudaMemsetAsync(d, 0, n_lit + 128, st) == cudaSuccess ? MG_OK : MG_ECUDA;
+        if (rc == MG_OK && n_lit > 0 && cudaMemcpyAsync(d + 64, lit, n_lit, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = MG_ECUDA;
         if (rc) { mg_set_error("literal upload failed"); mg_plan_destroy(p); return rc; }
-        p->d_lit = d + 16;
+        p->d_lit = d + 64;
     }
     if (rec_phase) TRY(upload(p, &p->d_rec_phase, rec_phase, n_rec, st));
     TRY(dalloc(p, &p->d_blk_r0, (p->n_piece + 255) / 256 + 1, st));
