@@ -337,13 +337,18 @@ def gpu_arm(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
     nuc_events = []
 
+    step_events = []
+
     def device_step(record):
+        ea = ev()
+        ea.record(stream)
         prepare(plans["cds"])
-        e0, e1 = ev(), ev()
+        e0, e1, ep = ev(), ev(), ev()
         e0.record(stream)
         _lib.check(lib.mg_emit_nuc_device(plans["cds"], P(out_cds_n), sp))
         e1.record(stream)
         _lib.check(lib.mg_emit_prot_device(plans["cds"], P(out_cds_p), sp))
+        ep.record(stream)
         prepare(plans["exon"])
         e2, e3 = ev(), ev()
         e2.record(stream)
@@ -351,6 +356,7 @@ def gpu_arm(args):
         e3.record(stream)
         if record:
             nuc_events.append((e0, e1, e2, e3))
+            step_events.append((ea, e0, e1, ep, e2, e3))
 
     def barrier():
         torch.cuda.synchronize()
@@ -374,6 +380,9 @@ def gpu_arm(args):
     dev_ms = s_ev.elapsed_time(e_ev) / args.steps
     nuc_ms_cds = sum(a.elapsed_time(b) for a, b, _, _ in nuc_events) / len(nuc_events)
     nuc_ms_exon = sum(c.elapsed_time(d) for _, _, c, d in nuc_events) / len(nuc_events)
+    _seg = lambda i: sum(t[i].elapsed_time(t[i + 1]) for t in step_events) / len(step_events)   # noqa: E731
+    breakdown = {"k1_plan_cds_ms": round(_seg(0), 4), "k2_nuc_cds_ms": round(_seg(1), 4), "k3_prot_cds_ms": round(_seg(2), 4),
+                 "k1_plan_exon_ms": round(_seg(3), 4), "k2_nuc_exon_ms": round(_seg(4), 4)}
 
     # ---- end to end through the C ABI with host buffers
     host_cds_n = torch.empty(sizes["cds"][0], dtype=torch.uint8, pin_memory=True)
@@ -476,7 +485,8 @@ def gpu_arm(args):
                 "launches_per_step": 2, "avg_launch_ms": round((nuc_ms_cds + nuc_ms_exon) / 2, 4),
                 "algorithmic_bytes_per_launch": int((ab_cds + ab_exon) / 2),
                 "per_launch": {"cds": {"ms": round(nuc_ms_cds, 4), "GBps": round(ab_cds / nuc_ms_cds / 1e6, 1)},
-                               "exon": {"ms": round(nuc_ms_exon, 4), "GBps": round(ab_exon / nuc_ms_exon / 1e6, 1)}}}
+                               "exon": {"ms": round(nuc_ms_exon, 4), "GBps": round(ab_exon / nuc_ms_exon / 1e6, 1)}},
+                "step_breakdown_ms": breakdown}
 
     line = None
     if rank == 0:

@@ -103,10 +103,8 @@ struct mg_plan {
     uint8_t *d_lit = nullptr;
     // derived (device)
     int64_t *d_blk_r0 = nullptr;              // [n_piece/256] record owning the first piece of each 256-piece block
-    int32_t *d_piece_len = nullptr;           // [n_piece]
     int64_t *d_piece_src = nullptr;           // [n_piece]  src | kind<<62
     int64_t *d_piece_off = nullptr;           // [n_piece+1] exclusive prefix = offsets in the nucleotide text
-    int32_t *d_prot_len = nullptr;            // [n_rec] bytes of record r in the protein text
     int64_t *d_prot_off = nullptr;            // [n_rec+1]
     int32_t *d_rec_aa = nullptr;              // [n_rec] amino acids, -1 = reference returns None
     int8_t *d_rec_skip = nullptr;             // [n_rec] spliced bases skipped before the first codon (0..3)

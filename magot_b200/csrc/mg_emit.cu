@@ -30,15 +30,27 @@
 #include "mg_gather.cuh"
 
 #define NUC_THREADS 256
-#define NUC_CAP 2048                                     // pieces staged per tile
+#ifndef NUC_MINB
+#define NUC_MINB 8                                       // 32 registers, 64 resident warps per SM
+#endif
+#ifndef NUC_CAP
+#define NUC_CAP 768                                      // pieces staged per tile (a 32 KB tile of config 4 has ~200); small, so
+                                                         // that 8 CTAs fit and most of the SM's 256 KB stays L1 cache (measured +7 %)
+#endif
 #define NUC_UNITS (MG_NUC_TILE / 64)
-#define NUC_ITERS (MG_NUC_TILE / 1024)                   // warp-iterations per tile (32 lanes x 32 bytes each)
-#define NUC_DEFER 512                                    // framing chunks listed per tile (a 32 KB tile of config 4 has ~40)
+#define NUC_CHUNKS (MG_NUC_TILE / 32 / NUC_THREADS)     // 4 chunks of 32 B per thread
 
 #define PROT_THREADS 256
 #define PROT_CHUNKS (MG_PROT_TILE / 16 / PROT_THREADS)  // 4
-#define PROT_RCAP 512                                    // records staged per tile
-#define PROT_PCAP 2048                                   // pieces staged per tile
+#ifndef PROT_MINB
+#define PROT_MINB 6
+#endif
+#ifndef PROT_RCAP
+#define PROT_RCAP 256                                    // records staged per tile (a 16 KB tile of config 4 has ~45)
+#endif
+#ifndef PROT_PCAP
+#define PROT_PCAP 768                                    // pieces staged per tile (~300); small for the same reason as NUC_CAP
+#endif
 #define PROT_UNITS (MG_PROT_TILE / 64)
 
 #define BIG 0x7fffffff
@@ -177,17 +189,18 @@ __device__ __noinline__ void nuc_chunk_slow(const uint32_t *__restrict__ packed,
 }
 
 // ---- K2 ---------------------------------------------------------------------------------------------------------
-// One lane = 32 output bytes = one 256-bit store; every byte of the text is written exactly once, framing included.
-//  * fast path (a chunk of genome bases only): piece A holds its first byte, piece Y (if A ends inside the chunk) is the
-//    next non-empty genome piece; both are fetched branch-free and merged with one boundary mask.
-//  * chunks with framing bytes are known after staging (one bit per chunk); they are collected in a list and done FIRST,
-//    32 of them per warp, by the slow path -- instead of one lane per warp diverging into it in every iteration
-//    (measured 0.300 ms vs 0.20 ms for the exon launch of config 4).
-//  * the 32 warp-iterations of a tile are claimed from a shared counter, which evens out the warps that did slow chunks.
+// One lane = 32 output bytes = one 256-bit store.
+//  * a chunk normally lies inside a run of genome pieces: X is the first genome piece that reaches into it, Y (if X ends
+//    inside the chunk) the next one; both are fetched branch-free and merged with one boundary mask.  Framing bytes
+//    (">ID\n", "\n") before, between or after them get whatever nibbles happen to be there: no lane ever branches on
+//    "is there framing in my chunk" (doing so costs a ~300-instruction divergent path in almost every warp-iteration).
+//  * after the tile's chunks are stored, the CTA writes the framing bytes of its tile over those positions, one thread
+//    per literal piece.  The lines are still in L2, so this costs no DRAM traffic; as a separate kernel after K2 it was
+//    0.028 ms per launch of config 4, assembling the framing chunks in a slow path inside K2 +17 % instructions.
 #define PIECE_G 0
 #define PIECE_E 1        // empty (clamped-away segment, empty literal)
 #define PIECE_L 2        // non-empty literal
-__global__ void __launch_bounds__(NUC_THREADS, 6) k_emit_nuc(
+__global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_nuc(
     const uint32_t *__restrict__ packed, const int64_t *__restrict__ piece_off, const int64_t *__restrict__ piece_src,
     int64_t n_piece, const int64_t *__restrict__ tile_first, int64_t total, int64_t T, const uint8_t *__restrict__ lit,
     const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte, int64_t n_exc, uint8_t *__restrict__ out) {
@@ -198,17 +211,12 @@ __global__ void __launch_bounds__(NUC_THREADS, 6) k_emit_nuc(
     __shared__ uint16_t s_ng[NUC_CAP + 2];
     __shared__ uint8_t s_kind[NUC_CAP + 2];
     __shared__ uint16_t s_unit[NUC_UNITS];            // piece holding byte 64*u of the tile
-    __shared__ uint32_t s_litmap[NUC_ITERS];          // bit l of word w: chunk 32*w + l contains framing bytes
-    __shared__ uint16_t s_defer[NUC_DEFER];           // those chunks
-    __shared__ int s_ndefer, s_next;
     const int64_t P0 = (int64_t)blockIdx.x * MG_NUC_TILE;
     const int64_t p_lo = tile_first[blockIdx.x];
     int64_t p_hi = tile_first[blockIdx.x + 1] + 1;    // one past the last piece this tile can touch
     if (p_hi > n_piece) p_hi = n_piece;
     const int ncache = (int)min((int64_t)NUC_CAP, p_hi - p_lo);
     const int tile_len = (int)min((int64_t)MG_NUC_TILE, total - P0);
-    if (threadIdx.x < NUC_ITERS) s_litmap[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { s_ndefer = 0; s_next = 0; }
     for (int i = threadIdx.x; i < ncache + 2; i += NUC_THREADS) {
         if (i < ncache) {
             const int64_t rel = __ldg(piece_off + p_lo + i) - P0;      // > -2^31: piece lengths are int32
@@ -234,70 +242,43 @@ __global__ void __launch_bounds__(NUC_THREADS, 6) k_emit_nuc(
             const int r0 = s_rel[i] < 0 ? 0 : s_rel[i], r1 = s_rel[i + 1] < 0 ? 0 : s_rel[i + 1];
             const int u1 = min((r1 + 63) >> 6, NUC_UNITS);
             for (int u = (r0 + 63) >> 6; u < u1; u++) s_unit[u] = (uint16_t)i;
-            if (s_kind[i] == PIECE_L && r1 > r0) {
-                for (int c = r0 >> 5; c <= (r1 - 1) >> 5; c++) {
-                    const uint32_t bit = 1u << (c & 31);
-                    if (!(atomicOr(&s_litmap[c >> 5], bit) & bit)) {
-                        const int slot = atomicAdd(&s_ndefer, 1);
-                        if (slot < NUC_DEFER) s_defer[slot] = (uint16_t)c;
-                    }
-                }
-            }
         }
     }
     __syncthreads();
     const int covered = s_rel[ncache];                // tile-relative position where the staged pieces end
-    const int lane = threadIdx.x & 31;
 
-    {   // chunks with framing bytes first (the list overflows only when records are shorter than ~64 bytes: then scan the map)
-        const int nd = s_ndefer;
-        const int n = nd <= NUC_DEFER ? nd : MG_NUC_TILE / 32;
-        for (int d = threadIdx.x; d < n; d += NUC_THREADS) {
-            int c = d;
-            if (nd <= NUC_DEFER) c = s_defer[d];
-            else if (!((s_litmap[d >> 5] >> (d & 31)) & 1u)) continue;
-            const int p = c << 5;
-            if (p + 32 > covered && covered < tile_len) continue;     // beyond the staged pieces: main loop, generic path
-            nuc_chunk_slow(packed, s_base, s_rel, s_kind, s_unit, ncache, p, min(32, tile_len - p), T, lit, exc_pos, exc_byte, n_exc,
-                           out + P0 + p);
-        }
-    }
-
-    const int n_iter = (tile_len + 1023) >> 10;
-    for (;;) {
-        int it = 0;
-        if (lane == 0) it = atomicAdd(&s_next, 1);
-        it = __shfl_sync(0xFFFFFFFFu, it, 0);
-        if (it >= n_iter) break;
-        const int p = (it * 32 + lane) << 5;
-        if (p >= tile_len) continue;
+#pragma unroll 1
+    for (int cidx = 0; cidx < NUC_CHUNKS; cidx++) {
+        const int p = (cidx * NUC_THREADS + (int)threadIdx.x) << 5;
+        if (p >= tile_len) break;
         if (p + 32 > covered && covered < tile_len) {  // staging overflowed: slow path straight from global memory
             const int64_t j = mg_search_le(piece_off, p_lo, n_piece, P0 + p);
             nuc_chunk_generic(packed, piece_off, piece_src, j, P0 + p, total, T, lit, exc_pos, exc_byte, n_exc, out);
             continue;
         }
-        if ((s_litmap[it] >> lane) & 1u) continue;     // done above
         int A = s_unit[p >> 6];
-        while (s_rel[A + 1] <= p) A++;                 // the non-empty piece that holds byte p: a genome piece
+        while (s_rel[A + 1] <= p) A++;                 // the (non-empty) piece that holds byte p
         const int end = min(32, tile_len - p);
-        const int hiA = s_rel[A + 1] - p;              // A covers chunk positions [0, hiA)
-        const int Y = s_ng[A + 1];
-        const bool hasY = hiA < end && s_rel[Y] - p < end;
+        const int X = s_ng[A];
+        const bool hasX = s_rel[X] - p < end;
+        const int hiX = s_rel[X + 1] - p;              // X covers chunk positions [.., hiX)
+        const int Y = s_ng[X + 1];
+        const bool hasY = hasX && hiX < end && s_rel[Y] - p < end;
         uint32_t rare = hasY && s_rel[Y + 1] - p < end;                // a third genome piece inside 32 bytes
-        const int64_t ga = s_base[A] + p;
+        const int64_t gx = hasX ? s_base[X] + p : (int64_t)MG_FRONT_PAD;
         const int64_t gy = hasY ? s_base[Y] + p : (int64_t)MG_FRONT_PAD;
-        const uint32_t *qa = packed + (ga >> 3), *qy = packed + (gy >> 3);
-        uint32_t ra[5], ry[5];
+        const uint32_t *qx = packed + (gx >> 3), *qy = packed + (gy >> 3);
+        uint32_t rx[5], ry[5];
 #pragma unroll
-        for (int k = 0; k < 5; k++) { ra[k] = ld_pk(qa + k); ry[k] = ld_pk(qy + k); }
-        const uint32_t sha = ((uint32_t)ga & 7u) << 2, shy = ((uint32_t)gy & 7u) << 2;
-        const int c = hiA > 32 ? 32 : hiA;
+        for (int k = 0; k < 5; k++) { rx[k] = ld_pk(qx + k); ry[k] = ld_pk(qy + k); }
+        const uint32_t shx = ((uint32_t)gx & 7u) << 2, shy = ((uint32_t)gy & 7u) << 2;
+        const int c = hiX > 32 ? 32 : hiX;
         uint32_t n[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {                  // positions < hiA come from A, the rest from Y
+        for (int k = 0; k < 4; k++) {                  // positions < hiX come from X, the rest from Y
             const int t = c - 8 * k;
             const uint32_t m = t >= 8 ? 0xFFFFFFFFu : (t <= 0 ? 0u : ((1u << (4 * t)) - 1u));
-            n[k] = (__funnelshift_r(ra[k], ra[k + 1], sha) & m) | (__funnelshift_r(ry[k], ry[k + 1], shy) & ~m);
+            n[k] = (__funnelshift_r(rx[k], rx[k + 1], shx) & m) | (__funnelshift_r(ry[k], ry[k + 1], shy) & ~m);
         }
         // code 15 = byte outside the packed alphabet on a '+' piece (the reverse plane already holds 'n',
         // genome.py:791-792): the exact byte the FASTA had must come out (genome.py:606 keeps it).  Rare.
@@ -317,36 +298,36 @@ __global__ void __launch_bounds__(NUC_THREADS, 6) k_emit_nuc(
         for (int k = 0; k < 4; k++) mg_decode8(n[k], w[2 * k], w[2 * k + 1]);
         st32(out + P0 + p, w);
     }
+
+    // framing bytes of this tile, over the placeholders the chunks above left (same CTA, ordered by the barrier)
+    __syncthreads();
+    for (int i = threadIdx.x; i < ncache; i += NUC_THREADS) {                      // one thread per piece (~50 literal pieces per tile)
+        if (s_kind[i] != PIECE_L) continue;
+        const int r0 = max(s_rel[i], 0), r1 = min(s_rel[i + 1], tile_len);
+        const uint8_t *src = lit + s_base[i];
+        uint8_t *dst = out + P0;
+        for (int q = r0; q < r1; q++) dst[q] = __ldg(src + q);
+    }
 }
 
-// ---- literal framing bytes (">ID\n" prefixes, "\n" suffixes): one thread per literal piece ------------------------
-// Runs AFTER K2 / K3 on the same stream and overwrites the placeholder bytes they left at those positions.  Folding
-// this into K2 (1 lane active, ~1.5 chunks per record) or writing whole literal chunks from a second kernel were both
-// measured slower on B200 (0.300 / 0.251 ms vs 0.204 + 0.027 ms per exon launch of config 4).
-// which = 0: nucleotide text (positions from piece_off); which = 1: protein text (positions from prot_off).
-__global__ void __launch_bounds__(256) k_emit_lit(int which, int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
-                                                  const int64_t *__restrict__ piece_off, const int64_t *__restrict__ prot_off,
-                                                  const int32_t *__restrict__ rec_aa, const int64_t *__restrict__ rec_lit_off,
-                                                  const int32_t *__restrict__ rec_pre, const int32_t *__restrict__ rec_suf,
-                                                  const uint8_t *__restrict__ lit, uint8_t *__restrict__ out) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= 2 * n_rec) return;
-    const int64_t r = i >> 1;
-    const bool suffix = i & 1;
-    const int pre = rec_pre[r];
-    const int n = suffix ? rec_suf[r] : pre;
-    if (n <= 0) return;
-    const uint8_t *src = lit + rec_lit_off[r] + (suffix ? pre : 0);
-    int64_t dst;
-    if (which == 0) {
-        const int64_t f0 = rec_seg_off[r] + 2 * r, f1 = rec_seg_off[r + 1] + 2 * (r + 1);
-        dst = suffix ? piece_off[f1 - 1] : piece_off[f0];
-    } else {
+// ---- K3 framing bytes (">ID\n" prefixes, "\n" suffixes) of one protein tile, one thread per record -----------------------
+// Runs at the end of the CTA that wrote the tile's residues, over the zero bytes it left at those positions: the lines are
+// still in L2, so this costs no DRAM traffic (as a separate kernel after K3 it was 0.025 ms per launch of config 4).
+__device__ __forceinline__ void prot_write_framing(int64_t r_lo, int64_t r_hi, int64_t P0, int tile_len,
+                                                   const int64_t *__restrict__ prot_off, const int32_t *__restrict__ rec_aa,
+                                                   const int64_t *__restrict__ rec_lit_off, const int32_t *__restrict__ rec_pre,
+                                                   const int32_t *__restrict__ rec_suf, const uint8_t *__restrict__ lit,
+                                                   uint8_t *__restrict__ out) {
+    for (int64_t r = r_lo + threadIdx.x; r < r_hi; r += blockDim.x) {
+        const int pre = rec_pre[r], suf = rec_suf[r];
         int32_t naa = rec_aa[r];
         if (naa < 0) naa = 0;
-        dst = prot_off[r] + (suffix ? pre + naa : 0);
+        const int64_t a = __ldg(prot_off + r) - P0;            // tile-relative start of the record
+        const uint8_t *src = lit + rec_lit_off[r];
+        const int64_t e = a + pre + naa;                       // suffix position
+        for (int64_t q = max(a, (int64_t)0); q < min(a + pre, (int64_t)tile_len); q++) out[P0 + q] = __ldg(src + (q - a));
+        for (int64_t q = max(e, (int64_t)0); q < min(e + suf, (int64_t)tile_len); q++) out[P0 + q] = __ldg(src + pre + (q - e));
     }
-    for (int k = 0; k < n; k++) out[dst + k] = __ldg(src + k);
 }
 
 // ---- K3 -------------------------------------------------------------------------------------------------------
@@ -388,7 +369,7 @@ __device__ __noinline__ void prot_gather_many(const uint32_t *__restrict__ packe
         const uint32_t sh = ((uint32_t)g & 7u) << 2;
         uint32_t w[7];
 #pragma unroll
-        for (int k = 0; k < 7; k++) w[k] = __ldg(pp + k);
+        for (int k = 0; k < 7; k++) w[k] = ld_pk(pp + k);
 #pragma unroll
         for (int k = 0; k < 6; k++) {
             const int a = min(max(lo - 8 * k, 0), 8), b = min(max(hi - 8 * k, 0), 8);
@@ -401,10 +382,11 @@ __device__ __noinline__ void prot_gather_many(const uint32_t *__restrict__ packe
 // Output chunk = 16 bytes of protein text.  Amino acid a of record r is the codon at spliced offset
 // skip[r] + 3a; the 4096-entry nibble-triplet table (case-insensitive, anything non-ACGT -> 'X') sits in
 // shared memory.  Stop codons are emitted as '*' and translation continues (genome.py:811-818).
-__global__ void __launch_bounds__(PROT_THREADS) k_emit_prot(
+__global__ void __launch_bounds__(PROT_THREADS, PROT_MINB) k_emit_prot(
     const uint32_t *__restrict__ packed, const int64_t *__restrict__ piece_off, const int64_t *__restrict__ piece_src,
     const int64_t *__restrict__ rec_seg_off, const int64_t *__restrict__ prot_off, const int32_t *__restrict__ rec_aa,
-    const int8_t *__restrict__ rec_skip, const int32_t *__restrict__ rec_pre, int64_t n_rec,
+    const int8_t *__restrict__ rec_skip, const int32_t *__restrict__ rec_pre, const int32_t *__restrict__ rec_suf,
+    const int64_t *__restrict__ rec_lit_off, const uint8_t *__restrict__ lit, int64_t n_rec,
     const int64_t *__restrict__ tile_first, int64_t total, const uint8_t *__restrict__ aa4096, uint8_t *__restrict__ out) {
     __shared__ __align__(16) uint8_t s_aa[4096];
     // records of the tile: residues occupy protein-text positions [r_s[i], r_e[i]) relative to the tile (empty when the
@@ -436,6 +418,8 @@ __global__ void __launch_bounds__(PROT_THREADS) k_emit_prot(
             prot_chunk_generic(packed, piece_off, piece_src, rec_seg_off, prot_off, rec_aa, rec_skip, rec_pre, r, P0 + p, total,
                                aa4096, out);
         }
+        __syncthreads();
+        if (lit) prot_write_framing(r_lo, r_hi, P0, tile_len, prot_off, rec_aa, rec_lit_off, rec_pre, rec_suf, lit, out);
         return;
     }
     const int nraw = (int)nraw64;
@@ -514,7 +498,7 @@ __global__ void __launch_bounds__(PROT_THREADS) k_emit_prot(
                 const uint32_t shx = ((uint32_t)gx & 7u) << 2, shy = ((uint32_t)gy & 7u) << 2;
                 uint32_t wx[7], wy[7];
 #pragma unroll
-                for (int k = 0; k < 7; k++) { wx[k] = __ldg(px + k); wy[k] = __ldg(py + k); }
+                for (int k = 0; k < 7; k++) { wx[k] = ld_pk(px + k); wy[k] = ld_pk(py + k); }
                 const int c = eX - q;                 // nibbles [0, c) of the 48 come from X, the rest from Y
 #pragma unroll
                 for (int k = 0; k < 6; k++) {
@@ -542,6 +526,8 @@ __global__ void __launch_bounds__(PROT_THREADS) k_emit_prot(
         }
         mg_st16(out + P0 + p, bw[0], bw[1], bw[2], bw[3]);
     }
+    __syncthreads();
+    if (lit) prot_write_framing(r_lo, r_hi, P0, tile_len, prot_off, rec_aa, rec_lit_off, rec_pre, rec_suf, lit, out);
 }
 
 // ---- host API -----------------------------------------------------------------------------------------------
@@ -581,14 +567,10 @@ extern "C" int mg_emit_prot_device(mg_plan *p, uint8_t *out_dev, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     p->last_stream = st;
     k_emit_prot<<<(unsigned)p->n_prot_tile, PROT_THREADS, 0, st>>>(g->d_packed, p->d_piece_off, p->d_piece_src, p->d_rec_seg_off,
-                                                                 p->d_prot_off, p->d_rec_aa, p->d_rec_skip, p->d_rec_pre, p->n_rec,
+                                                                 p->d_prot_off, p->d_rec_aa, p->d_rec_skip, p->d_rec_pre, p->d_rec_suf,
+                                                                 p->d_rec_lit_off, p->n_lit > 0 ? p->d_lit : nullptr, p->n_rec,
                                                                  p->d_prot_tile, p->prot_total, g->d_aa4096, out_dev);
     MG_LAUNCH_CHECK();
-    if (p->n_lit > 0) {
-        k_emit_lit<<<(unsigned)((2 * p->n_rec + 255) / 256), 256, 0, st>>>(1, p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_prot_off,
-                                                                         p->d_rec_aa, p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, p->d_lit, out_dev);
-        MG_LAUNCH_CHECK();
-    }
     return MG_OK;
 }
 

@@ -16,24 +16,25 @@
 #include <algorithm>
 #include "mg_common.cuh"
 #include "mg_gather.cuh"
+#include "mg_lookback.cuh"
 
 // ---- kernels ----------------------------------------------------------------------------------------
 
-// thread per 256-piece block: record that owns the block's first piece (largest r with F(r) = rec_seg_off[r]+2r <= 256*b)
+#define PLAN_ITEMS 4                                 // pieces per thread of k_plan_pieces
+#define PLAN_TILE (256 * PLAN_ITEMS)                 // pieces per block: large enough that the look-back never serialises
+
+// thread per record: record r owns pieces [F(r), F(r+1)), F(r) = rec_seg_off[r] + 2r; it writes itself into every
+// PLAN_TILE-piece block whose first piece it owns (coalesced and search-free; a binary search per block was 10 us of dependent loads)
 __global__ void __launch_bounds__(256) k_plan_block_rec(int64_t n_block, int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
                                                         int64_t *__restrict__ blk_r0) {
-    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (b >= n_block) return;
-    const int64_t pb = b * 256;
-    int64_t lo = 0, hi = n_rec;
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(rec_seg_off + mid) + 2 * mid <= pb) lo = mid; else hi = mid;
-    }
-    blk_r0[b] = lo;
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const int64_t f0 = __ldg(rec_seg_off + r) + 2 * r, f1 = __ldg(rec_seg_off + r + 1) + 2 * (r + 1);
+    for (int64_t b = (f0 + PLAN_TILE - 1) / PLAN_TILE; b * PLAN_TILE < f1 && b < n_block; b++) blk_r0[b] = r;
 }
 
-// thread per piece: find its record, clamp like a Python slice, write len + src
+// thread per piece: find its record, clamp like a Python slice, write src and -- through a block scan of the lengths plus a
+// decoupled look-back across blocks (mg_lookback.cuh) -- the piece's offset in the nucleotide text, all in one launch
 __global__ void __launch_bounds__(256) k_plan_pieces(int64_t n_piece, int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
                                                      const int64_t *__restrict__ blk_r0,
                                                      const int32_t *__restrict__ seg_contig, const int64_t *__restrict__ seg_start,
@@ -41,63 +42,92 @@ __global__ void __launch_bounds__(256) k_plan_pieces(int64_t n_piece, int64_t n_
                                                      const int64_t *__restrict__ rec_lit_off, const int32_t *__restrict__ rec_pre,
                                                      const int32_t *__restrict__ rec_suf, const int64_t *__restrict__ contig_len,
                                                      const int64_t *__restrict__ contig_base, int64_t n_contigs, int64_t two_T,
-                                                     int32_t *__restrict__ piece_len, int64_t *__restrict__ piece_src) {
-    // The 256 pieces of a block belong to at most 129 consecutive records starting at blk_r0[block] (found by
-    // k_plan_block_rec, 35 global searches per SM instead of one per thread): F(r) = rec_seg_off[r] + 2r of those
-    // records is staged in shared memory and every thread searches there.
-    __shared__ int64_t s_F[258];
-    const int64_t pb = blockIdx.x * (int64_t)blockDim.x;
-    const int64_t r0 = blk_r0[blockIdx.x];
-    for (int i = threadIdx.x; i < 258; i += blockDim.x) {
+                                                     unsigned long long *tmp, int64_t *__restrict__ piece_off,
+                                                     int64_t *__restrict__ piece_src, int64_t *__restrict__ total_out) {
+    // The PLAN_TILE pieces of a block belong to at most PLAN_TILE/2 + 1 consecutive records starting at blk_r0[block]
+    // (k_plan_block_rec): F(r) = rec_seg_off[r] + 2r of those records is staged in shared memory and every thread
+    // searches there.
+    __shared__ int64_t s_F[PLAN_TILE / 2 + 2];
+    __shared__ int64_t s_warp[8];
+    __shared__ int64_t s_prefix;
+    __shared__ unsigned int s_tile;
+    const int64_t tile = mg_next_tile(tmp, &s_tile);
+    const int64_t pb = tile * PLAN_TILE;
+    const int64_t r0 = blk_r0[tile];
+    for (int i = threadIdx.x; i < PLAN_TILE / 2 + 2; i += blockDim.x) {
         const int64_t r = r0 + i;
         s_F[i] = r <= n_rec ? __ldg(rec_seg_off + r) + 2 * r : INT64_MAX;
     }
     __syncthreads();
-    const int64_t p = pb + threadIdx.x;
-    if (p >= n_piece) return;
-    int lo = 0, hi = 257;                              // F(r0) <= p < F(r0 + 257) because F grows by >= 2 per record
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (s_F[mid] <= p) lo = mid; else hi = mid;
-    }
-    const int64_t r = r0 + lo;
-    const int64_t s0 = s_F[lo] - 2 * r, s1 = s_F[lo + 1] - 2 * (r + 1);
-    const int64_t local = p - (s0 + 2 * r);
-    if (local == 0) {                                   // literal prefix
-        piece_len[p] = rec_pre[r];
-        piece_src[p] = rec_lit_off[r] | (int64_t)(MG_KIND_LIT << MG_KIND_SHIFT);
-    } else if (local == s1 - s0 + 1) {                  // literal suffix
-        piece_len[p] = rec_suf[r];
-        piece_src[p] = (rec_lit_off[r] + rec_pre[r]) | (int64_t)(MG_KIND_LIT << MG_KIND_SHIFT);
-    } else {                                            // genome segment
-        const int64_t e = s0 + local - 1;
-        const int32_t c = seg_contig[e];
-        int64_t len = 0, src = MG_FRONT_PAD;
-        if (c >= 0 && c < n_contigs) {
-            const int64_t L = contig_len[c];
-            // contig[start-1:end] with Python slice semantics (genome.py:606)
-            int64_t i = seg_start[e] - 1, j = seg_end[e];
-            if (i < 0) { i += L; if (i < 0) i = 0; } else if (i > L) i = L;
-            if (j < 0) { j += L; if (j < 0) j = 0; } else if (j > L) j = L;
-            len = j > i ? j - i : 0;
-            if (len > 0x7fffffff) len = 0x7fffffff;     // rejected on the host side (see mg_plan_prepare)
-            src = contig_base[c] + i;
+    int64_t loc[PLAN_ITEMS];                           // exclusive offset of the piece inside the block
+    int64_t run = 0;
+#pragma unroll
+    for (int it = 0; it < PLAN_ITEMS; it++) {
+        const int64_t p = pb + it * 256 + threadIdx.x;
+        int64_t len = 0;
+        if (p < n_piece) {
+            int lo = 0, hi = PLAN_TILE / 2 + 1;        // F(r0) <= p < F(r0 + PLAN_TILE/2 + 1): F grows by >= 2 per record
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_F[mid] <= p) lo = mid; else hi = mid;
+            }
+            const int64_t r = r0 + lo;
+            const int64_t s0 = s_F[lo] - 2 * r, s1 = s_F[lo + 1] - 2 * (r + 1);
+            const int64_t local = p - (s0 + 2 * r);
+            if (local == 0) {                           // literal prefix
+                len = rec_pre[r];
+                piece_src[p] = rec_lit_off[r] | (int64_t)(MG_KIND_LIT << MG_KIND_SHIFT);
+            } else if (local == s1 - s0 + 1) {          // literal suffix
+                len = rec_suf[r];
+                piece_src[p] = (rec_lit_off[r] + rec_pre[r]) | (int64_t)(MG_KIND_LIT << MG_KIND_SHIFT);
+            } else {                                    // genome segment
+                const int64_t e = s0 + local - 1;
+                const int32_t c = seg_contig[e];
+                int64_t src = MG_FRONT_PAD;
+                if (c >= 0 && c < n_contigs) {
+                    const int64_t L = contig_len[c];
+                    // contig[start-1:end] with Python slice semantics (genome.py:606)
+                    int64_t i = seg_start[e] - 1, j = seg_end[e];
+                    if (i < 0) { i += L; if (i < 0) i = 0; } else if (i > L) i = L;
+                    if (j < 0) { j += L; if (j < 0) j = 0; } else if (j > L) j = L;
+                    len = j > i ? j - i : 0;
+                    if (len > 0x7fffffff) len = 0x7fffffff;
+                    src = contig_base[c] + i;
+                }
+                // '-' strand: forward bases [src, src+len) are bases [2T-src-len, 2T-src) of the reverse-complement plane,
+                // in exactly the order Sequence.reverse_compliment emits them (genome.py:784-793)
+                piece_src[p] = seg_strand[e] ? two_T - src - len : src;
+            }
         }
-        piece_len[p] = (int32_t)len;
-        // '-' strand: forward bases [src, src+len) are bases [2T-src-len, 2T-src) of the reverse-complement plane,
-        // in exactly the order Sequence.reverse_compliment emits them (genome.py:784-793)
-        piece_src[p] = seg_strand[e] ? two_T - src - len : src;
+        int64_t total;
+        const int64_t incl = mg_block_incl_scan(len, s_warp, &total);
+        loc[it] = run + incl - len;
+        run += total;
     }
+    const int64_t prefix = mg_lookback(tmp, tile, run, &s_prefix);
+#pragma unroll
+    for (int it = 0; it < PLAN_ITEMS; it++) {
+        const int64_t p = pb + it * 256 + threadIdx.x;
+        if (p < n_piece) piece_off[p] = prefix + loc[it];
+    }
+    if (tile == gridDim.x - 1 && threadIdx.x == 0) { piece_off[n_piece] = prefix + run; *total_out = prefix + run; }
 }
 
-// thread per record: spliced length -> amino-acid count (Sequence.translate, genome.py:810-821)
+// thread per record: spliced length -> amino-acid count (Sequence.translate, genome.py:810-821) and, with the same
+// scan + look-back, the record's offset in the protein text
 __global__ void __launch_bounds__(256) k_plan_records(int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
                                                       const int64_t *__restrict__ piece_off, const int64_t *__restrict__ piece_src,
                                                       const uint32_t *__restrict__ packed, const int8_t *__restrict__ rec_phase,
                                                       int flags, int32_t *__restrict__ rec_aa, int8_t *__restrict__ rec_skip,
-                                                      int32_t *__restrict__ prot_len) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= n_rec) return;
+                                                      unsigned long long *tmp, int64_t *__restrict__ prot_off,
+                                                      int64_t *__restrict__ total_out) {
+    __shared__ int64_t s_warp[8];
+    __shared__ int64_t s_prefix;
+    __shared__ unsigned int s_tile;
+    const int64_t tile = mg_next_tile(tmp, &s_tile);
+    const int64_t r = tile * (int64_t)blockDim.x + threadIdx.x;
+    int64_t plen = 0;
+    if (r < n_rec) {
     const int64_t f0 = rec_seg_off[r] + 2 * r, f1 = rec_seg_off[r + 1] + 2 * (r + 1);
     const int64_t pay0 = piece_off[f0 + 1], pay1 = piece_off[f1 - 1];
     const int64_t pre = pay0 - piece_off[f0], suf = piece_off[f1] - pay1;
@@ -122,14 +152,24 @@ __global__ void __launch_bounds__(256) k_plan_records(int64_t n_rec, const int64
     if (naa > 0x7fffffff) naa = 0x7fffffff;
     rec_aa[r] = (int32_t)naa;
     rec_skip[r] = (int8_t)skip;
-    prot_len[r] = (int32_t)(pre + (naa > 0 ? naa : 0) + suf);
+    plen = pre + (naa > 0 ? naa : 0) + suf;
+    }
+    int64_t total;
+    const int64_t incl = mg_block_incl_scan(plen, s_warp, &total);
+    const int64_t prefix = mg_lookback(tmp, tile, total, &s_prefix);
+    if (r < n_rec) prot_off[r] = prefix + incl - plen;
+    if (tile == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) { prot_off[n_rec] = prefix + total; *total_out = prefix + total; }
 }
 
-// thread per tile: index of the piece / record that contains the tile's first byte
-__global__ void __launch_bounds__(256) k_plan_tiles(const int64_t *__restrict__ off, int64_t n, int64_t tile_bytes,
-                                                    int64_t n_tile, int64_t *__restrict__ tile_first) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t > n_tile) return;
+// thread per tile: index of the piece / record that contains the tile's first byte; nucleotide tiles first, then protein tiles
+__global__ void __launch_bounds__(256) k_plan_tiles(const int64_t *__restrict__ off_a, int64_t n_a, int64_t tile_a, int64_t n_tile_a,
+                                                    int64_t *__restrict__ first_a, const int64_t *__restrict__ off_b, int64_t n_b,
+                                                    int64_t tile_b, int64_t n_tile_b, int64_t *__restrict__ first_b) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t *off = off_a;
+    int64_t n = n_a, tile_bytes = tile_a, n_tile = n_tile_a, *tile_first = first_a;
+    if (t > n_tile_a) { t -= n_tile_a + 1; off = off_b; n = n_b; tile_bytes = tile_b; n_tile = n_tile_b; tile_first = first_b; }
+    if (t > n_tile || n_tile == 0) return;
     if (t == n_tile) { tile_first[t] = n > 0 ? n - 1 : 0; return; }
     tile_first[t] = mg_search_le(off, 0, n, t * tile_bytes);
 }
@@ -207,15 +247,14 @@ extern "C" int mg_plan_create(mg_genome *g, int64_t n_rec, const int64_t *rec_se
         p->d_lit = d + 64;
     }
     if (rec_phase) TRY(upload(p, &p->d_rec_phase, rec_phase, n_rec, st));
-    TRY(dalloc(p, &p->d_blk_r0, (p->n_piece + 255) / 256 + 1, st));
-    TRY(dalloc(p, &p->d_piece_len, p->n_piece, st));
+    TRY(dalloc(p, &p->d_blk_r0, (p->n_piece + PLAN_TILE - 1) / PLAN_TILE + 1, st));
     TRY(dalloc(p, &p->d_piece_src, p->n_piece, st));
     TRY(dalloc(p, &p->d_piece_off, p->n_piece + 1, st));
-    TRY(dalloc(p, &p->d_prot_len, n_rec, st));
     TRY(dalloc(p, &p->d_prot_off, n_rec + 1, st));
     TRY(dalloc(p, &p->d_rec_aa, n_rec, st));
     TRY(dalloc(p, &p->d_rec_skip, n_rec, st));
-    p->scan_tmp_cap = mg_scan_tmp_elems(std::max(p->n_piece, n_rec)) + 2;
+    // look-back scratch: [ticket, status per 256-piece block] [ticket, status per 256-record block] [nuc total, prot total]
+    p->scan_tmp_cap = (p->n_piece + PLAN_TILE - 1) / PLAN_TILE + 1 + (n_rec + 255) / 256 + 1 + 2;
     TRY(dalloc(p, &p->d_scan_tmp, p->scan_tmp_cap, st));
 #undef TRY
     *out = p;
@@ -240,24 +279,22 @@ extern "C" int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, i
     p->last_stream = st;
     int64_t totals[2] = {0, 0};
     if (p->n_rec > 0) {
-        const int64_t n_block = (p->n_piece + 255) / 256;
-        k_plan_block_rec<<<(unsigned)((n_block + 255) / 256), 256, 0, st>>>(n_block, p->n_rec, p->d_rec_seg_off, p->d_blk_r0);
+        const int64_t n_block = (p->n_piece + PLAN_TILE - 1) / PLAN_TILE, n_rblock = (p->n_rec + 255) / 256;
+        unsigned long long *tmp_a = reinterpret_cast<unsigned long long *>(p->d_scan_tmp), *tmp_b = tmp_a + n_block + 1;
+        int64_t *d_totals = reinterpret_cast<int64_t *>(tmp_b + n_rblock + 1);
+        MG_CUDA(cudaMemsetAsync(p->d_scan_tmp, 0, p->scan_tmp_cap * sizeof(int64_t), st));
+        k_plan_block_rec<<<(unsigned)n_rblock, 256, 0, st>>>(n_block, p->n_rec, p->d_rec_seg_off, p->d_blk_r0);
         MG_LAUNCH_CHECK();
         k_plan_pieces<<<(unsigned)n_block, 256, 0, st>>>(
             p->n_piece, p->n_rec, p->d_rec_seg_off, p->d_blk_r0, p->d_seg_contig, p->d_seg_start, p->d_seg_end, p->d_seg_strand,
             p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, g->d_contig_len, g->d_contig_base, g->n_contigs, 2 * g->total_bases,
-            p->d_piece_len, p->d_piece_src);
+            tmp_a, p->d_piece_off, p->d_piece_src, d_totals);
         MG_LAUNCH_CHECK();
-        int rc = mg_scan_i32(p->d_piece_len, p->d_piece_off, p->n_piece, p->d_scan_tmp, p->scan_tmp_cap, st);
-        if (rc) return rc;
-        k_plan_records<<<(unsigned)((p->n_rec + 255) / 256), 256, 0, st>>>(
+        k_plan_records<<<(unsigned)n_rblock, 256, 0, st>>>(
             p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_piece_src, g->d_packed, p->d_rec_phase, prot_flags,
-            p->d_rec_aa, p->d_rec_skip, p->d_prot_len);
+            p->d_rec_aa, p->d_rec_skip, tmp_b, p->d_prot_off, d_totals + 1);
         MG_LAUNCH_CHECK();
-        rc = mg_scan_i32(p->d_prot_len, p->d_prot_off, p->n_rec, p->d_scan_tmp, p->scan_tmp_cap, st);
-        if (rc) return rc;
-        MG_CUDA(cudaMemcpyAsync(&totals[0], p->d_piece_off + p->n_piece, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-        MG_CUDA(cudaMemcpyAsync(&totals[1], p->d_prot_off + p->n_rec, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        MG_CUDA(cudaMemcpyAsync(totals, d_totals, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         MG_CUDA(cudaStreamSynchronize(st));
     }
     p->nuc_total = totals[0];
@@ -275,14 +312,10 @@ extern "C" int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, i
     }
     p->d_nuc_tile = p->d_tile_buf;
     p->d_prot_tile = p->d_tile_buf + p->n_nuc_tile + 1;
-    if (p->n_nuc_tile > 0) {
-        k_plan_tiles<<<(unsigned)((p->n_nuc_tile + 256) / 256), 256, 0, st>>>(p->d_piece_off, p->n_piece, MG_NUC_TILE,
-                                                                              p->n_nuc_tile, p->d_nuc_tile);
-        MG_LAUNCH_CHECK();
-    }
-    if (p->n_prot_tile > 0) {
-        k_plan_tiles<<<(unsigned)((p->n_prot_tile + 256) / 256), 256, 0, st>>>(p->d_prot_off, p->n_rec, MG_PROT_TILE,
-                                                                               p->n_prot_tile, p->d_prot_tile);
+    if (p->n_nuc_tile + p->n_prot_tile > 0) {
+        k_plan_tiles<<<(unsigned)((p->n_nuc_tile + p->n_prot_tile + 2 + 255) / 256), 256, 0, st>>>(
+            p->d_piece_off, p->n_piece, MG_NUC_TILE, p->n_nuc_tile, p->d_nuc_tile, p->d_prot_off, p->n_rec, MG_PROT_TILE, p->n_prot_tile,
+            p->d_prot_tile);
         MG_LAUNCH_CHECK();
     }
     p->prepared = true;
