@@ -9,19 +9,30 @@
 // strands from the same forward read: reverse-strand stops TAA/TAG/TGA are TTA/CTA/TCA forward).
 // Every stream (contig, frame, strand) is a chain of stops in ascending genome coordinate, bracketed
 // by a virtual stop at each contig end; each consecutive pair of stops bounds one ORF, attributed to
-// the HIGHER stop.  "Previous stop" is a prefix-max: warp shuffles inside the CTA, a three-phase
-// max-scan across CTA tiles.  Two passes over the genome count and emit (the ORF count is data
-// dependent), a prefix sum assigns output slots in reference order (plus strands ascend, minus
-// strands descend), and the residues are produced by a flat 16-residue-per-thread gather like K3.
+// the HIGHER stop.  "Previous stop" is a prefix-max: warp shuffles inside the CTA, a decoupled look-back
+// across CTA tiles.  ONE pass over the genome (k_six_scan) finds the stops, counts the kept ORFs per
+// (tile, stream) and lists them; a prefix sum of the counts assigns output slots in reference order
+// (plus strands ascend, minus strands descend; k_six_place), and the residues are produced by a flat
+// 16-residue-per-thread gather like K3 (k_six_aa).  Only when the kept ORFs do not fit the hit list
+// (tiny min_aa: an ORF every few bases) a second genome pass writes them (k_six_orfs<true>).
 #include <algorithm>
 #include "mg_common.cuh"
 
 #define SIX_THREADS 256
 #define SIX_BPT 48                                   // bases per thread
 #define SIX_TILE (SIX_THREADS * SIX_BPT)             // 12288 bases per CTA (multiple of 3 and of 16)
+#ifndef SIX_SCAN_MINB
+#define SIX_SCAN_MINB 4
+#endif
 #define AA_TILE 8192
 #define AA_THREADS 256
 #define AA_CAP 512
+
+struct SixHit {                                      // one kept ORF found by the scan pass, placed later (k_six_place)
+    int32_t tile, rank;                              // rank among the kept ORFs of (tile, stream), ascending position
+    int32_t xl, xh;                                  // contig offsets of the bounding stops
+    uint8_t s, xl_real, xh_real, pad;
+};
 
 struct mg_sixframe_state {
     int64_t contig_lo = 0, contig_hi = 0, min_aa = 0;
@@ -30,9 +41,11 @@ struct mg_sixframe_state {
     int64_t *d_tile_base = nullptr;
     int32_t *d_cs = nullptr;                         // [nc*6] first-codon offset of each stream
     int64_t *d_m = nullptr;                          // [nc*6] residues in each stream's translation
-    int64_t *d_tile_last = nullptr;                  // [6][n_tiles] last stop (global base index) or -1
     int64_t *d_carry = nullptr;                      // [6][n_tiles] last stop before the tile
-    int64_t *d_chunk = nullptr;                      // max-scan scratch
+    unsigned long long *d_look = nullptr;            // [1 + 6*n_tiles] ticket + look-back status words of the carry max-scan
+    struct SixHit *d_hits = nullptr;                 // kept ORFs in discovery order (single-pass path)
+    int64_t hit_cap = 0;
+    unsigned long long *d_hit_count = nullptr;
     int32_t *d_cnt = nullptr;                        // [n_tiles*6] kept ORFs per (contig, stream, tile) in output order
     int64_t *d_cnt_off = nullptr;                    // [n_tiles*6+1]
     int64_t *d_scan_tmp = nullptr;
@@ -190,114 +203,7 @@ __device__ __forceinline__ void tile_info(int64_t tile, const int64_t *__restric
     }
 }
 
-// ---- pass A: last stop of every stream in every tile ------------------------------------------------
-__global__ void __launch_bounds__(SIX_THREADS) k_six_last(const uint32_t *__restrict__ packed, const int64_t *__restrict__ tile_base,
-                                                          int64_t nc, int64_t contig_lo, const int64_t *__restrict__ contig_len,
-                                                          const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
-                                                          const int64_t *__restrict__ m, int64_t n_tiles,
-                                                          int64_t *__restrict__ tile_last) {
-    __shared__ TileInfo ti;
-    __shared__ int s_last[6];
-    if (threadIdx.x == 0) tile_info(blockIdx.x, tile_base, nc, contig_lo, contig_len, contig_base, cs, m, ti);
-    if (threadIdx.x < 6) s_last[threadIdx.x] = -1;
-    __syncthreads();
-    const int64_t x0 = ti.k * SIX_TILE + (int64_t)threadIdx.x * SIX_BPT;
-    if (x0 < ti.L) {
-        SixMasks sm;
-        six_masks(packed, ti.gb, ti.L, x0, ti.cs, sm);
-#pragma unroll
-        for (int s = 0; s < 6; s++) {
-            int first, last;
-            stream_first_last(sm, s, ti.Lm3, first, last);
-            if (last >= 0) atomicMax(&s_last[s], (int)threadIdx.x * SIX_BPT + last);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-        const int v = s_last[threadIdx.x];
-        tile_last[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = v < 0 ? -1 : ti.gb + ti.k * SIX_TILE + v;
-    }
-}
-
-// ---- pass B: exclusive max-scan of tile_last along tiles, one row per stream (blockIdx.y) ----------------
-#define MS_THREADS 256
-#define MS_ITEMS 8
-#define MS_TILE (MS_THREADS * MS_ITEMS)
-
-__device__ __forceinline__ int64_t warp_incl_max(int64_t v) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int64_t t = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d && t > v) v = t;
-    }
-    return v;
-}
-// exclusive max-scan across the block (identity -1); *total = block max
-__device__ __forceinline__ int64_t block_excl_max(int64_t v, int64_t *s_warp, int64_t *total) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t inc = warp_incl_max(v);
-    if (lane == 31) s_warp[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        int64_t w = lane < (MS_THREADS / 32) ? s_warp[lane] : -1;
-        w = warp_incl_max(w);
-        if (lane < (MS_THREADS / 32)) s_warp[lane] = w;
-    }
-    __syncthreads();
-    int64_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
-    if (lane == 0) ex = -1;
-    if (wid && s_warp[wid - 1] > ex) ex = s_warp[wid - 1];
-    *total = s_warp[MS_THREADS / 32 - 1];
-    __syncthreads();
-    return ex;
-}
-__global__ void __launch_bounds__(MS_THREADS) k_ms_reduce(const int64_t *__restrict__ in, int64_t n, int64_t nb, int64_t *__restrict__ cmax) {
-    __shared__ int64_t s_warp[MS_THREADS / 32];
-    const int64_t *row = in + (int64_t)blockIdx.y * n;
-    const int64_t base = (int64_t)blockIdx.x * MS_TILE;
-    int64_t v = -1;
-    for (int j = 0; j < MS_ITEMS; j++) {
-        const int64_t i = base + j * MS_THREADS + threadIdx.x;
-        if (i < n && row[i] > v) v = row[i];
-    }
-    int64_t total;
-    block_excl_max(v, s_warp, &total);
-    if (threadIdx.x == 0) cmax[(int64_t)blockIdx.y * nb + blockIdx.x] = total;
-}
-__global__ void __launch_bounds__(MS_THREADS) k_ms_chunks(int64_t *__restrict__ cmax, int64_t nb) {
-    __shared__ int64_t s_warp[MS_THREADS / 32];
-    int64_t *row = cmax + (int64_t)blockIdx.y * nb;
-    int64_t carry = -1;
-    for (int64_t b0 = 0; b0 < nb; b0 += MS_THREADS) {
-        const int64_t i = b0 + threadIdx.x;
-        const int64_t v = i < nb ? row[i] : -1;
-        int64_t total;
-        int64_t ex = block_excl_max(v, s_warp, &total);
-        if (carry > ex) ex = carry;
-        if (i < nb) row[i] = ex;
-        if (total > carry) carry = total;
-    }
-}
-__global__ void __launch_bounds__(MS_THREADS) k_ms_apply(const int64_t *__restrict__ in, int64_t n, int64_t nb,
-                                                         const int64_t *__restrict__ cmax, int64_t *__restrict__ out) {
-    __shared__ int64_t s_warp[MS_THREADS / 32];
-    const int64_t *row = in + (int64_t)blockIdx.y * n;
-    int64_t *orow = out + (int64_t)blockIdx.y * n;
-    const int64_t base = (int64_t)blockIdx.x * MS_TILE;
-    int64_t carry = cmax[(int64_t)blockIdx.y * nb + blockIdx.x];
-    for (int j = 0; j < MS_ITEMS; j++) {
-        const int64_t i = base + j * MS_THREADS + threadIdx.x;
-        const int64_t v = i < n ? row[i] : -1;
-        int64_t total;
-        int64_t ex = block_excl_max(v, s_warp, &total);
-        if (carry > ex) ex = carry;
-        if (i < n) orow[i] = ex;
-        if (total > carry) carry = total;
-    }
-}
-
-// ---- passes C/D: count, then emit, the kept ORFs of every tile ---------------------------------------------
+// ---- ORF enumeration shared by the single-pass scan (k_six_scan) and the dense-output second pass (k_six_orfs) ----
 // ORF between a lower stop xl and a higher stop xh of one stream (contig offsets; !xl_real = virtual stop at
 // the low end of the contig, !xh_real = virtual stop at the high end).  Residue index of a stop at x:
 // plus (x-cs)/3, minus (L-3-cs-x)/3 (descending in x).
@@ -323,10 +229,12 @@ __device__ __forceinline__ int64_t layout_index(const TileInfo &ti, const int64_
 
 // Enumerate the ORFs this thread owns in stream s (each ORF belongs to its higher stop).  WRITE == false: count.
 // WRITE == true: k-th kept ORF (ascending position) goes to slot0 + k ('+') or slot0 + (n_mine-1-k) ('-').
-template <bool WRITE>
+// WRITE == 2: k-th kept ORF goes to hits[slot0 + k] with rank n_mine + k (n_mine = kept ORFs of lower threads).
+template <int WRITE>
 __device__ __forceinline__ int enumerate_stream(const TileInfo &ti, const SixMasks &sm, int s, int64_t x0, int64_t prev,
                                                 bool is_end_thread, int64_t min_aa, int64_t two_T, int64_t slot0, int n_mine,
-                                                mg_orf *__restrict__ recs, int32_t *__restrict__ lens, int64_t *__restrict__ srcs) {
+                                                mg_orf *__restrict__ recs, int32_t *__restrict__ lens, int64_t *__restrict__ srcs,
+                                                SixHit *__restrict__ hits = nullptr, int32_t tile = 0, int fl = -2) {
     if (ti.m[s] <= 0) return 0;                       // `if translated_seq:` (genome.py:832)
     const int plus = s & 1;
     int k = 0;
@@ -343,7 +251,12 @@ __device__ __forceinline__ int enumerate_stream(const TileInfo &ti, const SixMas
         if (plus) span3 = (int64_t)(real ? qh : 3 * m32) - (xl_real ? ql : -3) - 3;
         else span3 = (int64_t)(xl_real ? ql : 3 * m32) - (real ? qh : -3) - 3;
         if (span3 >= need3) {
-            if (WRITE) {
+            if (WRITE == 2) {
+                SixHit h;
+                h.tile = tile; h.rank = n_mine + k; h.xl = (int32_t)xl; h.xh = (int32_t)xh;
+                h.s = (uint8_t)s; h.xl_real = xl_real; h.xh_real = real; h.pad = 0;
+                hits[slot0 + k] = h;
+            } else if (WRITE == 1) {
                 int64_t st, ln;
                 orf_of(plus, ti.L, ti.cs[s], ti.m[s], xl, xh, xl_real, real, st, ln);
                 const int64_t slot = slot0 + (plus ? k : n_mine - 1 - k);
@@ -361,8 +274,9 @@ __device__ __forceinline__ int enumerate_stream(const TileInfo &ti, const SixMas
     if (min_aa >= 16) {
         // Two stops of one stream inside a thread's 48 bases are < 16 codons apart, so only the FIRST stop of the thread
         // (and the virtual stop at the contig end) can close an ORF of >= 16 residues: no loop over stops.
-        int first, last;
-        stream_first_last(sm, s, ti.Lm3, first, last);
+        int first, last;                              // fl: (first, last) packed by the caller, -2 = not known
+        if (fl != -2) { first = (fl & 0xFF) - 1; last = ((fl >> 8) & 0xFF) - 1; }
+        else stream_first_last(sm, s, ti.Lm3, first, last);
         if (first >= 0) visit(prev, prev >= 0, x0 + first, true);
         if (is_end_thread) {
             const int64_t xl = last >= 0 ? x0 + last : prev;
@@ -470,7 +384,7 @@ __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
     int my_cnt[6];
 #pragma unroll
     for (int s = 0; s < 6; s++)
-        my_cnt[s] = active ? enumerate_stream<false>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, 0, 0, nullptr, nullptr, nullptr) : 0;
+        my_cnt[s] = active ? enumerate_stream<0>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, 0, 0, nullptr, nullptr, nullptr) : 0;
 
     if (!EMIT) {
 #pragma unroll
@@ -499,10 +413,173 @@ __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
                 // '+': ascending, my first ORF has rank = exclusive prefix; '-': descending, ranks count from the top
                 const int64_t rank0 = (s & 1) ? inc - my_cnt[s] : tot - inc;
                 const int64_t slot0 = cnt_off[layout_index(ti, tile_base, contig_lo, s)] + rank0;
-                enumerate_stream<true>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, slot0, my_cnt[s], recs, lens, srcs);
+                enumerate_stream<1>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, slot0, my_cnt[s], recs, lens, srcs);
             }
         }
     }
+}
+
+// ---- single pass: stops, carry, count and the kept ORFs themselves ------------------------------------------------
+// Replaces pass A (k_six_last), pass B (k_ms_*) and pass C (k_six_orfs<false>), and -- when the kept ORFs fit the hit
+// buffer, which they do for any practical min_aa -- pass D (k_six_orfs<true>) as well: the genome is read ONCE.
+//  * the carry (last stop of each stream before the tile) comes from a decoupled look-back over the tiles' own last
+//    stops.  Stop positions ascend with the tile index, so a tile that contains a stop publishes its inclusive prefix at
+//    once and the look-back of its successor ends after one step; warps 0..5 do the six streams in parallel.
+//  * kept ORFs are rare (one per ~3 kb for min_aa = 100): they are appended to a hit list in discovery order (one atomic
+//    per tile) with their rank inside (tile, stream); k_six_place puts them into reference order after the prefix sum of
+//    the per-(tile, stream) counts.
+#define SIX_LOOK_NONE 0ull
+#define SIX_LOOK_SUM (1ull << 62)                    // tile has no stop in this stream, prefix not known yet
+#define SIX_LOOK_PREFIX (2ull << 62)                 // value = 1 + last stop at or before the end of this tile (0 = none)
+#define SIX_LOOK_MASK (3ull << 62)
+
+__global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
+    const uint32_t *__restrict__ packed, const int64_t *__restrict__ tile_base, int64_t nc, int64_t contig_lo,
+    const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
+    const int64_t *__restrict__ m, int64_t n_tiles, unsigned long long *look, int64_t *__restrict__ carry_out, int64_t min_aa,
+    int64_t two_T, int32_t *__restrict__ cnt, SixHit *__restrict__ hits, int64_t hit_cap, unsigned long long *hit_count) {
+    __shared__ TileInfo ti;
+    __shared__ int64_t s_warp[SIX_THREADS / 32];
+    __shared__ int s_wlast[6][SIX_THREADS / 32];     // per-warp max of `last stop in thread`
+    __shared__ int64_t s_carry[6];
+    __shared__ int64_t s_tile;
+    __shared__ long long s_base;
+    if (threadIdx.x == 0) {
+        const int64_t t = (int64_t)atomicAdd(look, 1ull);              // tiles in launch order: look-back never waits on a
+        s_tile = t;                                                      // tile that has not started
+        tile_info(t, tile_base, nc, contig_lo, contig_len, contig_base, cs, m, ti);
+    }
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t tile0 = ti.k * SIX_TILE;
+    const int64_t x0 = tile0 + (int64_t)threadIdx.x * SIX_BPT;
+    const bool active = x0 < ti.L;
+    const bool is_end_thread = active && (x0 + SIX_BPT >= ti.L);       // owns the virtual high-end stops
+    SixMasks sm;
+    if (active) six_masks(packed, ti.gb, ti.L, x0, ti.cs, sm);
+    else { sm.pm[0] = sm.pm[1] = sm.pm[2] = sm.mm[0] = sm.mm[1] = sm.mm[2] = 0; }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+    int ex_local[6], fl[6];                          // fl: (first + 1) | (last + 1) << 8 of the thread's stops per stream
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        int first, last;
+        stream_first_last(sm, s, ti.Lm3, first, last);
+        fl[s] = (first + 1) | ((last + 1) << 8);
+        int inc = last < 0 ? -1 : (int)threadIdx.x * SIX_BPT + last;   // tile-local position
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d && t > inc) inc = t;
+        }
+        if (lane == 31) s_wlast[s][wid] = inc;
+        int ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) ex = -1;
+        ex_local[s] = ex;
+    }
+    __syncthreads();
+    if (wid < 6) {                                    // warp s: publish the tile's last stop of stream s, look back for the carry
+        const int s = wid;
+        volatile unsigned long long *st = look + 1 + (int64_t)s * n_tiles;
+        int agg = -1;
+#pragma unroll
+        for (int w = 0; w < SIX_THREADS / 32; w++) agg = max(agg, s_wlast[s][w]);
+        const unsigned long long own = agg >= 0 ? (unsigned long long)(ti.gb + tile0 + agg + 1) : 0ull;
+        if (lane == 0) st[tile] = (agg >= 0 || tile == 0) ? (SIX_LOOK_PREFIX | own) : SIX_LOOK_SUM;
+        unsigned long long best = 0;                  // 1 + last stop before this tile, 0 = none
+        int64_t j = tile - 1 - lane;
+        while (true) {
+            unsigned long long w = SIX_LOOK_PREFIX;   // before tile 0: nothing
+            if (j >= 0) { do { w = st[j]; } while ((w & SIX_LOOK_MASK) == SIX_LOOK_NONE); }
+            const unsigned int done = __ballot_sync(0xffffffffu, (w & SIX_LOOK_MASK) == SIX_LOOK_PREFIX);
+            if (done) {                               // nearest tile with a known prefix; tiles nearer than it hold no stop
+                best = __shfl_sync(0xffffffffu, w & ~SIX_LOOK_MASK, __ffs(done) - 1);
+                break;
+            }
+            j -= 32;
+        }
+        if (lane == 0) {
+            s_carry[s] = (int64_t)best - 1;
+            carry_out[(int64_t)s * n_tiles + tile] = (int64_t)best - 1;
+            if (agg < 0 && tile > 0) st[tile] = SIX_LOOK_PREFIX | best;
+        }
+    }
+    __syncthreads();
+    int64_t prev[6];
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        int ex = ex_local[s];
+        for (int w = 0; w < wid; w++) ex = max(ex, s_wlast[s][w]);
+        if (ex >= 0) prev[s] = tile0 + ex;            // contig offset
+        else {
+            const int64_t cg = s_carry[s];            // global base index; < gb: other contig
+            prev[s] = (cg >= ti.gb) ? cg - ti.gb : -1;
+        }
+    }
+    int my_cnt[6];
+    int mine = 0;
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        my_cnt[s] = active ? enumerate_stream<0>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, fl[s]) : 0;
+        mine += my_cnt[s];
+    }
+    const int any = __syncthreads_or(mine);
+    if (!any) {
+        if (threadIdx.x < 6) cnt[layout_index(ti, tile_base, contig_lo, threadIdx.x)] = 0;
+        return;
+    }
+    // ranks inside the tile: block prefix sums of the per-thread counts, three 21-bit fields per word
+    const int64_t pk0 = (int64_t)my_cnt[0] | ((int64_t)my_cnt[1] << 21) | ((int64_t)my_cnt[2] << 42);
+    const int64_t pk1 = (int64_t)my_cnt[3] | ((int64_t)my_cnt[4] << 21) | ((int64_t)my_cnt[5] << 42);
+    int64_t tot0, tot1;
+    const int64_t in0 = block_incl_sum(pk0, s_warp, &tot0);
+    const int64_t in1 = block_incl_sum(pk1, s_warp, &tot1);
+    int tot[6], before[6];                            // kept ORFs of the tile per stream; of the streams before s
+    int run = 0;
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        tot[s] = (int)(((s < 3 ? tot0 : tot1) >> (21 * (s % 3))) & 0x1FFFFF);
+        before[s] = run;
+        run += tot[s];
+    }
+    if (threadIdx.x < 6) cnt[layout_index(ti, tile_base, contig_lo, threadIdx.x)] = tot[threadIdx.x];
+    if (threadIdx.x == 0) s_base = (long long)atomicAdd(hit_count, (unsigned long long)run);
+    __syncthreads();
+    const int64_t base = s_base;
+    if (base + run > hit_cap || !active) return;      // overflow: the host falls back to the two-pass emit
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        if (my_cnt[s] == 0) continue;
+        const int excl = (int)(((s < 3 ? in0 : in1) >> (21 * (s % 3))) & 0x1FFFFF) - my_cnt[s];
+        enumerate_stream<2>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, base + before[s] + excl, excl, nullptr, nullptr, nullptr,
+                            hits, (int32_t)tile, fl[s]);
+    }
+}
+
+// thread per hit: reference-order slot of the ORF and its record
+__global__ void __launch_bounds__(256) k_six_place(const SixHit *__restrict__ hits, int64_t n_hit, const int64_t *__restrict__ tile_base,
+                                                   int64_t nc, int64_t contig_lo, const int64_t *__restrict__ contig_len,
+                                                   const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
+                                                   const int64_t *__restrict__ m, const int64_t *__restrict__ cnt_off, int64_t two_T,
+                                                   mg_orf *__restrict__ recs, int32_t *__restrict__ lens, int64_t *__restrict__ srcs) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_hit) return;
+    const SixHit h = hits[i];
+    TileInfo ti;
+    tile_info(h.tile, tile_base, nc, contig_lo, contig_len, contig_base, cs, m, ti);
+    const int s = h.s, plus = s & 1;
+    const int64_t li = layout_index(ti, tile_base, contig_lo, s);
+    const int64_t o0 = cnt_off[li], n = cnt_off[li + 1] - o0;
+    const int64_t slot = o0 + (plus ? h.rank : n - 1 - h.rank);
+    int64_t st, ln;
+    orf_of(plus, ti.L, ti.cs[s], ti.m[s], h.xl, h.xh, h.xl_real, h.xh_real, st, ln);
+    mg_orf o;
+    o.contig = (int32_t)ti.c; o.frame = (int8_t)(s >> 1); o.minus = (int8_t)(!plus); o.pad = 0;
+    o.start = st; o.len = ln; o.aa_off = 0;
+    recs[slot] = o;
+    lens[slot] = (int32_t)ln;
+    const int64_t q = ti.cs[s] + 3 * st;                                // oriented offset of the ORF's first base
+    srcs[slot] = plus ? (ti.gb + q) : (two_T - ti.gb - ti.L + q);      // '-': forward read of the reverse plane
 }
 
 __global__ void __launch_bounds__(256) k_six_fill_off(int64_t n_orf, const int64_t *__restrict__ aa_off, mg_orf *__restrict__ recs) {
@@ -642,26 +719,20 @@ extern "C" int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig
     MG_CUDA(cudaMemcpyAsync(s->d_tile_base, s->h_tile_base.data(), (nc + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     TRY(six_alloc(s, &s->d_cs, nc * 6));
     TRY(six_alloc(s, &s->d_m, nc * 6));
-    TRY(six_alloc(s, &s->d_tile_last, s->n_tiles * 6));
     TRY(six_alloc(s, &s->d_carry, s->n_tiles * 6));
-    const int64_t nb = (s->n_tiles + MS_TILE - 1) / MS_TILE;
-    TRY(six_alloc(s, &s->d_chunk, nb * 6));
     TRY(six_alloc(s, &s->d_cnt, s->n_tiles * 6));
     TRY(six_alloc(s, &s->d_cnt_off, s->n_tiles * 6 + 1));
+    TRY(six_alloc(s, &s->d_look, 6 * s->n_tiles + 2));
+    s->d_hit_count = s->d_look + 6 * s->n_tiles + 1;
+    s->hit_cap = std::max<int64_t>(1 << 16, s->n_tiles * 24);          // one kept ORF per 512 bases; more: two-pass emit
+    if (const char *e = getenv("MG_SIX_HIT_CAP")) s->hit_cap = std::max<int64_t>(1, atoll(e));   // tests force the second pass
+    TRY(six_alloc(s, &s->d_hits, s->hit_cap));
+    MG_CUDA(cudaMemsetAsync(s->d_look, 0, (6 * s->n_tiles + 2) * sizeof(unsigned long long), st));
     k_six_streams<<<(unsigned)((nc * 6 + 127) / 128), 128, 0, st>>>(g->d_packed, g->d_contig_len, g->d_contig_base, contig_lo, nc, s->d_cs, s->d_m);
     MG_LAUNCH_CHECK();
-    k_six_last<<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, contig_lo, g->d_contig_len, g->d_contig_base,
-                                                              s->d_cs, s->d_m, s->n_tiles, s->d_tile_last);
-    MG_LAUNCH_CHECK();
-    k_ms_reduce<<<dim3((unsigned)nb, 6), MS_THREADS, 0, st>>>(s->d_tile_last, s->n_tiles, nb, s->d_chunk);
-    MG_LAUNCH_CHECK();
-    k_ms_chunks<<<dim3(1, 6), MS_THREADS, 0, st>>>(s->d_chunk, nb);
-    MG_LAUNCH_CHECK();
-    k_ms_apply<<<dim3((unsigned)nb, 6), MS_THREADS, 0, st>>>(s->d_tile_last, s->n_tiles, nb, s->d_chunk, s->d_carry);
-    MG_LAUNCH_CHECK();
-    k_six_orfs<false><<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, contig_lo, g->d_contig_len,
-                                                                   g->d_contig_base, s->d_cs, s->d_m, s->n_tiles, s->d_carry, min_aa, 2 * g->total_bases,
-                                                                   s->d_cnt, nullptr, nullptr, nullptr, nullptr);
+    k_six_scan<<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, contig_lo, g->d_contig_len, g->d_contig_base,
+                                                              s->d_cs, s->d_m, s->n_tiles, s->d_look, s->d_carry, min_aa, 2 * g->total_bases,
+                                                              s->d_cnt, s->d_hits, s->hit_cap, s->d_hit_count);
     MG_LAUNCH_CHECK();
     s->scan_tmp_cap = mg_scan_tmp_elems(s->n_tiles * 6) + 2;
     TRY(six_alloc(s, &s->d_scan_tmp, s->scan_tmp_cap));
@@ -673,9 +744,15 @@ extern "C" int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig
         TRY(six_alloc(s, &s->d_len, s->n_orf));
         TRY(six_alloc(s, &s->d_src, s->n_orf));
         TRY(six_alloc(s, &s->d_aa_off, s->n_orf + 1));
-        k_six_orfs<true><<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, contig_lo, g->d_contig_len,
-                                                                      g->d_contig_base, s->d_cs, s->d_m, s->n_tiles, s->d_carry, min_aa, 2 * g->total_bases,
-                                                                      nullptr, s->d_cnt_off, s->d_recs, s->d_len, s->d_src);
+        if (s->n_orf <= s->hit_cap) {
+            k_six_place<<<(unsigned)((s->n_orf + 255) / 256), 256, 0, st>>>(s->d_hits, s->n_orf, s->d_tile_base, nc, contig_lo, g->d_contig_len,
+                                                                            g->d_contig_base, s->d_cs, s->d_m, s->d_cnt_off, 2 * g->total_bases,
+                                                                            s->d_recs, s->d_len, s->d_src);
+        } else {                                     // dense output (tiny min_aa): second pass over the genome
+            k_six_orfs<true><<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, contig_lo, g->d_contig_len,
+                                                                          g->d_contig_base, s->d_cs, s->d_m, s->n_tiles, s->d_carry, min_aa,
+                                                                          2 * g->total_bases, nullptr, s->d_cnt_off, s->d_recs, s->d_len, s->d_src);
+        }
         MG_LAUNCH_CHECK();
         const int64_t need = mg_scan_tmp_elems(s->n_orf) + 2;
         int64_t *tmp = s->d_scan_tmp;

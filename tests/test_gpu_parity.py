@@ -326,6 +326,16 @@ def test_sixframe_random_contigs(mg, min_aa):
     _sixframe_case(mg, contigs, min_aa)
 
 
+@pytest.mark.parametrize("min_aa", [0, 16])
+def test_sixframe_dense_output_second_pass(mg, min_aa, monkeypatch):
+    """More kept ORFs than the scan pass's hit list holds: the records come from the second genome pass instead."""
+    monkeypatch.setenv("MG_SIX_HIT_CAP", "7")
+    rng = np.random.default_rng(300 + min_aa)
+    alpha = np.frombuffer(b"ACGTacgtNn", dtype=np.uint8)
+    contigs = [alpha[rng.integers(0, alpha.size, size=n)].tobytes() for n in (5, 12289, 40000)]
+    _sixframe_case(mg, contigs, min_aa)
+
+
 def test_dna2orfs_entry_point(mg, tmp_path):
     """dna2orfs (genome_tools.py:145-180) as intended: ORF strings are get_orfs', positions follow its own formula."""
     from magot_b200 import genome_tools as gt
