@@ -9,6 +9,30 @@
 #include <cuda_runtime.h>
 #define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("%s: %s\n",#x,cudaGetErrorString(e)); exit(1);} }while(0)
 
+template <int F> __device__ __forceinline__ uint2 ldf(const uint2* p) {
+    uint2 v;
+    if (F == 0) v = __ldg(p);
+    else if (F == 1) asm volatile("ld.global.ca.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    else if (F == 2) asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    else if (F == 3) asm volatile("ld.global.cs.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    else if (F == 4) asm volatile("ld.global.lu.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    else if (F == 5) asm volatile("ld.global.cv.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    else if (F == 6) asm volatile("ld.global.nc.L2::64B.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    else if (F == 7) asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    else if (F == 8) asm volatile("ld.global.nc.L1::evict_first.L2::64B.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    else if (F == 9) { uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol)); }
+    else if (F == 10) asm volatile("ld.global.nc.L2::256B.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+template <int F>
+__global__ void k_gatherF(const uint2* __restrict__ src, const int64_t* __restrict__ idx, int64_t n, uint4* __restrict__ out) {
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 v = ldf<F>(src + idx[c]);
+        uint4 o = make_uint4(v.x, v.y, v.x ^ 0x55555555u, v.y ^ 0x33333333u);
+        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(out + c), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+    }
+}
 __global__ void k_gather(const uint2* __restrict__ src, const int64_t* __restrict__ idx, int64_t n, uint4* __restrict__ out) {
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
         const uint2 v = __ldg(src + idx[c]);
@@ -43,6 +67,20 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&d_idx, n * 8)); CK(cudaMemcpy(d_idx, idx.data(), n * 8, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_out, n * 16));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    if (argc > 2) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(argv[2]));
+    for (int F = 0; F <= 10; F++) {
+        float best = 1e9;
+        for (int it = 0; it < 5; it++) {
+            cudaEventRecord(e0);
+            switch (F) {
+#define C(F) case F: k_gatherF<F><<<148 * 16, 256>>>(d_src, d_idx, n, d_out); break;
+            C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10)
+            }
+            cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+            float ms; cudaEventElapsedTime(&ms, e0, e1); if (it >= 2 && ms < best) best = ms;
+        }
+        printf("flavor %d: %.1f us\n", F, best * 1e3);
+    }
     for (int mode = 0; mode < 2; mode++) {
         float best = 1e9;
         for (int it = 0; it < 8; it++) {
