@@ -465,6 +465,13 @@ class AnnotationSet(object):
         kwargs["annotation_set_to_modify"] = self
         read_gff(gff, *args, **kwargs)
 
+    def read_exonerate(self, exonerate_output):
+        read_exonerate(exonerate_output, annotation_set_to_modify=self)
+
+    def read_blast_csv(self, blast_csv, hierarchy=['match', 'match_part'], source='blast', find_truncated_locname=False):
+        read_blast_csv(blast_csv, annotation_set_to_modify=self, hierarchy=hierarchy, source=source,
+                       find_truncated_locname=find_truncated_locname)
+
     def get_fasta(self, feature, seq_type="nucleotide", longest=False, genomic=False):
         """genome.py:578-582: '\\n'.join of every <feature> annotation's fasta, in dict order
         (empty results stay in the list -> blank lines).  All records go through ONE device plan."""
@@ -647,6 +654,158 @@ def read_gff(gff, annotation_set_to_modify=None, base_features=['CDS', 'match_pa
         return annotation_set
 
 
+def _py2_reorder(annotation_set):
+    """Leave every feature dict in the order a CPython-2.7 dict would iterate after these insertions (no deepcopy on
+    the read_blast_csv / read_exonerate paths: both fill the set they are given, genome.py:88-120, :425-499)."""
+    adict = annotation_set.__dict__
+    for name in annotation_set._dict_names():
+        tbl = adict[name]
+        if tbl:
+            adict[name] = {k: tbl[k] for k in _order(list(tbl), deepcopy=False)}
+
+
+def vulgar2gff(vulgarlist, feature_types=['match', 'match_part'], source='exonerate'):
+    """genome.py:32-85 -- one exonerate `vulgar:` line (already split) -> GFF3 lines: a top-level hit and one
+    sub-feature per run of M/S/G/F triples.  Quirk kept: the sub-feature's coordinates are the min/max of the
+    positions AS STRINGS (lexicographic), as the reference computes them."""
+    qname = vulgarlist[0] + '-against-' + vulgarlist[4]
+    tname, tstart, tend, tstrand, score = vulgarlist[4], vulgarlist[5], vulgarlist[6], vulgarlist[7], vulgarlist[8]
+    triples = vulgarlist[9:]
+    if tstrand == "+":
+        tposition = int(tstart) + 1
+    else:
+        tposition = int(tstart)
+        tend = str(int(tend) + 1)
+    gfflines = ["\t".join([tname, source, feature_types[0], str(tposition), tend, score, tstrand, '.', 'ID=' + qname])]
+    open_feature = False
+    coords = []
+    IDnum = 1
+
+    def close():
+        return '\t'.join([tname, source, feature_types[1], str(min(coords)), str(max(coords)), '.', tstrand, '.',
+                          'ID=' + qname + '_' + feature_types[1] + str(IDnum) + ';Parent=' + qname])
+
+    for i, field in enumerate(triples):
+        if i % 3 == 0:
+            if field in ('M', 'S', 'G', 'F'):
+                if not open_feature:
+                    open_feature = True
+                    coords = [str(tposition)]
+            elif open_feature:
+                gfflines.append(close())
+                IDnum += 1
+                open_feature = False
+        if i % 3 == 2:
+            if tstrand == "+":
+                tposition += int(field)
+            elif tstrand == "-":
+                tposition -= int(field)
+            if open_feature:
+                if tstrand == '+':
+                    coords.append(str(tposition - 1))
+                elif tstrand == '-':
+                    coords.append(str(tposition + 1))
+    if open_feature:
+        gfflines.append(close())
+    return '\n'.join(gfflines)
+
+
+def read_exonerate(exonerate_output, annotation_set_to_modify=None):
+    """genome.py:88-120 -- exonerate text output (Query:/Target:/vulgar: lines) -> match / match_part annotations."""
+    annotation_set = AnnotationSet() if annotation_set_to_modify is None else annotation_set_to_modify
+    gfflines = []
+    seen = {}
+    qname = ""
+    tname = ""
+    for original_line in ensure_file(exonerate_output):
+        line = original_line.replace('\r', '').replace('\n', '')
+        if line[:16] == "         Query: ":
+            qname = line[16:]
+        elif line[:16] == "        Target: ":
+            tname = line[16:].replace(':[revcomp]', '').replace('[revcomp]', '')
+            if tname[-1] == " ":
+                tname = tname[:-1]
+        elif line[:8] == "vulgar: ":
+            v = line[8:].split()
+            v[0] = qname                              # names with spaces survive: the header lines win over the vulgar fields
+            v[4] = tname
+            ID = v[0] + '-against-' + v[4]
+            if ID in seen:
+                v[0] = v[0] + str(seen[ID])
+                seen[ID] += 1
+            else:
+                seen[ID] = 1
+            gfflines.append(vulgar2gff(v))
+    read_gff("\n".join(gfflines), annotation_set_to_modify=annotation_set)
+    _py2_reorder(annotation_set)
+    if annotation_set_to_modify is None:
+        return annotation_set
+
+
+def read_blast_csv(blast_csv, annotation_set_to_modify=None, hierarchy=['match', 'match_part'], source='blast',
+                   find_truncated_locname=False):
+    """genome.py:425-499 -- blast -outfmt 10 lines -> one base feature per hit plus its chain of single-child parents.
+    Hits are not strung together; repeated query IDs become ID-1, ID-2, ..."""
+    blast_file = ensure_file(blast_csv)
+    annotation_set = AnnotationSet() if annotation_set_to_modify is None else annotation_set_to_modify
+    adict = annotation_set.__dict__
+    next_suffix = {}
+    feature_type = hierarchy[-1]
+    parents_chain = list(hierarchy[:-1])
+    parents_chain.reverse()
+    if feature_type not in adict:
+        adict[feature_type] = {}
+    genome_seqids = None
+    if find_truncated_locname:
+        if annotation_set.genome is None:
+            print('"warning: find_truncated_locname" was set to true, but annotation set has no associated genome object so this '
+                  'cannot be done')
+            find_truncated_locname = False
+        else:
+            genome_seqids = annotation_set.genome.get_seqids()
+    for whole_line in blast_file:
+        fields = whole_line.replace('\r', '').replace('\n', '').split(',')
+        if len(fields) <= 8:
+            continue
+        seqid = fields[1]
+        if find_truncated_locname and seqid not in genome_seqids:
+            for genome_seqid in genome_seqids:
+                if seqid == genome_seqid.split()[0]:
+                    seqid = genome_seqid
+                    break
+        tstart, tend = int(fields[8]), int(fields[9])
+        if tstart < tend:
+            coords, strand = (tstart, tend), '+'
+        else:
+            coords, strand = (tend, tstart), '-'
+        IDbase = fields[0]
+        base_tbl = adict[feature_type]
+        if IDbase in base_tbl:
+            ID = IDbase + '-' + str(next_suffix[IDbase])
+            next_suffix[IDbase] += 1
+            while ID in base_tbl:
+                ID = IDbase + '-' + str(next_suffix[IDbase])
+                next_suffix[IDbase] += 1
+        else:
+            ID = IDbase
+            next_suffix[IDbase] = 1
+        other_attributes = {'evalue': fields[10], 'score': fields[11]}
+        parent = ID + '-' + parents_chain[0]
+        child_to_set = ID
+        for k, parent_feature in enumerate(parents_chain):
+            if parent_feature not in adict:
+                adict[parent_feature] = {}
+            parent_to_set = ID + '-' + parents_chain[k + 1] if k != len(parents_chain) - 1 else None
+            adict[parent_feature][ID + '-' + parent_feature] = ParentAnnotation(
+                ID + '-' + parent_feature, seqid, parent_feature, [child_to_set], parent_to_set, strand, annotation_set,
+                other_attributes={})
+            child_to_set = ID + '-' + parent_feature
+        base_tbl[ID] = BaseAnnotation(ID, seqid, coords, feature_type, parent, strand, other_attributes, annotation_set)
+    _py2_reorder(annotation_set)
+    if annotation_set_to_modify is None:
+        return annotation_set
+
+
 # ---------------------------------------------------------------------------------------------
 # Genome (genome.py:880-978)
 # ---------------------------------------------------------------------------------------------
@@ -669,8 +828,14 @@ class Genome(object):
             elif annotation_format == 'gff3':
                 self.annotations = read_gff(annotations)
                 self.annotations.genome = self
-            elif annotation_format in ('cegma_gff', 'blast_csv', 'exonerate_output'):
-                raise NotImplementedError("annotation_format %r is outside the B200 hot path (SURVEY 8f)" % annotation_format)
+            elif annotation_format == 'blast_csv':
+                self.annotations = read_blast_csv(annotations)
+                self.annotations.genome = self
+            elif annotation_format == 'exonerate_output':
+                self.annotations = read_exonerate(annotations)
+                self.annotations.genome = self
+            elif annotation_format == 'cegma_gff':
+                raise NotImplementedError("annotation_format 'cegma_gff' needs read_gff presets (Python-2 exec), out of scope")
         else:
             self.annotations = annotations
 
@@ -709,3 +874,18 @@ class Genome(object):
         else:
             self.annotations = read_gff(gff, *args, **kwargs)
             self.annotations.genome = self
+
+    def read_exonerate(self, exonerate_output):
+        """genome.py:950-955"""
+        if getattr(self, "annotations", None) is not None:
+            self.annotations.read_exonerate(exonerate_output)
+        else:
+            self.annotations = read_exonerate(exonerate_output)
+            self.annotations.genome = self
+
+    def read_blast_csv(self, blast_csv, hierarchy=['match', 'match_part'], source='blast', find_truncated_locname=False):
+        """genome.py:957-961"""
+        if getattr(self, "annotations", None) is None:
+            self.annotations = AnnotationSet()
+            self.annotations.genome = self
+        self.annotations.read_blast_csv(blast_csv, hierarchy=hierarchy, source=source, find_truncated_locname=find_truncated_locname)

@@ -8,6 +8,7 @@ reference) and every tool prints to stdout exactly what the reference prints.
 
 Kept (file:line in genome_tools.py): gff2fasta :324, cds2pep :664, coords2fasta :656,
 get_seq_from_fasta :483, exclude_from_fasta :377, extract_upstream_downstream :457,
+blast_csv2fasta :265, exonerate2fasta :274,
 dna2orfs :145 (the reference's version cannot run -- it calls str.translate with keyword
 arguments -- this one does what it intended, on the device).  The dispatcher (main :25-45)
 keeps the grammar but looks the function up in a table instead of eval()-ing a string.
@@ -39,6 +40,20 @@ def gff2fasta(genome_sequence, gff, from_exons="False", seq_type="nucleotide", l
     else:
         my_genome.read_gff(gff)
     print(my_genome.annotations.get_fasta('gene', seq_type=seq_type, longest=_truth(longest), genomic=_truth(genomic)))
+
+
+def blast_csv2fasta(genome_sequence, blast_csv):
+    """genome_tools.py:265-271 -- one record per blast hit (`match`), all hits through ONE device plan."""
+    my_genome = genome.Genome(genome_sequence)
+    my_genome.read_blast_csv(blast_csv)
+    print(my_genome.annotations.get_fasta('match'))
+
+
+def exonerate2fasta(genome_sequence, exonerate_file):
+    """genome_tools.py:274-280 -- one record per exonerate alignment (`match`), its match_parts spliced."""
+    my_genome = genome.Genome(genome_sequence)
+    my_genome.read_exonerate(exonerate_file)
+    print(my_genome.annotations.get_fasta('match'))
 
 
 def cds2pep(fasta_file):
@@ -181,7 +196,7 @@ def dna2orfs(fasta_location, output_file, from_atg=False, longest=False, min_orf
 
 
 FUNCTIONS = {f.__name__: f for f in (gff2fasta, cds2pep, coords2fasta, get_seq_from_fasta, exclude_from_fasta,
-                                     extract_upstream_downstream, dna2orfs)}
+                                     extract_upstream_downstream, dna2orfs, blast_csv2fasta, exonerate2fasta)}
 
 
 def help_func():

@@ -60,3 +60,42 @@ def gff2fasta(fasta, gff, from_exons="False", seq_type="nucleotide", longest="Fa
     else:
         my = load_genome(fasta, gff)
     return my.annotations.get_fasta('gene', seq_type=seq_type, longest=eval(longest), genomic=eval(genomic)) + "\n"
+
+
+def reorder_no_deepcopy(aset):
+    """CPython-2.7 iteration order of dicts that were filled in place (read_blast_csv / read_exonerate, no deepcopy)."""
+    for name, val in list(aset.__dict__.items()):
+        if type(val) == dict:
+            aset.__dict__[name] = {k: val[k] for k in py2_order(list(val))}
+    return aset
+
+
+def _aligner2fasta(fasta, reader, path):
+    g = ref()
+    my = g.Genome(fasta)
+    reorder_genome_sequence(my.genome_sequence)
+    getattr(my, reader)(path)
+    reorder_no_deepcopy(my.annotations)
+    out = [my.annotations.match[m].get_fasta() for m in my.annotations.match]
+    return my, "\n".join(out) + "\n"
+
+
+def blast_csv2fasta(fasta, blast_csv):
+    """stdout of genome_tools.py:265-271."""
+    return _aligner2fasta(fasta, "read_blast_csv", blast_csv)[1]
+
+
+def exonerate2fasta(fasta, exonerate_file):
+    """stdout of genome_tools.py:274-280."""
+    return _aligner2fasta(fasta, "read_exonerate", exonerate_file)[1]
+
+
+def aligner_model(fasta, reader, path):
+    """Object model the reference builds (IDs in py2 order, coords, strand, parent, children) as plain data."""
+    my = _aligner2fasta(fasta, reader, path)[0]
+    model = {}
+    for name, val in my.annotations.__dict__.items():
+        if type(val) == dict and val:
+            model[name] = [[k, v.seqid, list(v.get_coords()) if hasattr(v, "coords") else None, v.strand, v.parent,
+                            list(getattr(v, "child_list", []))] for k, v in val.items()]
+    return model

@@ -89,6 +89,91 @@ def whole_file_cases(tmp):
     return cases
 
 
+def aligner_inputs():
+    """Synthetic blast -outfmt 10 and exonerate outputs against the O.biroi contigs (committed: aligner_inputs/)."""
+    rnd = random.Random(424242)
+    contigs = []
+    name = None
+    with open(os.path.join(REF_DATA, DATA_FILES[0])) as fh:
+        for line in fh:
+            if line.startswith(">"):
+                name = line[1:].strip()
+                contigs.append([name, 0])
+            else:
+                contigs[-1][1] += len(line.strip())
+    out = os.path.join(HERE, "aligner_inputs")
+    os.makedirs(out, exist_ok=True)
+    # blast: qseqid,sseqid,pident,length,mismatch,gapopen,qstart,qend,sstart,send,evalue,bitscore
+    rows = []
+    for i in range(70):
+        full, L = rnd.choice(contigs)
+        q = "query%02d" % rnd.randrange(25)              # repeated query ids -> ID-1, ID-2 ...
+        n = rnd.randrange(30, min(1500, L // 2))
+        a = rnd.randrange(1, L - n)
+        s0, s1 = (a, a + n) if rnd.random() < 0.5 else (a + n, a)
+        rows.append(",".join([q, full.split()[0], "%.2f" % rnd.uniform(70, 100), str(n), "3", "1", "1", str(n), str(s0), str(s1),
+                              "1e-%d" % rnd.randrange(5, 90), "%.1f" % rnd.uniform(50, 900)]))
+    rows.insert(10, "short,line,only")                   # fewer than 9 fields: skipped
+    rows.append(",".join(["edge", contigs[0][0].split()[0], "99.0", "50", "0", "0", "1", "50", str(contigs[0][1] - 20),
+                          str(contigs[0][1] + 30), "0.0", "99"]))          # runs off the contig end: slice clamps
+    with open(os.path.join(out, "obiroi_blast.csv"), "w") as fh:
+        fh.write("\n".join(rows) + "\n")
+    # exonerate: Query / Target header lines + vulgar line (label, query length, target length triples)
+    blocks = []
+    big = [c for c in contigs if c[1] > 80000]
+    for i in range(40):
+        full, L = rnd.choice(big)
+        q = "prot%02d some description" % rnd.randrange(28)   # repeats against the same target -> numbered
+        plus = rnd.random() < 0.5
+        pos = rnd.randrange(5000, L - 60000)
+        triples = []
+        span = 0
+        nex = rnd.randrange(1, 7)
+        for e in range(nex):
+            m = 3 * rnd.randrange(10, 150)
+            triples += ["M", str(m // 3), str(m)]
+            span += m
+            if rnd.random() < 0.3:
+                triples += ["G", "0", "3", "M", "20", "60"]
+                span += 63
+            if rnd.random() < 0.15:
+                triples += ["F", "0", "1", "M", "5", "15"]
+                span += 16
+            if e != nex - 1:
+                if rnd.random() < 0.5:
+                    triples += ["S", "0", "2"]
+                    span += 2
+                intron = rnd.randrange(60, 4000)
+                triples += ["5", "0", "2", "I", "0", str(intron), "3", "0", "2"]
+                span += intron + 4
+                if rnd.random() < 0.5:
+                    triples += ["S", "1", "1"]
+                    span += 1
+        ts, te = (pos, pos + span) if plus else (pos + span, pos)
+        target = full + (":[revcomp]" if not plus and rnd.random() < 0.5 else ("[revcomp]" if not plus else ""))
+        blocks.append("C4 Alignment:\n------------\n         Query: %s\n        Target: %s\n         Model: protein2genome:local\n"
+                      "     Raw score: %d\n\nvulgar: %s 0 %d . %s %d %d %s %d %s\n" %
+                      (q, target, rnd.randrange(100, 2000), q.split()[0], span // 3, full.split()[0], ts, te, "+" if plus else "-",
+                       rnd.randrange(100, 2000), " ".join(triples)))
+    with open(os.path.join(out, "obiroi_exonerate.txt"), "w") as fh:
+        fh.write("Command line: [exonerate --model protein2genome q.fa t.fa --showvulgar yes]\n\n" + "\n".join(blocks) +
+                 "-- completed exonerate analysis\n")
+    return os.path.join(out, "obiroi_blast.csv"), os.path.join(out, "obiroi_exonerate.txt")
+
+
+def aligner_cases(cases):
+    blast, exo = aligner_inputs()
+    ob_fa = os.path.join(REF_DATA, DATA_FILES[0])
+    for name, text in (("obiroi:blast_csv2fasta", ref_runner.blast_csv2fasta(ob_fa, blast)),
+                       ("obiroi:exonerate2fasta", ref_runner.exonerate2fasta(ob_fa, exo))):
+        c, n = cksum(text)
+        cases[name] = {"cksum": c, "bytes": n}
+    model = {"blast": ref_runner.aligner_model(ob_fa, "read_blast_csv", blast),
+             "exonerate": ref_runner.aligner_model(ob_fa, "read_exonerate", exo)}
+    with open(os.path.join(HERE, "aligner_model.json"), "w") as fh:
+        json.dump(model, fh, indent=0)
+
+
 ALPHABETS = {
     "acgt": "ACGT",
     "mixed": "ACGTacgtNn",
@@ -147,6 +232,7 @@ def main():
     copy_data()
     with tempfile.TemporaryDirectory() as tmp:
         cases = whole_file_cases(tmp)
+    aligner_cases(cases)
     with open(os.path.join(HERE, "manifest.json"), "w") as fh:
         json.dump(cases, fh, indent=1, sort_keys=True)
     with open(os.path.join(HERE, "kat.json"), "w") as fh:

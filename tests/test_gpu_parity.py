@@ -102,6 +102,18 @@ def test_c14_genomic_longest_transcript(mg, ref_data, manifest):
     assert _ck(g.annotations.get_fasta('transcript') + "\n") == manifest["c14:StandardGTF.gtf:get_fasta_transcript"]
 
 
+def test_aligner_output_entry_points(mg, ref_data, manifest):
+    """blast_csv2fasta / exonerate2fasta (genome_tools.py:265-280) on synthetic aligner outputs against the O.biroi contigs:
+    whole stdout against the reference's (cksums from the shimmed reference, tests/golden/make_golden.py)."""
+    from magot_b200 import genome_tools as gt
+    fa = os.path.join(ref_data, "O.biroi_refseqGenomeSubset.fasta")
+    inputs = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aligner_inputs")
+    assert _ck(_stdout_of(gt.blast_csv2fasta, fa, os.path.join(inputs, "obiroi_blast.csv"))) == manifest["obiroi:blast_csv2fasta"]
+    assert _ck(_stdout_of(gt.exonerate2fasta, fa, os.path.join(inputs, "obiroi_exonerate.txt"))) == manifest["obiroi:exonerate2fasta"]
+    g = mg.Genome(fa, os.path.join(inputs, "obiroi_blast.csv"), annotation_format='blast_csv')
+    assert _ck(g.annotations.get_fasta('match') + "\n") == manifest["obiroi:blast_csv2fasta"]
+
+
 def test_obiroi_whole_api(mg, ref_data, manifest):
     from magot_b200 import genome_tools as gt
     fa = os.path.join(ref_data, "O.biroi_refseqGenomeSubset.fasta")

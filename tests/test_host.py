@@ -212,3 +212,27 @@ def test_multi_rank_sharding_gloo(tmp_path):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert out.read_text() == "OK"
+
+
+@pytest.mark.parametrize("kind", ["blast", "exonerate"])
+def test_aligner_readers_build_the_reference_object_model(kind):
+    """read_blast_csv (genome.py:425-499) / read_exonerate + vulgar2gff (genome.py:32-120): IDs in py2 order, coords (incl. the
+    lexicographic min/max of vulgar2gff), strands, parents and child lists equal what the reference itself built
+    (tests/golden/aligner_model.json, generated by tests/golden/make_golden.py from the shimmed reference)."""
+    import json
+    gold = os.path.join(ROOT, "tests", "golden")
+    with open(os.path.join(gold, "aligner_model.json")) as fh:
+        want = json.load(fh)[kind]
+    if kind == "blast":
+        aset = genome.read_blast_csv(os.path.join(gold, "aligner_inputs", "obiroi_blast.csv"))
+    else:
+        aset = genome.read_exonerate(os.path.join(gold, "aligner_inputs", "obiroi_exonerate.txt"))
+    got = {}
+    for name in aset._dict_names():
+        tbl = aset.__dict__[name]
+        if tbl:
+            got[name] = [[k, v.seqid, list(v.coords) if hasattr(v, "coords") else None, v.strand, v.parent,
+                          list(getattr(v, "child_list", []))] for k, v in tbl.items()]
+    assert sorted(got) == sorted(want)
+    for name in want:
+        assert got[name] == want[name], name
