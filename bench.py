@@ -434,12 +434,17 @@ def gpu_arm(args):
     six = None
     if not args.no_sixframe:
         try:
+            # contigs are independent: each rank scans a contiguous, length-balanced range of contigs (strong scaling,
+            # no exchange step); time = max over ranks, ORFs and residues summed
+            cb = engine.shard_bounds(np.array([l for _, l in layout], dtype=np.int64), world)
+            c_lo, c_hi = int(cb[rank]), int(cb[rank + 1])
+            my_bp = sum(l for _, l in layout[c_lo:c_hi])
             n_orf, n_bytes = ctypes.c_int64(0), ctypes.c_int64(0)
-            _lib.check(lib.mg_sixframe_count(g.handle, 0, len(layout), 100, ctypes.byref(n_orf), ctypes.byref(n_bytes), sp))   # warm-up
+            _lib.check(lib.mg_sixframe_count(g.handle, c_lo, c_hi, 100, ctypes.byref(n_orf), ctypes.byref(n_bytes), sp))   # warm-up
             torch.cuda.synchronize()
             a0, a1, a2 = ev(), ev(), ev()
             a0.record(stream)
-            _lib.check(lib.mg_sixframe_count(g.handle, 0, len(layout), 100, ctypes.byref(n_orf), ctypes.byref(n_bytes), sp))
+            _lib.check(lib.mg_sixframe_count(g.handle, c_lo, c_hi, 100, ctypes.byref(n_orf), ctypes.byref(n_bytes), sp))
             a1.record(stream)
             aa_dev = torch.empty((n_bytes.value + 31) // 32 * 32 + 32, dtype=torch.uint8, device=dev)
             a1b = ev()
@@ -448,13 +453,27 @@ def gpu_arm(args):
             a2.record(stream)
             torch.cuda.synchronize()
             t_scan, t_emit = a0.elapsed_time(a1), a1b.elapsed_time(a2)
+            tot_orf, tot_bytes, max_bp = n_orf.value, n_bytes.value, my_bp
+            if dist is not None:
+                tt = torch.tensor([t_scan, t_emit, float(my_bp)], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t_scan, t_emit, max_bp = [float(x) for x in tt.tolist()]
+                ts = torch.tensor([n_orf.value, n_bytes.value], dtype=torch.float64, device=dev)
+                dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+                tot_orf, tot_bytes = [int(x) for x in ts.tolist()]
             six = {"workload": "config 5: six-frame translation + ORF scan of the whole genome, min ORF 100 aa (reference semantics of Sequence.get_orfs)",
-                   "orfs": n_orf.value, "aa_bytes": n_bytes.value, "scan_ms": round(t_scan, 3), "emit_ms": round(t_emit, 3),
+                   "sharding": "contigs split into %d contiguous length-balanced ranges, one per GPU; largest shard %.3f Gbp; strong scaling, "
+                               "times are the max over ranks" % (world, max_bp / 1e9),
+                   "orfs": tot_orf, "aa_bytes": tot_bytes, "scan_ms": round(t_scan, 3), "emit_ms": round(t_emit, 3),
                    "genome_Gbp_per_s": round(GENOME_BP / ((t_scan + t_emit) * 1e-3) / 1e9, 1),
-                   "algorithmic_GBps": round((GENOME_BP * 0.5 + n_bytes.value + 32 * n_orf.value) / ((t_scan + t_emit) * 1e-3) / 1e9, 1)}
+                   "six_frame_Gbp_per_s": round(6 * GENOME_BP / ((t_scan + t_emit) * 1e-3) / 1e9, 1),
+                   "algorithmic_GBps": round((GENOME_BP * 0.5 + tot_bytes + 32 * tot_orf) / ((t_scan + t_emit) * 1e-3) / 1e9, 1),
+                   "bound": "instruction issue (~47 thread-instructions per base), not HBM: see DESIGN.md section 4"}
             del aa_dev
         except Exception as e:
             six = {"error": str(e)[:300]}
+            if dist is not None:
+                raise
 
     # max over ranks
     if dist is not None:

@@ -7,6 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# MAGOT_B200_LIB: developer knob for A/B runs of differently compiled builds of the same sources (scratch/variants.sh)
 LIB_PATH = os.environ.get("MAGOT_B200_LIB") or os.path.join(_HERE, "libmagot_b200.so")
 
 MG_PROT_TRIMX = 1

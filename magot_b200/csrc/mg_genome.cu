@@ -72,7 +72,6 @@ extern "C" int mg_genome_create(int device, int64_t n_contigs, const int64_t *co
         return MG_ECUDA;
     }
     MG_CUDA(cudaSetDevice(device));
-    if (const char *e = getenv("MG_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
     mg_genome *g = new mg_genome();
     g->device = device;
     g->n_contigs = n_contigs;
