@@ -59,12 +59,14 @@ __global__ void __launch_bounds__(256) k_plan_pieces(int64_t n_piece, int64_t n_
         s_F[i] = r <= n_rec ? __ldg(rec_seg_off + r) + 2 * r : INT64_MAX;
     }
     __syncthreads();
-    int64_t loc[PLAN_ITEMS];                           // exclusive offset of the piece inside the block
-    int64_t run = 0;
+    // blocked arrangement: a thread owns PLAN_ITEMS consecutive pieces, so the block needs ONE scan and nothing between
+    // the pieces' (dependent) table loads makes them wait for each other
+    int64_t len[PLAN_ITEMS];
+    const int64_t p0 = pb + (int64_t)threadIdx.x * PLAN_ITEMS;
 #pragma unroll
     for (int it = 0; it < PLAN_ITEMS; it++) {
-        const int64_t p = pb + it * 256 + threadIdx.x;
-        int64_t len = 0;
+        const int64_t p = p0 + it;
+        len[it] = 0;
         if (p < n_piece) {
             int lo = 0, hi = PLAN_TILE / 2 + 1;        // F(r0) <= p < F(r0 + PLAN_TILE/2 + 1): F grows by >= 2 per record
             while (hi - lo > 1) {
@@ -75,42 +77,45 @@ __global__ void __launch_bounds__(256) k_plan_pieces(int64_t n_piece, int64_t n_
             const int64_t s0 = s_F[lo] - 2 * r, s1 = s_F[lo + 1] - 2 * (r + 1);
             const int64_t local = p - (s0 + 2 * r);
             if (local == 0) {                           // literal prefix
-                len = rec_pre[r];
+                len[it] = rec_pre[r];
                 piece_src[p] = rec_lit_off[r] | (int64_t)(MG_KIND_LIT << MG_KIND_SHIFT);
             } else if (local == s1 - s0 + 1) {          // literal suffix
-                len = rec_suf[r];
+                len[it] = rec_suf[r];
                 piece_src[p] = (rec_lit_off[r] + rec_pre[r]) | (int64_t)(MG_KIND_LIT << MG_KIND_SHIFT);
             } else {                                    // genome segment
                 const int64_t e = s0 + local - 1;
                 const int32_t c = seg_contig[e];
-                int64_t src = MG_FRONT_PAD;
+                int64_t src = MG_FRONT_PAD, n = 0;
                 if (c >= 0 && c < n_contigs) {
                     const int64_t L = contig_len[c];
                     // contig[start-1:end] with Python slice semantics (genome.py:606)
                     int64_t i = seg_start[e] - 1, j = seg_end[e];
                     if (i < 0) { i += L; if (i < 0) i = 0; } else if (i > L) i = L;
                     if (j < 0) { j += L; if (j < 0) j = 0; } else if (j > L) j = L;
-                    len = j > i ? j - i : 0;
-                    if (len > 0x7fffffff) len = 0x7fffffff;
+                    n = j > i ? j - i : 0;
+                    if (n > 0x7fffffff) n = 0x7fffffff;
                     src = contig_base[c] + i;
                 }
+                len[it] = n;
                 // '-' strand: forward bases [src, src+len) are bases [2T-src-len, 2T-src) of the reverse-complement plane,
                 // in exactly the order Sequence.reverse_compliment emits them (genome.py:784-793)
-                piece_src[p] = seg_strand[e] ? two_T - src - len : src;
+                piece_src[p] = seg_strand[e] ? two_T - src - n : src;
             }
         }
-        int64_t total;
-        const int64_t incl = mg_block_incl_scan(len, s_warp, &total);
-        loc[it] = run + incl - len;
-        run += total;
     }
-    const int64_t prefix = mg_lookback(tmp, tile, run, &s_prefix);
+    int64_t mine = 0;
+#pragma unroll
+    for (int it = 0; it < PLAN_ITEMS; it++) mine += len[it];
+    int64_t total;
+    const int64_t incl = mg_block_incl_scan(mine, s_warp, &total);
+    const int64_t prefix = mg_lookback(tmp, tile, total, &s_prefix);
+    int64_t run = prefix + incl - mine;
 #pragma unroll
     for (int it = 0; it < PLAN_ITEMS; it++) {
-        const int64_t p = pb + it * 256 + threadIdx.x;
-        if (p < n_piece) piece_off[p] = prefix + loc[it];
+        if (p0 + it < n_piece) piece_off[p0 + it] = run;
+        run += len[it];
     }
-    if (tile == gridDim.x - 1 && threadIdx.x == 0) { piece_off[n_piece] = prefix + run; *total_out = prefix + run; }
+    if (tile == gridDim.x - 1 && threadIdx.x == 0) { piece_off[n_piece] = prefix + total; *total_out = prefix + total; }
 }
 
 // thread per record: spliced length -> amino-acid count (Sequence.translate, genome.py:810-821) and, with the same
