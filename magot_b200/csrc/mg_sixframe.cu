@@ -18,11 +18,13 @@
 #include <algorithm>
 #include "mg_common.cuh"
 
-#define SIX_THREADS 256
+#ifndef SIX_THREADS
+#define SIX_THREADS 512                              // 24576 bases per CTA: the per-tile prologue (ticket, tile info, look-back) is paid half as often (-12 %)
+#endif
 #define SIX_BPT 48                                   // bases per thread
-#define SIX_TILE (SIX_THREADS * SIX_BPT)             // 12288 bases per CTA (multiple of 3 and of 16)
+#define SIX_TILE (SIX_THREADS * SIX_BPT)             // bases per CTA (multiple of 3 and of 16)
 #ifndef SIX_SCAN_MINB
-#define SIX_SCAN_MINB 4
+#define SIX_SCAN_MINB 3                             // 42 registers, 48 resident warps per SM
 #endif
 #define AA_TILE 8192
 #define AA_THREADS 256
@@ -39,6 +41,7 @@ struct mg_sixframe_state {
     int64_t n_tiles = 0;
     std::vector<int64_t> h_tile_base;                // [n_contig_in_range + 1], starts at 0
     int64_t *d_tile_base = nullptr;
+    int32_t *d_tile_contig = nullptr;                // [n_tiles] contig (index in the range) of each tile
     int32_t *d_cs = nullptr;                         // [nc*6] first-codon offset of each stream
     int64_t *d_m = nullptr;                          // [nc*6] residues in each stream's translation
     int64_t *d_carry = nullptr;                      // [6][n_tiles] last stop before the tile
@@ -181,6 +184,24 @@ struct TileInfo {
     int64_t m[6];
 };
 
+// thread per tile: index (within the scanned range) of the contig that owns the tile
+__global__ void __launch_bounds__(256) k_six_tile_contig(const int64_t *__restrict__ tile_base, int64_t nc, int64_t n_tiles,
+                                                         int32_t *__restrict__ tile_contig) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    int64_t lo = 0, hi = nc;                          // largest ci with tile_base[ci] <= t (contigs without tiles: the last one)
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (tile_base[mid] <= t) lo = mid; else hi = mid;
+    }
+    tile_contig[t] = (int32_t)lo;
+}
+
+// tile_info with the contig index already known (k_six_tile_contig): independent loads, no search
+__device__ __forceinline__ void tile_info_at(int64_t tile, int64_t lo, const int64_t *__restrict__ tile_base, int64_t contig_lo,
+                                             const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base,
+                                             const int32_t *__restrict__ cs, const int64_t *__restrict__ m, struct TileInfo &ti);
+
 __device__ __forceinline__ void tile_info(int64_t tile, const int64_t *__restrict__ tile_base, int64_t nc, int64_t contig_lo,
                                           const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base,
                                           const int32_t *__restrict__ cs, const int64_t *__restrict__ m, TileInfo &ti) {
@@ -190,6 +211,22 @@ __device__ __forceinline__ void tile_info(int64_t tile, const int64_t *__restric
         if (tile_base[mid] <= tile) lo = mid; else hi = mid;
     }
     // contigs without tiles (L == 0) share a tile_base value with their successor: take the last one
+    ti.c = contig_lo + lo;
+    ti.k = tile - tile_base[lo];
+    ti.Tc = tile_base[lo + 1] - tile_base[lo];
+    ti.gb = contig_base[ti.c];
+    ti.L = contig_len[ti.c];
+    ti.Lm3 = (int)(ti.L % 3);
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        ti.cs[s] = cs[lo * 6 + s];
+        ti.m[s] = m[lo * 6 + s];
+    }
+}
+
+__device__ __forceinline__ void tile_info_at(int64_t tile, int64_t lo, const int64_t *__restrict__ tile_base, int64_t contig_lo,
+                                             const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base,
+                                             const int32_t *__restrict__ cs, const int64_t *__restrict__ m, TileInfo &ti) {
     ti.c = contig_lo + lo;
     ti.k = tile - tile_base[lo];
     ti.Tc = tile_base[lo + 1] - tile_base[lo];
@@ -436,18 +473,18 @@ __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
 __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
     const uint32_t *__restrict__ packed, const int64_t *__restrict__ tile_base, int64_t nc, int64_t contig_lo,
     const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
-    const int64_t *__restrict__ m, int64_t n_tiles, unsigned long long *look, int64_t *__restrict__ carry_out, int64_t min_aa,
+    const int64_t *__restrict__ m, const int32_t *__restrict__ tile_contig, int64_t n_tiles, unsigned long long *look, int64_t *__restrict__ carry_out, int64_t min_aa,
     int64_t two_T, int32_t *__restrict__ cnt, SixHit *__restrict__ hits, int64_t hit_cap, unsigned long long *hit_count) {
     __shared__ TileInfo ti;
     __shared__ int64_t s_warp[SIX_THREADS / 32];
     __shared__ int s_wlast[6][SIX_THREADS / 32];     // per-warp max of `last stop in thread`
-    __shared__ int64_t s_carry[6];
+    __shared__ int64_t s_wprev[6][SIX_THREADS / 32]; // last stop of the stream before each warp (contig offset, -1 = none)
     __shared__ int64_t s_tile;
     __shared__ long long s_base;
     if (threadIdx.x == 0) {
         const int64_t t = (int64_t)atomicAdd(look, 1ull);              // tiles in launch order: look-back never waits on a
         s_tile = t;                                                      // tile that has not started
-        tile_info(t, tile_base, nc, contig_lo, contig_len, contig_base, cs, m, ti);
+        tile_info_at(t, tile_contig[t], tile_base, contig_lo, contig_len, contig_base, cs, m, ti);
     }
     __syncthreads();
     const int64_t tile = s_tile;
@@ -481,16 +518,23 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
     if (wid < 6) {                                    // warp s: publish the tile's last stop of stream s, look back for the carry
         const int s = wid;
         volatile unsigned long long *st = look + 1 + (int64_t)s * n_tiles;
-        int agg = -1;
+        // exclusive running max over the CTA's warps (lanes 0..7 hold one warp each)
+        int inc = lane < SIX_THREADS / 32 ? s_wlast[s][lane] : -1;
 #pragma unroll
-        for (int w = 0; w < SIX_THREADS / 32; w++) agg = max(agg, s_wlast[s][w]);
+        for (int d = 1; d < SIX_THREADS / 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d && t > inc) inc = t;
+        }
+        const int agg = __shfl_sync(0xffffffffu, inc, SIX_THREADS / 32 - 1);
+        int exw = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) exw = -1;
         const unsigned long long own = agg >= 0 ? (unsigned long long)(ti.gb + tile0 + agg + 1) : 0ull;
         if (lane == 0) st[tile] = (agg >= 0 || tile == 0) ? (SIX_LOOK_PREFIX | own) : SIX_LOOK_SUM;
         unsigned long long best = 0;                  // 1 + last stop before this tile, 0 = none
         int64_t j = tile - 1 - lane;
         while (true) {
             unsigned long long w = SIX_LOOK_PREFIX;   // before tile 0: nothing
-            if (j >= 0) { do { w = st[j]; } while ((w & SIX_LOOK_MASK) == SIX_LOOK_NONE); }
+            if (j >= 0) { while (((w = st[j]) & SIX_LOOK_MASK) == SIX_LOOK_NONE) __nanosleep(64); }
             const unsigned int done = __ballot_sync(0xffffffffu, (w & SIX_LOOK_MASK) == SIX_LOOK_PREFIX);
             if (done) {                               // nearest tile with a known prefix; tiles nearer than it hold no stop
                 best = __shfl_sync(0xffffffffu, w & ~SIX_LOOK_MASK, __ffs(done) - 1);
@@ -498,24 +542,17 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
             }
             j -= 32;
         }
+        const int64_t cg = (int64_t)best - 1;         // global base index; < gb: a stop of another contig
+        if (lane < SIX_THREADS / 32) s_wprev[s][lane] = exw >= 0 ? tile0 + exw : (cg >= ti.gb ? cg - ti.gb : -1);
         if (lane == 0) {
-            s_carry[s] = (int64_t)best - 1;
-            carry_out[(int64_t)s * n_tiles + tile] = (int64_t)best - 1;
+            carry_out[(int64_t)s * n_tiles + tile] = cg;
             if (agg < 0 && tile > 0) st[tile] = SIX_LOOK_PREFIX | best;
         }
     }
     __syncthreads();
-    int64_t prev[6];
+    int64_t prev[6];                                  // contig offset of the last stop of the stream before this thread, or -1
 #pragma unroll
-    for (int s = 0; s < 6; s++) {
-        int ex = ex_local[s];
-        for (int w = 0; w < wid; w++) ex = max(ex, s_wlast[s][w]);
-        if (ex >= 0) prev[s] = tile0 + ex;            // contig offset
-        else {
-            const int64_t cg = s_carry[s];            // global base index; < gb: other contig
-            prev[s] = (cg >= ti.gb) ? cg - ti.gb : -1;
-        }
-    }
+    for (int s = 0; s < 6; s++) prev[s] = ex_local[s] >= 0 ? tile0 + ex_local[s] : s_wprev[s][wid];
     int my_cnt[6];
     int mine = 0;
 #pragma unroll
@@ -523,22 +560,67 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
         my_cnt[s] = active ? enumerate_stream<0>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, fl[s]) : 0;
         mine += my_cnt[s];
     }
+    int tot[6], before[6], excl[6];                   // kept ORFs of the tile per stream; of the streams before s; of lower threads
+    int run = 0;
+    if (min_aa >= 16) {
+        // a thread keeps at most two ORFs per stream (its first stop, the contig end): ranks from two ballots per stream and
+        // the per-warp totals, one barrier; only the rare threads that hold an ORF read the totals back
+        __shared__ int s_wcnt[6][SIX_THREADS / 32];
+        const unsigned int lt = (1u << lane) - 1u;
+        int ex_w[6];
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            const unsigned int b1 = __ballot_sync(0xffffffffu, my_cnt[s] >= 1), b2 = __ballot_sync(0xffffffffu, my_cnt[s] >= 2);
+            ex_w[s] = __popc(b1 & lt) + __popc(b2 & lt);
+            if (lane == 0) s_wcnt[s][wid] = __popc(b1) + __popc(b2);
+        }
+        __syncthreads();
+        if (mine == 0 && threadIdx.x >= 6) return;
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            int t = 0, e = 0;
+#pragma unroll
+            for (int w = 0; w < SIX_THREADS / 32; w++) {
+                const int c = s_wcnt[s][w];
+                t += c;
+                if (w < wid) e += c;
+            }
+            tot[s] = t;
+            excl[s] = e + ex_w[s];
+            before[s] = run;
+            run += t;
+        }
+        if (threadIdx.x < 6) cnt[layout_index(ti, tile_base, contig_lo, threadIdx.x)] = tot[threadIdx.x];
+        if (run == 0 || mine == 0) return;
+        // the tile's slice of the hit list: claimed once, by the lowest thread that holds an ORF, and found by the others
+        // through shared memory is not possible after the early return above, so every holder claims for its own ORFs
+        const long long base = (long long)atomicAdd(hit_count, (unsigned long long)mine);
+        if (base + mine > hit_cap) return;            // overflow: the host falls back to the two-pass emit
+        int off = 0;
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            if (my_cnt[s] == 0) continue;
+            enumerate_stream<2>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, base + off, excl[s], nullptr, nullptr, nullptr,
+                                hits, (int32_t)tile, fl[s]);
+            off += my_cnt[s];
+        }
+        return;
+    }
     const int any = __syncthreads_or(mine);
     if (!any) {
         if (threadIdx.x < 6) cnt[layout_index(ti, tile_base, contig_lo, threadIdx.x)] = 0;
         return;
     }
-    // ranks inside the tile: block prefix sums of the per-thread counts, three 21-bit fields per word
+    // general case: block prefix sums of the per-thread counts, three 21-bit fields per word
     const int64_t pk0 = (int64_t)my_cnt[0] | ((int64_t)my_cnt[1] << 21) | ((int64_t)my_cnt[2] << 42);
     const int64_t pk1 = (int64_t)my_cnt[3] | ((int64_t)my_cnt[4] << 21) | ((int64_t)my_cnt[5] << 42);
     int64_t tot0, tot1;
     const int64_t in0 = block_incl_sum(pk0, s_warp, &tot0);
     const int64_t in1 = block_incl_sum(pk1, s_warp, &tot1);
-    int tot[6], before[6];                            // kept ORFs of the tile per stream; of the streams before s
-    int run = 0;
 #pragma unroll
     for (int s = 0; s < 6; s++) {
         tot[s] = (int)(((s < 3 ? tot0 : tot1) >> (21 * (s % 3))) & 0x1FFFFF);
+        excl[s] = (int)(((s < 3 ? in0 : in1) >> (21 * (s % 3))) & 0x1FFFFF) - my_cnt[s];
         before[s] = run;
         run += tot[s];
     }
@@ -550,8 +632,7 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
 #pragma unroll
     for (int s = 0; s < 6; s++) {
         if (my_cnt[s] == 0) continue;
-        const int excl = (int)(((s < 3 ? in0 : in1) >> (21 * (s % 3))) & 0x1FFFFF) - my_cnt[s];
-        enumerate_stream<2>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, base + before[s] + excl, excl, nullptr, nullptr, nullptr,
+        enumerate_stream<2>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, base + before[s] + excl[s], excl[s], nullptr, nullptr, nullptr,
                             hits, (int32_t)tile, fl[s]);
     }
 }
@@ -724,14 +805,17 @@ extern "C" int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig
     TRY(six_alloc(s, &s->d_cnt_off, s->n_tiles * 6 + 1));
     TRY(six_alloc(s, &s->d_look, 6 * s->n_tiles + 2));
     s->d_hit_count = s->d_look + 6 * s->n_tiles + 1;
-    s->hit_cap = std::max<int64_t>(1 << 16, s->n_tiles * 24);          // one kept ORF per 512 bases; more: two-pass emit
+    s->hit_cap = std::max<int64_t>(1 << 16, s->n_tiles * (SIX_TILE / 512));   // one kept ORF per 512 bases; more: two-pass emit
     if (const char *e = getenv("MG_SIX_HIT_CAP")) s->hit_cap = std::max<int64_t>(1, atoll(e));   // tests force the second pass
     TRY(six_alloc(s, &s->d_hits, s->hit_cap));
     MG_CUDA(cudaMemsetAsync(s->d_look, 0, (6 * s->n_tiles + 2) * sizeof(unsigned long long), st));
     k_six_streams<<<(unsigned)((nc * 6 + 127) / 128), 128, 0, st>>>(g->d_packed, g->d_contig_len, g->d_contig_base, contig_lo, nc, s->d_cs, s->d_m);
     MG_LAUNCH_CHECK();
+    TRY(six_alloc(s, &s->d_tile_contig, s->n_tiles));
+    k_six_tile_contig<<<(unsigned)((s->n_tiles + 255) / 256), 256, 0, st>>>(s->d_tile_base, nc, s->n_tiles, s->d_tile_contig);
+    MG_LAUNCH_CHECK();
     k_six_scan<<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, contig_lo, g->d_contig_len, g->d_contig_base,
-                                                              s->d_cs, s->d_m, s->n_tiles, s->d_look, s->d_carry, min_aa, 2 * g->total_bases,
+                                                              s->d_cs, s->d_m, s->d_tile_contig, s->n_tiles, s->d_look, s->d_carry, min_aa, 2 * g->total_bases,
                                                               s->d_cnt, s->d_hits, s->hit_cap, s->d_hit_count);
     MG_LAUNCH_CHECK();
     s->scan_tmp_cap = mg_scan_tmp_elems(s->n_tiles * 6) + 2;
