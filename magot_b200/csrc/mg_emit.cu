@@ -356,29 +356,6 @@ __device__ __noinline__ void prot_chunk_generic(const uint32_t *__restrict__ pac
     mg_st16(out + P, w[0], w[1], w[2], w[3]);
 }
 
-// rare path of K3: the 48 nibbles of a chunk's codons spread over three or more segment pieces
-__device__ __noinline__ void prot_gather_many(const uint32_t *__restrict__ packed, const int64_t *s_base, const int32_t *s_rel,
-                                              int j, int q, int need_lo, int need_hi, uint32_t n[6]) {
-#pragma unroll
-    for (int k = 0; k < 6; k++) n[k] = 0;
-    for (; s_rel[j] < need_hi; j++) {
-        const int lo = max(s_rel[j], need_lo) - q, hi = min(s_rel[j + 1], need_hi) - q;     // nibble range of this piece
-        if (hi <= lo) continue;
-        const int64_t g = s_base[j] + q;
-        const uint32_t *pp = packed + (g >> 3);
-        const uint32_t sh = ((uint32_t)g & 7u) << 2;
-        uint32_t w[7];
-#pragma unroll
-        for (int k = 0; k < 7; k++) w[k] = ld_pk(pp + k);
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            const int a = min(max(lo - 8 * k, 0), 8), b = min(max(hi - 8 * k, 0), 8);
-            const uint32_t m = b > a ? ((0xFFFFFFFFu >> (32 - 4 * (b - a))) << (4 * a)) : 0u;
-            n[k] |= __funnelshift_r(w[k], w[k + 1], sh) & m;
-        }
-    }
-}
-
 // Output chunk = 16 bytes of protein text.  Amino acid a of record r is the codon at spliced offset
 // skip[r] + 3a; the 4096-entry nibble-triplet table (case-insensitive, anything non-ACGT -> 'X') sits in
 // shared memory.  Stop codons are emitted as '*' and translation continues (genome.py:811-818).
@@ -486,28 +463,27 @@ __global__ void __launch_bounds__(PROT_THREADS, PROT_MINB) k_emit_prot(
                 }
                 X = a;
             }
-            const int eX = s_rel[X + 1];              // X covers nibbles [.., eX)
-            const bool hasY = eX < need_hi;
-            const int Y = X + 1;                      // next segment piece of the same record (may be empty)
-            const bool many = hasY && s_rel[Y + 1] < need_hi;           // three or more pieces in 48 nibbles: rare
-            uint32_t n[6];
-            if (!many) {
-                const int64_t gx = s_base[X] + q;
-                const int64_t gy = hasY ? s_base[Y] + q : (int64_t)MG_FRONT_PAD;
-                const uint32_t *px = packed + (gx >> 3), *py = packed + (gy >> 3);
-                const uint32_t shx = ((uint32_t)gx & 7u) << 2, shy = ((uint32_t)gy & 7u) << 2;
-                uint32_t wx[7], wy[7];
+            // The 48 nibbles come from the record's consecutive segment pieces, left to right: each piece overwrites the
+            // window from its first nibble on (one one-sided mask), so one, two or more pieces are the same code.  One trip
+            // for 73 % of the lanes of config 4, two for 26 %, more for the rest (a separate three-piece slow path was
+            // entered by some lane in 43 % of the warp-iterations and cost 17 % of the kernel).
+            uint32_t n[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+            for (int j = X; s_rel[j] < need_hi; j++) {
+                const int c = s_rel[j] - q;               // first window nibble this piece provides (<= 0 for the first piece)
+                if (s_rel[j + 1] - q <= c) continue;      // empty piece
+                const int64_t g = s_base[j] + q;
+                const uint32_t *pp = packed + (g >> 3);
+                const uint32_t sh = ((uint32_t)g & 7u) << 2;
+                uint32_t v[7];
 #pragma unroll
-                for (int k = 0; k < 7; k++) { wx[k] = ld_pk(px + k); wy[k] = ld_pk(py + k); }
-                const int c = eX - q;                 // nibbles [0, c) of the 48 come from X, the rest from Y
+                for (int k = 0; k < 7; k++) v[k] = ld_pk(pp + k);
 #pragma unroll
                 for (int k = 0; k < 6; k++) {
                     const int t = c - 8 * k;
-                    const uint32_t m = t >= 8 ? 0xFFFFFFFFu : (t <= 0 ? 0u : ((1u << (4 * t)) - 1u));
-                    n[k] = (__funnelshift_r(wx[k], wx[k + 1], shx) & m) | (__funnelshift_r(wy[k], wy[k + 1], shy) & ~m);
+                    const uint32_t keep = t >= 8 ? 0xFFFFFFFFu : (t <= 0 ? 0u : ((1u << (4 * t)) - 1u));   // nibbles before the piece
+                    n[k] = (n[k] & keep) | (__funnelshift_r(v[k], v[k + 1], sh) & ~keep);
                 }
-            } else {
-                prot_gather_many(packed, s_base, s_rel, X, q, need_lo, need_hi, n);
             }
             uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -515,7 +491,11 @@ __global__ void __launch_bounds__(PROT_THREADS, PROT_MINB) k_emit_prot(
                 const int bit = 12 * k, ww = bit >> 5, sh = bit & 31;
                 uint32_t idx = n[ww] >> sh;
                 if (sh > 20) idx |= n[ww + 1] << (32 - sh);
+#ifdef K3_ABL_NOLUT
+                w[k >> 2] |= (idx & 0xFFu) << ((k & 3) * 8);
+#else
                 w[k >> 2] |= (uint32_t)s_aa[idx & 0xFFFu] << ((k & 3) * 8);
+#endif
             }
             const uint32_t m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
             if (m == 0xFFFFu) { bw[0] = w[0]; bw[1] = w[1]; bw[2] = w[2]; bw[3] = w[3]; }
