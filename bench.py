@@ -338,25 +338,35 @@ def gpu_arm(args):
     nuc_events = []
 
     step_events = []
+    # The two plans of a step are independent: the CDS plan runs on `stream`, the exon plan on `stream_b`, so the
+    # latency-bound plan kernels (and the host round trip for the totals) of one overlap the emit kernels of the other.
+    stream_b = torch.cuda.Stream(device=dev)
+    spb = ctypes.c_void_p(stream_b.cuda_stream)
+
+    def prepare_on(h, s):
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.check(lib.mg_plan_prepare(h, _lib.MG_PROT_TRIMX, ctypes.byref(a), ctypes.byref(b), s))
 
     def device_step(record):
         ea = ev()
         ea.record(stream)
-        prepare(plans["cds"])
+        prepare_on(plans["cds"], sp)
         e0, e1, ep = ev(), ev(), ev()
         e0.record(stream)
         _lib.check(lib.mg_emit_nuc_device(plans["cds"], P(out_cds_n), sp))
         e1.record(stream)
         _lib.check(lib.mg_emit_prot_device(plans["cds"], P(out_cds_p), sp))
         ep.record(stream)
-        prepare(plans["exon"])
+        eb = ev()
+        eb.record(stream_b)
+        prepare_on(plans["exon"], spb)
         e2, e3 = ev(), ev()
-        e2.record(stream)
-        _lib.check(lib.mg_emit_nuc_device(plans["exon"], P(out_exon_n), sp))
-        e3.record(stream)
+        e2.record(stream_b)
+        _lib.check(lib.mg_emit_nuc_device(plans["exon"], P(out_exon_n), spb))
+        e3.record(stream_b)
         if record:
             nuc_events.append((e0, e1, e2, e3))
-            step_events.append((ea, e0, e1, ep, e2, e3))
+            step_events.append((ea, e0, e1, ep, eb, e2, e3))
 
     def barrier():
         torch.cuda.synchronize()
@@ -374,6 +384,7 @@ def gpu_arm(args):
     s_ev.record(stream)
     for _ in range(args.steps):
         device_step(True)
+    stream.wait_stream(stream_b)
     e_ev.record(stream)
     barrier()
     launches = lib.mg_kernel_launches() - l0
@@ -382,7 +393,8 @@ def gpu_arm(args):
     nuc_ms_exon = sum(c.elapsed_time(d) for _, _, c, d in nuc_events) / len(nuc_events)
     _seg = lambda i: sum(t[i].elapsed_time(t[i + 1]) for t in step_events) / len(step_events)   # noqa: E731
     breakdown = {"k1_plan_cds_ms": round(_seg(0), 4), "k2_nuc_cds_ms": round(_seg(1), 4), "k3_prot_cds_ms": round(_seg(2), 4),
-                 "k1_plan_exon_ms": round(_seg(3), 4), "k2_nuc_exon_ms": round(_seg(4), 4)}
+                 "k1_plan_exon_ms": round(_seg(4), 4), "k2_nuc_exon_ms": round(_seg(5), 4),
+                 "note": "CDS plan on one stream, exon plan on a second: the segments overlap, their sum exceeds ms_per_step"}
 
     # ---- end to end through the C ABI with host buffers
     host_cds_n = torch.empty(sizes["cds"][0], dtype=torch.uint8, pin_memory=True)
@@ -391,9 +403,6 @@ def gpu_arm(args):
 
     # The two plans are independent, so the exon plan goes to a second stream: its table upload (H2D engine) and its
     # kernels overlap the device->host copy of the CDS texts (D2H engine), which is what bounds the step.
-    stream_b = torch.cuda.Stream(device=dev)
-    spb = ctypes.c_void_p(stream_b.cuda_stream)
-
     def create_plan_on(k, s):
         p = pinned[k]
         h = ctypes.c_void_p()
@@ -528,7 +537,7 @@ def gpu_arm(args):
             "config": {"workload": "config 4: synthetic %.2f Gbp human-scale genome (replicated per GPU; forward + reverse-complement planes, 0.5 B/base each) + %d-transcript GTF-shaped batch per GPU; products: CDS nucleotide FASTA + CDS protein FASTA + exon-based transcript FASTA" % (GENOME_BP / 1e9, N_TX),
                        "genome_bp": GENOME_BP, "transcripts_per_gpu": N_TX, "cds_segments": int(tables["cds"].n_seg),
                        "exons": int(tables["exon"].n_seg), "spliced_cds_bp": S_cds, "spliced_exon_bp": S_exon,
-                       "bp_per_step_per_gpu": bp_step, "parallelism": "transcript batches per GPU, genome replicated, no collective",
+                       "bp_per_step_per_gpu": bp_step, "parallelism": "transcript batches per GPU, genome replicated, no collective; per GPU the CDS and exon plans run on two CUDA streams",
                        "l2": "no flush: each step streams ~%.1f GB of distinct output + genome lines, far above the 126 MB L2" % ((d2h_bytes + 0.5 * bp_step) / 1e9),
                        "genome_device_bytes": int(g.device_bytes()), "pack_s": round(t_pack, 3), "setup_s": round(setup_s, 1)},
             "clocks": clk,
