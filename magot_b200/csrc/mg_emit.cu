@@ -95,6 +95,11 @@ __device__ __forceinline__ uint32_t ld_pk(const uint32_t *p) {
     return v;
 }
 
+// word mask with the low 4*t bits set, t clamped to [0, 8] nibbles: one max and one clamped funnel shift
+__device__ __forceinline__ uint32_t low_nibbles(int t) {
+    return __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)(4 * max(t, 0)));
+}
+
 __device__ __forceinline__ void st32(uint8_t *p, const uint32_t w[8]) {          // one 256-bit store (STG.E.ENL2.256)
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
                  "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_nuc(
 #pragma unroll
         for (int k = 0; k < 4; k++) {                  // positions < hiX come from X, the rest from Y
             const int t = c - 8 * k;
-            const uint32_t m = t >= 8 ? 0xFFFFFFFFu : (t <= 0 ? 0u : ((1u << (4 * t)) - 1u));
+            const uint32_t m = low_nibbles(t);
             n[k] = (__funnelshift_r(rx[k], rx[k + 1], shx) & m) | (__funnelshift_r(ry[k], ry[k + 1], shy) & ~m);
         }
         // code 15 = byte outside the packed alphabet on a '+' piece (the reverse plane already holds 'n',
@@ -481,7 +486,7 @@ __global__ void __launch_bounds__(PROT_THREADS, PROT_MINB) k_emit_prot(
 #pragma unroll
                 for (int k = 0; k < 6; k++) {
                     const int t = c - 8 * k;
-                    const uint32_t keep = t >= 8 ? 0xFFFFFFFFu : (t <= 0 ? 0u : ((1u << (4 * t)) - 1u));   // nibbles before the piece
+                    const uint32_t keep = low_nibbles(t);     // nibbles before the piece
                     n[k] = (n[k] & keep) | (__funnelshift_r(v[k], v[k + 1], sh) & ~keep);
                 }
             }
