@@ -37,7 +37,7 @@
 #define NUC_CAP 768                                      // pieces staged per tile (a 32 KB tile of config 4 has ~200); small, so
                                                          // that 8 CTAs fit and most of the SM's 256 KB stays L1 cache (measured +7 %)
 #endif
-#define NUC_UNITS (MG_NUC_TILE / 64)
+#define NUC_UNITS (MG_NUC_TILE / 32)
 #define NUC_CHUNKS (MG_NUC_TILE / 32 / NUC_THREADS)     // 4 chunks of 32 B per thread
 
 #define PROT_THREADS 256
@@ -159,8 +159,7 @@ __device__ __noinline__ void nuc_chunk_slow(const uint32_t *__restrict__ packed,
                                             const uint8_t *__restrict__ lit, const int64_t *__restrict__ exc_pos,
                                             const uint8_t *__restrict__ exc_byte, int64_t n_exc, uint8_t *__restrict__ dst) {
     uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int k = s_unit[p >> 6];
-    while (s_rel[k + 1] <= p) k++;
+    int k = s_unit[p >> 5];
     for (; k < ncache && s_rel[k] - p < end; k++) {
         const int lo = max(s_rel[k] - p, 0), hi = min(s_rel[k + 1] - p, end);
         if (hi <= lo) continue;
@@ -215,7 +214,7 @@ __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_nuc(
     __shared__ int32_t s_rel[NUC_CAP + 3];
     __shared__ uint16_t s_ng[NUC_CAP + 2];
     __shared__ uint8_t s_kind[NUC_CAP + 2];
-    __shared__ uint16_t s_unit[NUC_UNITS];            // piece holding byte 64*u of the tile
+    __shared__ uint16_t s_unit[NUC_UNITS];            // piece holding byte 32*u of the tile, i.e. the first byte of chunk u
     const int64_t P0 = (int64_t)blockIdx.x * MG_NUC_TILE;
     const int64_t p_lo = tile_first[blockIdx.x];
     int64_t p_hi = tile_first[blockIdx.x + 1] + 1;    // one past the last piece this tile can touch
@@ -245,8 +244,8 @@ __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_nuc(
         s_ng[i] = (uint16_t)k;
         if (i < ncache) {
             const int r0 = s_rel[i] < 0 ? 0 : s_rel[i], r1 = s_rel[i + 1] < 0 ? 0 : s_rel[i + 1];
-            const int u1 = min((r1 + 63) >> 6, NUC_UNITS);
-            for (int u = (r0 + 63) >> 6; u < u1; u++) s_unit[u] = (uint16_t)i;
+            const int u1 = min((r1 + 31) >> 5, NUC_UNITS);
+            for (int u = (r0 + 31) >> 5; u < u1; u++) s_unit[u] = (uint16_t)i;
         }
     }
     __syncthreads();
@@ -261,8 +260,7 @@ __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_nuc(
             nuc_chunk_generic(packed, piece_off, piece_src, j, P0 + p, total, T, lit, exc_pos, exc_byte, n_exc, out);
             continue;
         }
-        int A = s_unit[p >> 6];
-        while (s_rel[A + 1] <= p) A++;                 // the (non-empty) piece that holds byte p
+        const int A = s_unit[p >> 5];                  // the (non-empty) piece that holds byte p
         const int end = min(32, tile_len - p);
         const int X = s_ng[A];
         const bool hasX = s_rel[X] - p < end;
