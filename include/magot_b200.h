@@ -92,6 +92,13 @@ int mg_plan_destroy(mg_plan *p);
  * total bytes of the nucleotide text and of the protein text (literals included).
  * Must be called once before any emit; everything stays on the device.                      */
 int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, int64_t *prot_total, void *stream);
+/* The same without the host round trip, for callers that already hold buffers: nuc_capacity / prot_capacity are the sizes
+ * the caller's nucleotide / protein output buffers can take (an upper bound is sum(max(0, end-start+1)) + framing bytes,
+ * resp. a third of it + framing).  K1, K2 and K3 can then be queued back to back on the stream (or captured in a CUDA
+ * graph): the tile counts are derived on the device and surplus CTAs exit.  mg_plan_totals waits for the stream and
+ * returns the real sizes; it fails if they exceeded the capacities (the texts are then truncated).             */
+int mg_plan_prepare_async(mg_plan *p, int prot_flags, int64_t nuc_capacity, int64_t prot_capacity, void *stream);
+int mg_plan_totals(mg_plan *p, int64_t *nuc_total, int64_t *prot_total, void *stream);
 /* Per-record payload lengths to the host (for `longest=True`, genome.py:720-724).
  * nuc_len[r] = spliced bases; aa_len[r] = amino acids, or -1 where the reference's translate
  * returns None (spliced length <= 2, genome.py:810).  Either pointer may be NULL.           */

@@ -206,8 +206,13 @@ __device__ __noinline__ void nuc_chunk_slow(const uint32_t *__restrict__ packed,
 #define PIECE_L 2        // non-empty literal
 __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_nuc(
     const uint32_t *__restrict__ packed, const int64_t *__restrict__ piece_off, const int64_t *__restrict__ piece_src,
-    int64_t n_piece, const int64_t *__restrict__ tile_first, int64_t total, int64_t T, const uint8_t *__restrict__ lit,
-    const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte, int64_t n_exc, uint8_t *__restrict__ out) {
+    int64_t n_piece, const int64_t *__restrict__ tile_first, const int64_t *__restrict__ total_dev, int64_t cap, int64_t T,
+    const uint8_t *__restrict__ lit, const int64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte, int64_t n_exc,
+    uint8_t *__restrict__ out) {
+    // the text size lives on the device (written by K1): the grid may be larger than the text (mg_plan_prepare_async);
+    // cap = what the caller's buffer holds
+    const int64_t total = min(__ldg(total_dev), cap);
+    if ((int64_t)blockIdx.x * MG_NUC_TILE >= total) return;
     // pieces of the tile: piece i covers text [s_rel[i], s_rel[i+1]) relative to the tile; the nibble index (literal: byte
     // index) of tile position q is s_base[i] + q; s_ng[i] = first non-empty GENOME piece at or after i
     __shared__ int64_t s_base[NUC_CAP + 2];
@@ -367,7 +372,10 @@ __global__ void __launch_bounds__(PROT_THREADS, PROT_MINB) k_emit_prot(
     const int64_t *__restrict__ rec_seg_off, const int64_t *__restrict__ prot_off, const int32_t *__restrict__ rec_aa,
     const int8_t *__restrict__ rec_skip, const int32_t *__restrict__ rec_pre, const int32_t *__restrict__ rec_suf,
     const int64_t *__restrict__ rec_lit_off, const uint8_t *__restrict__ lit, int64_t n_rec,
-    const int64_t *__restrict__ tile_first, int64_t total, const uint8_t *__restrict__ aa4096, uint8_t *__restrict__ out) {
+    const int64_t *__restrict__ tile_first, const int64_t *__restrict__ total_dev, int64_t cap, const uint8_t *__restrict__ aa4096,
+    uint8_t *__restrict__ out) {
+    const int64_t total = min(__ldg(total_dev), cap); // on the device, see k_emit_nuc
+    if ((int64_t)blockIdx.x * MG_PROT_TILE >= total) return;
     __shared__ __align__(16) uint8_t s_aa[4096];
     // records of the tile: residues occupy protein-text positions [r_s[i], r_e[i]) relative to the tile (empty when the
     // record has none); r_q0 = nucleotide-text position (relative to O) of the codon that would land on tile position 0;
@@ -535,7 +543,7 @@ extern "C" int mg_emit_nuc_device(mg_plan *p, uint8_t *out_dev, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     p->last_stream = st;
     k_emit_nuc<<<(unsigned)p->n_nuc_tile, NUC_THREADS, 0, st>>>(g->d_packed, p->d_piece_off, p->d_piece_src, p->n_piece, p->d_nuc_tile,
-                                                              p->nuc_total, g->total_bases, p->d_lit, g->d_exc_pos, g->d_exc_byte, g->n_exc, out_dev);
+                                                              p->d_totals, p->nuc_total, g->total_bases, p->d_lit, g->d_exc_pos, g->d_exc_byte, g->n_exc, out_dev);
     MG_LAUNCH_CHECK();
     return MG_OK;
 }
@@ -552,7 +560,7 @@ extern "C" int mg_emit_prot_device(mg_plan *p, uint8_t *out_dev, void *stream) {
     k_emit_prot<<<(unsigned)p->n_prot_tile, PROT_THREADS, 0, st>>>(g->d_packed, p->d_piece_off, p->d_piece_src, p->d_rec_seg_off,
                                                                  p->d_prot_off, p->d_rec_aa, p->d_rec_skip, p->d_rec_pre, p->d_rec_suf,
                                                                  p->d_rec_lit_off, p->n_lit > 0 ? p->d_lit : nullptr, p->n_rec,
-                                                                 p->d_prot_tile, p->prot_total, g->d_aa4096, out_dev);
+                                                                 p->d_prot_tile, p->d_totals + 1, p->prot_total, g->d_aa4096, out_dev);
     MG_LAUNCH_CHECK();
     return MG_OK;
 }
@@ -560,6 +568,7 @@ extern "C" int mg_emit_prot_device(mg_plan *p, uint8_t *out_dev, void *stream) {
 extern "C" int mg_emit_nuc_host(mg_plan *p, uint8_t *out_host, void *stream) {
     MG_REQUIRE(p != nullptr, "plan handle is NULL");
     if (!p->prepared) { mg_set_error("mg_plan_prepare has not been called"); return MG_ESTATE; }
+    if (!p->totals_known) { int rc0 = mg_plan_totals(p, nullptr, nullptr, stream); if (rc0) return rc0; }
     if (p->nuc_total == 0) return MG_OK;
     MG_REQUIRE(out_host != nullptr, "out_host is NULL");
     MG_CUDA(cudaSetDevice(p->device));
@@ -575,6 +584,7 @@ extern "C" int mg_emit_nuc_host(mg_plan *p, uint8_t *out_host, void *stream) {
 extern "C" int mg_emit_prot_host(mg_plan *p, uint8_t *out_host, void *stream) {
     MG_REQUIRE(p != nullptr, "plan handle is NULL");
     if (!p->prepared) { mg_set_error("mg_plan_prepare has not been called"); return MG_ESTATE; }
+    if (!p->totals_known) { int rc0 = mg_plan_totals(p, nullptr, nullptr, stream); if (rc0) return rc0; }
     if (p->prot_total == 0) return MG_OK;
     MG_REQUIRE(out_host != nullptr, "out_host is NULL");
     MG_CUDA(cudaSetDevice(p->device));

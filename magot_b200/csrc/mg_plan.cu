@@ -166,14 +166,18 @@ __global__ void __launch_bounds__(256) k_plan_records(int64_t n_rec, const int64
     if (tile == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) { prot_off[n_rec] = prefix + total; *total_out = prefix + total; }
 }
 
-// thread per tile: index of the piece / record that contains the tile's first byte; nucleotide tiles first, then protein tiles
-__global__ void __launch_bounds__(256) k_plan_tiles(const int64_t *__restrict__ off_a, int64_t n_a, int64_t tile_a, int64_t n_tile_a,
-                                                    int64_t *__restrict__ first_a, const int64_t *__restrict__ off_b, int64_t n_b,
-                                                    int64_t tile_b, int64_t n_tile_b, int64_t *__restrict__ first_b) {
+// thread per tile: index of the piece / record that contains the tile's first byte; nucleotide tiles first, then protein
+// tiles.  The tile counts come from the totals ON THE DEVICE, so the launch needs no host round trip: the grid covers
+// cap_a + cap_b + 2 slots (capacities of the two tables), threads beyond the real counts do nothing.
+__global__ void __launch_bounds__(256) k_plan_tiles(const int64_t *__restrict__ totals, const int64_t *__restrict__ off_a, int64_t n_a,
+                                                    int64_t tile_a, int64_t cap_a, int64_t *__restrict__ first_a,
+                                                    const int64_t *__restrict__ off_b, int64_t n_b, int64_t tile_b, int64_t cap_b,
+                                                    int64_t *__restrict__ first_b) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t *off = off_a;
-    int64_t n = n_a, tile_bytes = tile_a, n_tile = n_tile_a, *tile_first = first_a;
-    if (t > n_tile_a) { t -= n_tile_a + 1; off = off_b; n = n_b; tile_bytes = tile_b; n_tile = n_tile_b; tile_first = first_b; }
+    int64_t n = n_a, tile_bytes = tile_a, cap = cap_a, total = totals[0], *tile_first = first_a;
+    if (t > cap_a) { t -= cap_a + 1; off = off_b; n = n_b; tile_bytes = tile_b; cap = cap_b; total = totals[1]; tile_first = first_b; }
+    const int64_t n_tile = min(cap, (total + tile_bytes - 1) / tile_bytes);
     if (t > n_tile || n_tile == 0) return;
     if (t == n_tile) { tile_first[t] = n > 0 ? n - 1 : 0; return; }
     tile_first[t] = mg_search_le(off, 0, n, t * tile_bytes);
@@ -275,38 +279,35 @@ extern "C" int mg_plan_destroy(mg_plan *p) {
     return MG_OK;
 }
 
-extern "C" int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, int64_t *prot_total, void *stream) {
-    MG_REQUIRE(p != nullptr, "plan handle is NULL");
-    MG_CUDA(cudaSetDevice(p->device));
-    cudaStream_t st = (cudaStream_t)stream;
+// K1, first half: clamp + lengths + offsets of every piece and record; the two text sizes land in p->d_totals
+static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st) {
     mg_genome *g = p->g;
     p->prot_flags = prot_flags;
     p->last_stream = st;
-    int64_t totals[2] = {0, 0};
-    if (p->n_rec > 0) {
-        const int64_t n_block = (p->n_piece + PLAN_TILE - 1) / PLAN_TILE, n_rblock = (p->n_rec + 255) / 256;
-        unsigned long long *tmp_a = reinterpret_cast<unsigned long long *>(p->d_scan_tmp), *tmp_b = tmp_a + n_block + 1;
-        int64_t *d_totals = reinterpret_cast<int64_t *>(tmp_b + n_rblock + 1);
-        MG_CUDA(cudaMemsetAsync(p->d_scan_tmp, 0, p->scan_tmp_cap * sizeof(int64_t), st));
-        k_plan_block_rec<<<(unsigned)n_rblock, 256, 0, st>>>(n_block, p->n_rec, p->d_rec_seg_off, p->d_blk_r0);
-        MG_LAUNCH_CHECK();
-        k_plan_pieces<<<(unsigned)n_block, 256, 0, st>>>(
-            p->n_piece, p->n_rec, p->d_rec_seg_off, p->d_blk_r0, p->d_seg_contig, p->d_seg_start, p->d_seg_end, p->d_seg_strand,
-            p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, g->d_contig_len, g->d_contig_base, g->n_contigs, 2 * g->total_bases,
-            tmp_a, p->d_piece_off, p->d_piece_src, d_totals);
-        MG_LAUNCH_CHECK();
-        k_plan_records<<<(unsigned)n_rblock, 256, 0, st>>>(
-            p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_piece_src, g->d_packed, p->d_rec_phase, prot_flags,
-            p->d_rec_aa, p->d_rec_skip, tmp_b, p->d_prot_off, d_totals + 1);
-        MG_LAUNCH_CHECK();
-        MG_CUDA(cudaMemcpyAsync(totals, d_totals, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-        MG_CUDA(cudaStreamSynchronize(st));
-    }
-    p->nuc_total = totals[0];
-    p->prot_total = totals[1];
-    // tile -> first piece / first record (removes every global binary search from the emit kernels)
-    p->n_nuc_tile = (p->nuc_total + MG_NUC_TILE - 1) / MG_NUC_TILE;
-    p->n_prot_tile = (p->prot_total + MG_PROT_TILE - 1) / MG_PROT_TILE;
+    const int64_t n_block = (p->n_piece + PLAN_TILE - 1) / PLAN_TILE, n_rblock = (p->n_rec + 255) / 256;
+    unsigned long long *tmp_a = reinterpret_cast<unsigned long long *>(p->d_scan_tmp), *tmp_b = tmp_a + n_block + 1;
+    p->d_totals = reinterpret_cast<int64_t *>(tmp_b + n_rblock + 1);
+    MG_CUDA(cudaMemsetAsync(p->d_scan_tmp, 0, p->scan_tmp_cap * sizeof(int64_t), st));
+    if (p->n_rec == 0) return MG_OK;
+    k_plan_block_rec<<<(unsigned)n_rblock, 256, 0, st>>>(n_block, p->n_rec, p->d_rec_seg_off, p->d_blk_r0);
+    MG_LAUNCH_CHECK();
+    k_plan_pieces<<<(unsigned)n_block, 256, 0, st>>>(
+        p->n_piece, p->n_rec, p->d_rec_seg_off, p->d_blk_r0, p->d_seg_contig, p->d_seg_start, p->d_seg_end, p->d_seg_strand,
+        p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, g->d_contig_len, g->d_contig_base, g->n_contigs, 2 * g->total_bases,
+        tmp_a, p->d_piece_off, p->d_piece_src, p->d_totals);
+    MG_LAUNCH_CHECK();
+    k_plan_records<<<(unsigned)n_rblock, 256, 0, st>>>(
+        p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_piece_src, g->d_packed, p->d_rec_phase, prot_flags,
+        p->d_rec_aa, p->d_rec_skip, tmp_b, p->d_prot_off, p->d_totals + 1);
+    MG_LAUNCH_CHECK();
+    return MG_OK;
+}
+
+// K1, second half: tile -> first piece / first record, for texts of up to cap_nuc / cap_prot bytes (the real tile counts are
+// derived on the device from p->d_totals).  Removes every global binary search from the emit kernels.
+static int plan_launch_tiles(mg_plan *p, int64_t cap_nuc, int64_t cap_prot, cudaStream_t st) {
+    p->n_nuc_tile = (cap_nuc + MG_NUC_TILE - 1) / MG_NUC_TILE;
+    p->n_prot_tile = (cap_prot + MG_PROT_TILE - 1) / MG_PROT_TILE;
     const int64_t tile_need = p->n_nuc_tile + 1 + p->n_prot_tile + 1;
     if (tile_need > p->tile_cap) {                   // re-used when the same plan is prepared again
         void *d = nullptr;
@@ -317,13 +318,80 @@ extern "C" int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, i
     }
     p->d_nuc_tile = p->d_tile_buf;
     p->d_prot_tile = p->d_tile_buf + p->n_nuc_tile + 1;
-    if (p->n_nuc_tile + p->n_prot_tile > 0) {
+    if (p->n_rec > 0 && p->n_nuc_tile + p->n_prot_tile > 0) {
         k_plan_tiles<<<(unsigned)((p->n_nuc_tile + p->n_prot_tile + 2 + 255) / 256), 256, 0, st>>>(
-            p->d_piece_off, p->n_piece, MG_NUC_TILE, p->n_nuc_tile, p->d_nuc_tile, p->d_prot_off, p->n_rec, MG_PROT_TILE, p->n_prot_tile,
-            p->d_prot_tile);
+            p->d_totals, p->d_piece_off, p->n_piece, MG_NUC_TILE, p->n_nuc_tile, p->d_nuc_tile, p->d_prot_off, p->n_rec, MG_PROT_TILE,
+            p->n_prot_tile, p->d_prot_tile);
         MG_LAUNCH_CHECK();
     }
+    return MG_OK;
+}
+
+static int plan_read_totals(mg_plan *p, cudaStream_t st, int64_t totals[2]) {
+    totals[0] = totals[1] = 0;
+    if (p->n_rec > 0) {
+        MG_CUDA(cudaMemcpyAsync(totals, p->d_totals, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        MG_CUDA(cudaStreamSynchronize(st));
+    }
+    return MG_OK;
+}
+
+extern "C" int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, int64_t *prot_total, void *stream) {
+    MG_REQUIRE(p != nullptr, "plan handle is NULL");
+    MG_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    p->prepared = false;
+    int rc = plan_launch_scans(p, prot_flags, st);
+    if (rc) return rc;
+    int64_t totals[2];
+    rc = plan_read_totals(p, st, totals);            // the one host round trip: the caller sizes its buffers from these
+    if (rc) return rc;
+    p->nuc_total = totals[0];
+    p->prot_total = totals[1];
+    p->totals_known = true;
+    rc = plan_launch_tiles(p, p->nuc_total, p->prot_total, st);
+    if (rc) return rc;
     p->prepared = true;
+    if (nuc_total) *nuc_total = p->nuc_total;
+    if (prot_total) *prot_total = p->prot_total;
+    return MG_OK;
+}
+
+extern "C" int mg_plan_prepare_async(mg_plan *p, int prot_flags, int64_t nuc_capacity, int64_t prot_capacity, void *stream) {
+    MG_REQUIRE(p != nullptr, "plan handle is NULL");
+    MG_REQUIRE(nuc_capacity >= 0 && prot_capacity >= 0, "capacities must be >= 0");
+    MG_CUDA(cudaSetDevice(p->device));
+    p->prepared = false;
+    int rc = plan_launch_scans(p, prot_flags, (cudaStream_t)stream);
+    if (rc) return rc;
+    rc = plan_launch_tiles(p, nuc_capacity, prot_capacity, (cudaStream_t)stream);
+    if (rc) return rc;
+    p->nuc_total = nuc_capacity;                     // until mg_plan_totals: what the caller's buffers can take
+    p->prot_total = prot_capacity;
+    p->totals_known = false;
+    p->prepared = true;
+    return MG_OK;
+}
+
+extern "C" int mg_plan_totals(mg_plan *p, int64_t *nuc_total, int64_t *prot_total, void *stream) {
+    MG_REQUIRE(p != nullptr, "plan handle is NULL");
+    if (!p->prepared) { mg_set_error("mg_plan_prepare has not been called"); return MG_ESTATE; }
+    MG_CUDA(cudaSetDevice(p->device));
+    if (!p->totals_known) {
+        int64_t totals[2];
+        int rc = plan_read_totals(p, (cudaStream_t)stream, totals);
+        if (rc) return rc;
+        if (totals[0] > p->nuc_total || totals[1] > p->prot_total) {
+            mg_set_error("text sizes (%lld nucleotide, %lld protein bytes) exceed the capacities given to mg_plan_prepare_async "
+                         "(%lld, %lld): the emitted texts are truncated", (long long)totals[0], (long long)totals[1],
+                         (long long)p->nuc_total, (long long)p->prot_total);
+            return MG_EINVAL;
+        }
+        p->nuc_total = totals[0];
+        p->prot_total = totals[1];
+        p->totals_known = true;
+        // the tile tables stay sized for the capacities: n_nuc_tile / n_prot_tile remain upper bounds of the grids
+    }
     if (nuc_total) *nuc_total = p->nuc_total;
     if (prot_total) *prot_total = p->prot_total;
     return MG_OK;

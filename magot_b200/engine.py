@@ -160,6 +160,31 @@ class Plan(object):
         self.nuc_total, self.prot_total = a.value, b.value
         return self.nuc_total, self.prot_total
 
+    def capacities(self):
+        """Upper bounds of the two text sizes from the host tables alone (what mg_plan_prepare_async needs): every
+        segment at most end-start+1 bases before clamping, a protein at most a third of its record's bases."""
+        t = self.table
+        pay = t.approx_bytes_per_record() - t.rec_pre_len - t.rec_suf_len
+        lit = int(t.rec_pre_len.astype(np.int64).sum() + t.rec_suf_len.astype(np.int64).sum())
+        return int(pay.sum()) + lit, int((pay // 3).sum()) + lit
+
+    def prepare_async(self, nuc_capacity=None, prot_capacity=None, trimx=True, use_phase=False):
+        """K1 without the host round trip; sizes come later from totals()."""
+        if nuc_capacity is None or prot_capacity is None:
+            a, b = self.capacities()
+            nuc_capacity = a if nuc_capacity is None else nuc_capacity
+            prot_capacity = b if prot_capacity is None else prot_capacity
+        flags = (_lib.MG_PROT_TRIMX if trimx else 0) | (_lib.MG_PROT_USE_PHASE if use_phase else 0)
+        check(lib.mg_plan_prepare_async(self.handle, flags, int(nuc_capacity), int(prot_capacity), self.stream))
+        self.nuc_total = self.prot_total = None
+        return int(nuc_capacity), int(prot_capacity)
+
+    def totals(self):
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(lib.mg_plan_totals(self.handle, ctypes.byref(a), ctypes.byref(b), self.stream))
+        self.nuc_total, self.prot_total = a.value, b.value
+        return self.nuc_total, self.prot_total
+
     def lengths(self):
         n = self.table.n_rec
         nuc = np.empty(n, dtype=np.int64)

@@ -338,6 +338,59 @@ def test_sixframe_random_contigs(mg, min_aa):
     _sixframe_case(mg, contigs, min_aa)
 
 
+def test_prepare_async_equals_prepare(mg):
+    """mg_plan_prepare_async (no host round trip, grids sized by the caller's capacities, text sizes read on the device)
+    produces the same two texts as mg_plan_prepare -- with tight capacities, generous ones, and with segments that the
+    Python-slice clamp shortens (capacity >> real size); too small a capacity is reported by mg_plan_totals."""
+    import torch
+    from magot_b200 import engine, synth, _lib
+    layout = synth.contig_layout("human", 3_000_000, 11)
+    contigs = synth.synth_genome_host(layout, 11, n_mean=300)
+    g = engine.DeviceGenome([a.size for a in contigs], device=0)
+    for i, a in enumerate(contigs):
+        g.pack(i, a)
+    g.finalize()
+    ann = synth.synth_annotation(layout, 1500, 11)
+    for which, framing in (("cds", True), ("exon", True), ("cds", False)):
+        tbl = ann.table(which, framing=framing)
+        # make some segments run off their contig: the clamp shortens them, the host-side upper bound does not know
+        tbl.seg_end[::97] += 5_000_000
+        plan = engine.Plan(g, tbl)
+        nuc, prot = plan.prepare()
+        want_n = plan.emit_host(protein=False).tobytes()
+        want_p = plan.emit_host(protein=True).tobytes()
+        plan.close()
+        for slack in (0, 1, 100_000):
+            plan = engine.Plan(g, tbl)
+            cap_n, cap_p = plan.capacities()
+            assert cap_n >= nuc and cap_p >= prot
+            if slack == 0:
+                cap_n, cap_p = nuc, prot                       # exactly tight
+            else:
+                cap_n, cap_p = cap_n + slack, cap_p + slack
+            plan.prepare_async(cap_n, cap_p)
+            out_n = torch.zeros((cap_n + 31) // 32 * 32 + 32, dtype=torch.uint8, device="cuda")
+            out_p = torch.zeros((cap_p + 31) // 32 * 32 + 32, dtype=torch.uint8, device="cuda")
+            plan.emit_device(out_n.data_ptr(), protein=False)
+            plan.emit_device(out_p.data_ptr(), protein=True)
+            assert plan.totals() == (nuc, prot)
+            assert out_n[:nuc].cpu().numpy().tobytes() == want_n
+            assert out_p[:prot].cpu().numpy().tobytes() == want_p
+            # host variants after an async prepare resolve the sizes themselves
+            assert plan.emit_host(protein=True).tobytes() == want_p
+            plan.close()
+        plan = engine.Plan(g, tbl)
+        plan.prepare_async(max(nuc - 40_000, 0), prot)
+        out_n = torch.zeros((nuc + 31) // 32 * 32 + 32, dtype=torch.uint8, device="cuda")
+        plan.emit_device(out_n.data_ptr(), protein=False)
+        with pytest.raises(_lib.MagotError):
+            plan.totals()
+        torch.cuda.synchronize()
+        assert int(out_n[max(nuc - 40_000, 0) + 64:].max().item()) == 0      # nothing written past the capacity (+ one chunk)
+        plan.close()
+    g.close()
+
+
 @pytest.mark.parametrize("min_aa", [0, 16])
 def test_sixframe_dense_output_second_pass(mg, min_aa, monkeypatch):
     """More kept ORFs than the scan pass's hit list holds: the records come from the second genome pass instead."""
