@@ -245,6 +245,53 @@ def test_synthetic_twin_against_c_oracle(mg, kind, total, ntx, seed):
     g.close()
 
 
+@pytest.mark.parametrize("framing", [False, True])
+def test_dense_tiny_segments_overflow_the_tile_staging(mg, framing):
+    """Thousands of 1-8 base segments per 32 KB of text: far more pieces / records per tile than K2 and K3 stage in shared
+    memory (NUC_CAP, PROT_RCAP, PROT_PCAP), so whole tiles go through the generic global-memory paths -- same bytes."""
+    from magot_b200 import engine
+    rng = np.random.default_rng(77)
+    alpha = np.frombuffer(b"ACGTacgtNnRY*", dtype=np.uint8)
+    contigs = [alpha[rng.integers(0, alpha.size, size=n)].copy() for n in (50_000, 777, 120_000)]
+    g = engine.DeviceGenome([a.size for a in contigs], device=0)
+    for i, a in enumerate(contigs):
+        g.pack(i, a)
+    g.finalize()
+    n_rec = 4000
+    n_seg = rng.integers(0, 40, size=n_rec)
+    n_seg[::50] = 400                                   # a few records with hundreds of tiny segments
+    rec_off = np.concatenate(([0], np.cumsum(n_seg)))
+    E = int(rec_off[-1])
+    cid = rng.integers(0, 3, size=E).astype(np.int32)
+    lens = np.array([a.size for a in contigs])[cid]
+    st = rng.integers(1, lens - 10)
+    en = st + rng.integers(0, 8, size=E)
+    sd = rng.integers(0, 2, size=E).astype(np.int8)
+    names = ["r%d" % i for i in range(n_rec)]
+    if framing:
+        pre = np.array([len(n) + 2 for n in names], dtype=np.int32)
+        suf = np.ones(n_rec, dtype=np.int32)
+        lit = np.frombuffer("".join(">" + n + "\n\n" for n in names).encode(), dtype=np.uint8)
+        lit_off = np.concatenate(([0], np.cumsum(pre + suf)[:-1]))
+    else:
+        pre = suf = np.zeros(n_rec, dtype=np.int32)
+        lit = np.zeros(0, dtype=np.uint8)
+        lit_off = np.zeros(n_rec, dtype=np.int64)
+    tbl = engine.RecordTable(rec_off, cid, st, en, sd, lit_off, pre, suf, lit)
+    nuc, off, aa, aa_off, aa_len = _oracle_products(contigs, tbl)
+    text, (got_n, got_a) = engine.run_table(g, tbl, want_lengths=True)
+    textp, _ = engine.run_table(g, tbl, protein=True)
+    assert np.array_equal(got_n, np.diff(off)) and np.array_equal(got_a, aa_len)
+    if framing:
+        want = b"".join(b">" + n.encode() + b"\n" + nuc[off[i]:off[i + 1]].tobytes() + b"\n" for i, n in enumerate(names))
+        wantp = b"".join(b">" + n.encode() + b"\n" + aa[aa_off[i]:aa_off[i + 1]].tobytes() + b"\n" for i, n in enumerate(names))
+    else:
+        want, wantp = nuc.tobytes(), aa.tobytes()
+    assert text == want
+    assert textp == wantp
+    g.close()
+
+
 def test_edge_records(mg):
     """Empty records, zero-length segments, 1-base segments, records <= 2 bases (translate -> None)."""
     from magot_b200 import engine
