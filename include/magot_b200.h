@@ -64,6 +64,14 @@ int64_t mg_genome_bytes(const mg_genome *g);          /* device bytes held by th
  * get_scaffold_fasta (genome.py:907) and BaseAnnotation.get_seq (genome.py:603-608).        */
 int mg_genome_fetch(mg_genome *g, int64_t contig, int64_t lo, int64_t hi, int minus, uint8_t *out_host, void *stream);
 
+/* ---- K5: interval scatter -- replaces the list surgery of mask_from_gff (genome_tools.py:394-428).
+ * Intervals are 0-based half-open [lo, hi) on `contig`, already clamped like the Python slice
+ * [start-1:stop]; they may overlap.  hard = 0: lower-case them (soft mask); hard = 1: replace them
+ * by 'N'.  upper_first != 0 upper-cases the whole genome before (overwrite_softmask, :403-404).
+ * Both planes and the exception list are updated; the handle stays finalized.                 */
+int mg_genome_mask(mg_genome *g, int64_t n_intervals, const int32_t *contig, const int64_t *lo, const int64_t *hi,
+                   int hard, int upper_first, void *stream);
+
 /* ---- K1: interval tables -- replaces the per-child work of ParentAnnotation.get_fasta
  * (genome.py:687-705) and the slice arithmetic of BaseAnnotation.get_seq (genome.py:603-608).
  * A plan is a list of n_rec output records.  Record r owns segments

@@ -52,6 +52,7 @@ SIGNATURES = {
     "mg_genome_fetch": (_i32, [_vp, _i64, _i64, _i64, _i32, _vp, _vp]),
     "mg_plan_create": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _pp]),
     "mg_plan_destroy": (_i32, [_vp]),
+    "mg_genome_mask": (_i32, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp]),
     "mg_plan_prepare": (_i32, [_vp, _i32, _pi64, _pi64, _vp]),
     "mg_plan_prepare_async": (_i32, [_vp, _i32, _i64, _i64, _vp]),
     "mg_plan_totals": (_i32, [_vp, _pi64, _pi64, _vp]),

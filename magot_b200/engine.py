@@ -79,6 +79,13 @@ class DeviceGenome(object):
         check(lib.mg_genome_fetch(self.handle, contig, lo, hi, 1 if minus else 0, _ptr(out), None))
         return out.tobytes()
 
+    def mask(self, contig, lo, hi, hard=False, upper_first=False):
+        """K5: lower-case (soft) or 'N' (hard) the 0-based half-open intervals, optionally upper-casing everything first."""
+        contig = np.ascontiguousarray(contig, dtype=np.int32)
+        lo = np.ascontiguousarray(lo, dtype=np.int64)
+        hi = np.ascontiguousarray(hi, dtype=np.int64)
+        check(lib.mg_genome_mask(self.handle, contig.size, _ptr(contig), _ptr(lo), _ptr(hi), int(bool(hard)), int(bool(upper_first)), None))
+
     def device_bytes(self):
         return lib.mg_genome_bytes(self.handle)
 

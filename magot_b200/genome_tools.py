@@ -8,7 +8,7 @@ reference) and every tool prints to stdout exactly what the reference prints.
 
 Kept (file:line in genome_tools.py): gff2fasta :324, cds2pep :664, coords2fasta :656,
 get_seq_from_fasta :483, exclude_from_fasta :377, extract_upstream_downstream :457,
-blast_csv2fasta :265, exonerate2fasta :274,
+blast_csv2fasta :265, exonerate2fasta :274, mask_from_gff :394,
 dna2orfs :145 (the reference's version cannot run -- it calls str.translate with keyword
 arguments -- this one does what it intended, on the device).  The dispatcher (main :25-45)
 keeps the grammar but looks the function up in a table instead of eval()-ing a string.
@@ -54,6 +54,75 @@ def exonerate2fasta(genome_sequence, exonerate_file):
     my_genome = genome.Genome(genome_sequence)
     my_genome.read_exonerate(exonerate_file)
     print(my_genome.annotations.get_fasta('match'))
+
+
+def mask_from_gff(genome_sequence, gff, mask_type="soft", overwrite_softmask="True", feature_type="CDS"):
+    """genome_tools.py:394-428 -- soft- (lower-case) or hard- ('N') mask every `feature_type` interval of a GFF and print
+    the genome, one line per sequence.  The intervals are scattered onto the packed genome on the device (K5).
+    Kept from the reference: seqid = first word of the header, a repeated header starts the sequence over, any GFF line with
+    more than 5 tabs counts, coordinates follow Python slice rules, the printed order is the reference's dict order.
+    Not kept: a hard mask whose slice is clamped changes the sequence LENGTH in the reference (list slice assignment);
+    that raises NotImplementedError here."""
+    with open(genome_sequence, "rb") as fh:
+        data = fh.read()
+    if overwrite_softmask in ("True", "T", "true", "t", "TRUE"):
+        upper_first = True
+    elif overwrite_softmask in ("False", "F", "false", "f", "FALSE"):
+        upper_first = False
+    else:
+        upper_first = None
+    seqs = {}
+    working = None
+    lines = data.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()                                     # no line after the final newline
+    for line in lines:
+        if line[:1] == b">":
+            working = line.decode("latin-1").split()[0][1:].replace('\r', '')
+            seqs[working] = []
+        elif line or working is None:
+            if working is None:
+                raise KeyError("")                      # sequence before the first header: genome_dict[""] in the reference
+            if upper_first is None:
+                print("Invalid option for 'overwrite_softmask', argument accepts 'True' or 'False'")
+                return None
+            seqs[working].append(line.replace(b"\r", b""))
+    names = genome._order(list(seqs))
+    arrays = [np.frombuffer(b"".join(seqs[n]), dtype=np.uint8) for n in names]
+    index = {n: i for i, n in enumerate(names)}
+    cid, lo, hi = [], [], []
+    with open(gff, encoding="latin-1", newline="\n") as fh:
+        for line in fh:
+            if line.count('\t') > 5:
+                fields = line.split('\t')
+                if fields[2] == feature_type:
+                    start, stop = int(fields[3]), int(fields[4])
+                    ci = index[fields[0]]                # KeyError for an unknown seqid, as the reference
+                    a, b, _ = slice(start - 1, stop).indices(arrays[ci].size)
+                    b = max(a, b)
+                    if mask_type == "soft":
+                        pass
+                    elif mask_type == "hard":
+                        if b - a != max(1 + stop - start, 0):
+                            raise NotImplementedError("hard mask %s:%d-%d is clamped by the sequence end: the reference would "
+                                                      "change the sequence length here" % (fields[0], start, stop))
+                    else:
+                        print("Invalid option for mask_type, argument accepts 'soft' and 'hard'")
+                        return None
+                    cid.append(ci)
+                    lo.append(a)
+                    hi.append(b)
+    g = engine.DeviceGenome([a.size for a in arrays], device=0)
+    try:
+        for ci, a in enumerate(arrays):
+            g.pack(ci, a)
+        g.finalize()
+        g.mask(cid, lo, hi, hard=(mask_type == "hard"), upper_first=bool(upper_first))
+        for ci, n in enumerate(names):
+            L = arrays[ci].size
+            print(">" + n + "\n" + (g.fetch(ci, 0, L).decode("latin-1") if L else ""))
+    finally:
+        g.close()
 
 
 def cds2pep(fasta_file):
@@ -196,7 +265,7 @@ def dna2orfs(fasta_location, output_file, from_atg=False, longest=False, min_orf
 
 
 FUNCTIONS = {f.__name__: f for f in (gff2fasta, cds2pep, coords2fasta, get_seq_from_fasta, exclude_from_fasta,
-                                     extract_upstream_downstream, dna2orfs, blast_csv2fasta, exonerate2fasta)}
+                                     extract_upstream_downstream, dna2orfs, blast_csv2fasta, exonerate2fasta, mask_from_gff)}
 
 
 def help_func():

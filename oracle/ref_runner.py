@@ -99,3 +99,23 @@ def aligner_model(fasta, reader, path):
             model[name] = [[k, v.seqid, list(v.get_coords()) if hasattr(v, "coords") else None, v.strand, v.parent,
                             list(getattr(v, "child_list", []))] for k, v in val.items()]
     return model
+
+
+def mask_from_gff(fasta, gff, **kw):
+    """stdout of genome_tools.py:394-428 (the reference's own function), records put back into Python-2.7 dict order."""
+    import contextlib
+    import importlib
+    import io
+    ref()
+    gt = importlib.import_module("genome_tools")
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        gt.mask_from_gff(fasta, gff, **kw)
+    text = buf.getvalue()
+    if not text.startswith(">"):
+        return text
+    recs = {}
+    lines = text.split("\n")
+    for k in range(0, len(lines) - 1, 2):
+        recs[lines[k][1:]] = lines[k + 1]
+    return "".join(">" + n + "\n" + recs[n] + "\n" for n in py2_order(list(recs)))

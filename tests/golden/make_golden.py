@@ -174,6 +174,61 @@ def aligner_cases(cases):
         json.dump(model, fh, indent=0)
 
 
+def mask_inputs():
+    """Small FASTA + GFF for mask_from_gff (committed under aligner_inputs/): soft-masked and IUPAC bases, bytes outside
+    the packed alphabet, a repeated header, CRLF lines, overlapping / duplicate / clamped / empty intervals."""
+    rnd = random.Random(99)
+    out = os.path.join(HERE, "aligner_inputs")
+    os.makedirs(out, exist_ok=True)
+    alpha = "ACGT" * 8 + "acgt" * 6 + "NNnn" + "RYKMrykmSWBDHVswbdhv*-. x"
+    seqs = [("ctgA desc one", 5000), ("ctgB", 1234), ("ctgC\tTabbed", 801), ("ctgA second copy replaces the first", 3000),
+            ("short", 7), ("ctgD", 40000)]
+    with open(os.path.join(out, "mask.fasta"), "w", newline="") as fh:
+        for name, n in seqs:
+            s = "".join(rnd.choice(alpha) for _ in range(n))
+            fh.write(">" + name + "\n")
+            eol = "\r\n" if name == "ctgB" else "\n"
+            for k in range(0, n, 70):
+                fh.write(s[k:k + 70] + eol)
+    lens = {"ctgA": 3000, "ctgB": 1234, "ctgC": 801, "short": 7, "ctgD": 40000}
+    rows = ["##gff-version 3"]
+    for i in range(300):
+        c = rnd.choice(list(lens))
+        L = lens[c]
+        a = rnd.randrange(1, L + 1)
+        b = min(L, a + rnd.randrange(0, 400))
+        ftype = rnd.choice(["CDS", "CDS", "CDS", "exon", "gene"])
+        rows.append("\t".join([c, "src", ftype, str(a), str(b), ".", rnd.choice("+-"), ".", "ID=f%d" % i]))
+    rows.append("\t".join(["ctgA", "src", "CDS", "10", "20", ".", "+", ".", "ID=dup"]))
+    rows.append("\t".join(["ctgA", "src", "CDS", "10", "20", ".", "+", ".", "ID=dup"]))
+    rows.append("\t".join(["ctgA", "src", "CDS", "15", "12", ".", "+", ".", "ID=backwards"]))          # empty slice
+    rows.append("\t".join(["ctgB", "src", "CDS", "1", "1234", ".", "+"]))                               # 6 tabs only: still counts
+    rows.append("ctgB\tsrc\tCDS\t5\t9")                                                               # 4 tabs: ignored
+    with open(os.path.join(out, "mask.gff"), "w") as fh:
+        fh.write("\n".join(rows) + "\n")
+    soft_extra = list(rows)
+    soft_extra.append("\t".join(["short", "src", "CDS", "3", "500", ".", "+", ".", "ID=clamped"]))        # soft: slice clamps
+    soft_extra.append("\t".join(["ctgC", "src", "CDS", "0", "5", ".", "+", ".", "ID=zero"]))             # [-1:5] -> empty
+    soft_extra.append("\t".join(["ctgC", "src", "CDS", "-20", "-3", ".", "+", ".", "ID=negative"]))       # negative indices
+    with open(os.path.join(out, "mask_soft.gff"), "w") as fh:
+        fh.write("\n".join(soft_extra) + "\n")
+    return os.path.join(out, "mask.fasta"), os.path.join(out, "mask.gff"), os.path.join(out, "mask_soft.gff")
+
+
+def mask_cases(cases):
+    fa, gff, gff_soft = mask_inputs()
+    ob_fa, ob_gff = os.path.join(REF_DATA, DATA_FILES[0]), os.path.join(REF_DATA, DATA_FILES[1])
+    runs = {"mask:soft": (fa, gff_soft, {}),
+            "mask:soft_keep_case": (fa, gff_soft, {"overwrite_softmask": "False"}),
+            "mask:hard": (fa, gff, {"mask_type": "hard"}),
+            "mask:hard_keep_case_exon": (fa, gff, {"mask_type": "hard", "overwrite_softmask": "F", "feature_type": "exon"}),
+            "mask:obiroi_soft": (ob_fa, ob_gff, {}),
+            "mask:obiroi_hard_exon": (ob_fa, ob_gff, {"mask_type": "hard", "feature_type": "exon", "overwrite_softmask": "False"})}
+    for name, (a, b, kw) in runs.items():
+        c, n = cksum(ref_runner.mask_from_gff(a, b, **kw))
+        cases[name] = {"cksum": c, "bytes": n}
+
+
 ALPHABETS = {
     "acgt": "ACGT",
     "mixed": "ACGTacgtNn",
@@ -233,6 +288,7 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         cases = whole_file_cases(tmp)
     aligner_cases(cases)
+    mask_cases(cases)
     with open(os.path.join(HERE, "manifest.json"), "w") as fh:
         json.dump(cases, fh, indent=1, sort_keys=True)
     with open(os.path.join(HERE, "kat.json"), "w") as fh:

@@ -1,4 +1,5 @@
-"""Parity at BASELINE.json's FULL sizes (configs 4 and 5: 3.1 Gbp genome, 200 k transcripts) through size-independent
+"""Parity at BASELINE.json's FULL sizes (config 3: 500 Mbp / 60 k transcripts; configs 4 and 5: 3.1 Gbp genome, 200 k
+transcripts, whole-genome six-frame) through size-independent
 properties -- the C oracle cannot redo 800 Mbp of text in seconds, so the checks are:
 
   * sampled records: K2's text of a record == its framing + the record's segments fetched one by one through the
@@ -26,26 +27,39 @@ N_TX = 200_000
 SEED = 4
 
 
-@pytest.fixture(scope="module")
-def big():
+def _build(kind, genome_bp, n_tx, seed):
     import torch
     from magot_b200 import engine, synth, _lib
     _lib.require_device(0)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    layout = synth.contig_layout("human", GENOME_BP, SEED)
+    layout = synth.contig_layout(kind, genome_bp, seed)
     g = engine.DeviceGenome([l for _, l in layout], device=0)
     CH = 256 << 20
     for ci, (_, L) in enumerate(layout):
         for off in range(0, L, CH):
             n = min(CH, L - off)
-            a = synth.synth_contig_device(n, SEED * 1000003 + ci * 64 + off // CH, dev)
+            a = synth.synth_contig_device(n, seed * 1000003 + ci * 64 + off // CH, dev)
             g.pack_device(ci, a.data_ptr(), n, offset=off)
             torch.cuda.synchronize()
             del a
     g.finalize()
     torch.cuda.empty_cache()
-    ann = synth.synth_annotation(layout, N_TX, SEED)
+    return g, layout, synth.synth_annotation(layout, n_tx, seed)
+
+
+@pytest.fixture(scope="module")
+def insect():
+    """BASELINE config 3: 500 Mbp in 2 000 scaffolds, 60 k transcripts."""
+    g, layout, ann = _build("insect", 500_000_000, 60_000, 3)
+    yield g, layout, ann
+    g.close()
+
+
+@pytest.fixture(scope="module")
+def big():
+    """BASELINE configs 4 and 5: 3.1 Gbp in 24 chromosomes + 170 scaffolds, 200 k transcripts."""
+    g, layout, ann = _build("human", GENOME_BP, N_TX, SEED)
     yield g, layout, ann
     g.close()
 
@@ -68,9 +82,17 @@ def _record_offsets(table, nuc_len):
     return np.concatenate(([0], np.cumsum(sizes)))
 
 
+def test_config3_full_size_properties(insect):
+    _check_splice_properties(insect, "cds")
+
+
 @pytest.mark.parametrize("which", ["cds", "exon"])
 def test_config4_full_size_properties(big, which):
-    g, layout, ann = big
+    _check_splice_properties(big, which)
+
+
+def _check_splice_properties(fixture, which):
+    g, layout, ann = fixture
     table = ann.table(which)
     lens = np.array([l for _, l in layout], dtype=np.int64)
     text, nuc_len, aa_len = _emit(g, table)

@@ -114,6 +114,30 @@ def test_aligner_output_entry_points(mg, ref_data, manifest):
     assert _ck(g.annotations.get_fasta('match') + "\n") == manifest["obiroi:blast_csv2fasta"]
 
 
+def test_mask_from_gff(mg, ref_data, manifest):
+    """mask_from_gff (genome_tools.py:394-428) through the K5 interval scatter: soft / hard, with and without upper-casing first,
+    on a FASTA with soft-masked, IUPAC and out-of-alphabet bytes, CRLF lines and a repeated header, and a GFF with
+    overlapping, duplicate, clamped, negative and empty intervals; whole stdout against the reference's."""
+    from magot_b200 import genome_tools as gt
+    inputs = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aligner_inputs")
+    fa, gff, gff_soft = (os.path.join(inputs, f) for f in ("mask.fasta", "mask.gff", "mask_soft.gff"))
+    ob_fa = os.path.join(ref_data, "O.biroi_refseqGenomeSubset.fasta")
+    ob_gff = os.path.join(ref_data, "O.biroi_NCBIrefseq_gff3Subset.gff")
+    assert _ck(_stdout_of(gt.mask_from_gff, fa, gff_soft)) == manifest["mask:soft"]
+    assert _ck(_stdout_of(gt.mask_from_gff, fa, gff_soft, overwrite_softmask="False")) == manifest["mask:soft_keep_case"]
+    assert _ck(_stdout_of(gt.mask_from_gff, fa, gff, mask_type="hard")) == manifest["mask:hard"]
+    assert _ck(_stdout_of(gt.mask_from_gff, fa, gff, mask_type="hard", overwrite_softmask="F", feature_type="exon")) == \
+        manifest["mask:hard_keep_case_exon"]
+    assert _ck(_stdout_of(gt.mask_from_gff, ob_fa, ob_gff)) == manifest["mask:obiroi_soft"]
+    assert _ck(_stdout_of(gt.mask_from_gff, ob_fa, ob_gff, mask_type="hard", feature_type="exon", overwrite_softmask="False")) == \
+        manifest["mask:obiroi_hard_exon"]
+    # option handling of the reference: a message and None
+    assert "Invalid option for 'overwrite_softmask'" in _stdout_of(gt.mask_from_gff, fa, gff, overwrite_softmask="maybe")
+    assert "Invalid option for mask_type" in _stdout_of(gt.mask_from_gff, fa, gff, mask_type="medium")
+    with pytest.raises(NotImplementedError):            # the reference would lengthen the sequence here
+        gt.mask_from_gff(fa, gff_soft, mask_type="hard")
+
+
 def test_obiroi_whole_api(mg, ref_data, manifest):
     from magot_b200 import genome_tools as gt
     fa = os.path.join(ref_data, "O.biroi_refseqGenomeSubset.fasta")
