@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(PROT_THREADS, PROT_MINB) k_emit_prot(
     const int8_t *__restrict__ rec_skip, const int32_t *__restrict__ rec_pre, const int32_t *__restrict__ rec_suf,
     const int64_t *__restrict__ rec_lit_off, const uint8_t *__restrict__ lit, int64_t n_rec,
     const int64_t *__restrict__ tile_first, const int64_t *__restrict__ total_dev, int64_t cap, const uint8_t *__restrict__ aa4096,
-    uint8_t *__restrict__ out) {
+    const uint8_t *__restrict__ aa4096h, uint8_t *__restrict__ out) {
     const int64_t total = min(__ldg(total_dev), cap); // on the device, see k_emit_nuc
     if ((int64_t)blockIdx.x * MG_PROT_TILE >= total) return;
     __shared__ __align__(16) uint8_t s_aa[4096];
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(PROT_THREADS, PROT_MINB) k_emit_prot(
     __shared__ int64_t s_base[PROT_PCAP + 4];
     __shared__ int32_t s_rel[PROT_PCAP + 5];
     __shared__ uint16_t s_unit[PROT_UNITS];
-    reinterpret_cast<uint4 *>(s_aa)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(aa4096) + threadIdx.x);
+    reinterpret_cast<uint4 *>(s_aa)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(aa4096h) + threadIdx.x);   // mg_aa_slot order
     const int64_t P0 = (int64_t)blockIdx.x * MG_PROT_TILE;
     const int64_t r_lo = tile_first[blockIdx.x];
     int64_t r_hi = tile_first[blockIdx.x + 1] + 1;
@@ -502,11 +502,7 @@ __global__ void __launch_bounds__(PROT_THREADS, PROT_MINB) k_emit_prot(
                 const int bit = 12 * k, ww = bit >> 5, sh = bit & 31;
                 uint32_t idx = n[ww] >> sh;
                 if (sh > 20) idx |= n[ww + 1] << (32 - sh);
-#ifdef K3_ABL_NOLUT
-                w[k >> 2] |= (idx & 0xFFu) << ((k & 3) * 8);
-#else
-                w[k >> 2] |= (uint32_t)s_aa[idx & 0xFFFu] << ((k & 3) * 8);
-#endif
+                w[k >> 2] |= (uint32_t)s_aa[mg_aa_slot(idx)] << ((k & 3) * 8);
             }
             const uint32_t m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
             if (m == 0xFFFFu) { bw[0] = w[0]; bw[1] = w[1]; bw[2] = w[2]; bw[3] = w[3]; }
@@ -560,7 +556,7 @@ extern "C" int mg_emit_prot_device(mg_plan *p, uint8_t *out_dev, void *stream) {
     k_emit_prot<<<(unsigned)p->n_prot_tile, PROT_THREADS, 0, st>>>(g->d_packed, p->d_piece_off, p->d_piece_src, p->d_rec_seg_off,
                                                                  p->d_prot_off, p->d_rec_aa, p->d_rec_skip, p->d_rec_pre, p->d_rec_suf,
                                                                  p->d_rec_lit_off, p->n_lit > 0 ? p->d_lit : nullptr, p->n_rec,
-                                                                 p->d_prot_tile, p->d_totals + 1, p->prot_total, g->d_aa4096, out_dev);
+                                                                 p->d_prot_tile, p->d_totals + 1, p->prot_total, g->d_aa4096, g->d_aa4096h, out_dev);
     MG_LAUNCH_CHECK();
     return MG_OK;
 }

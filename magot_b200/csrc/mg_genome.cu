@@ -101,6 +101,10 @@ extern "C" int mg_genome_create(int device, int64_t n_contigs, const int64_t *co
     build_aa4096(tbl);
     MG_CUDA(cudaMalloc(&g->d_aa4096, 4096));
     MG_CUDA(cudaMemcpy(g->d_aa4096, tbl, 4096, cudaMemcpyHostToDevice));
+    uint8_t tblh[4096];
+    for (uint32_t c = 0; c < 4096; c++) tblh[mg_aa_slot(c)] = tbl[c];
+    MG_CUDA(cudaMalloc(&g->d_aa4096h, 4096));
+    MG_CUDA(cudaMemcpy(g->d_aa4096h, tblh, 4096, cudaMemcpyHostToDevice));
     g->device_bytes = words * 4 + (2 * n_contigs + 1) * 8 + 4096;
     // keep freed stream-ordered allocations cached: plans are created and destroyed per batch
     cudaMemPool_t pool;
@@ -126,6 +130,7 @@ extern "C" int mg_genome_destroy(mg_genome *g) {
     cudaFree(g->d_exc_count);
     cudaFree(g->d_stage);
     cudaFree(g->d_aa4096);
+    cudaFree(g->d_aa4096h);
     if (g->h_pin) cudaFreeHost(g->h_pin);
     delete g;
     return MG_OK;
