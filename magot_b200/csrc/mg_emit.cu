@@ -1,7 +1,7 @@
 // mg_emit.cu -- K2 (segmented interval gather + per-segment reverse complement + FASTA framing) and
-// K3 (codon translation of the spliced sequence).  Both are flat passes over OUTPUT bytes: one thread
-// owns one aligned 16-byte chunk of the final text and issues exactly one 16-byte streaming store, so
-// stores are perfectly coalesced and the load balance is independent of transcript/exon lengths.
+// K3 (codon translation of the spliced sequence).  Both are flat passes over OUTPUT bytes: one lane owns
+// one aligned chunk of the final text (32 bytes in K2, 16 in K3) and issues exactly one vector store,
+// so stores are perfectly coalesced and the load balance is independent of transcript/exon lengths.
 //
 //   K2 replaces ParentAnnotation.get_fasta seq_type="nucleotide" (genome.py:687-710),
 //      BaseAnnotation.get_seq (genome.py:603-608) and Sequence.reverse_compliment (genome.py:784-793).
@@ -11,20 +11,16 @@
 // Algorithmic HBM bytes: K2 = 0.5 B/base packed read + 1 B/base text written (+ tables);
 // K3 = 0.5 B/base read + 1/3 B/base written.  No dense contraction exists -> no tensor cores.
 //
-// How the kernels got here (ncu evidence under profiles/):
-//   r1a  first version: 16 bytes/thread, per-chunk binary search, per-piece shifting, reverse complement in
-//        registers.  Issue-bound: ~520 (K2) / ~1900 (K3) warp instructions per 32 chunks, 17 of 32 lanes
-//        active, DRAM at 20 % -- nowhere near the HBM roofline the algorithm allows.
-//   r1b  tile-relative 32-bit tables in shared memory, position-aligned loads, 64-byte-unit lookup table:
-//        ~370 instructions per 32 chunks; what was left was divergence (second piece of a chunk executed by
-//        2 lanes, literal bytes by 1 lane) and the strand branch.
-//   r1c  (this file) * the genome keeps a second, reverse-complemented plane, so a '-' interval is a plain
-//        forward read: no strand branch, no register reversal (mg_common.cuh);
-//        * the first two GENOME pieces of every chunk are handled branch-free by all lanes (literal and
-//          clamped-away empty pieces are skipped by flag: at most two sit between two genome pieces in the
-//          common case); anything else in 16 bytes is rare and takes a loop;
-//        * literal bytes (">ID\n", "\n") are not touched here at all: a tiny second kernel writes them
-//          afterwards, one thread per record.
+// How the kernels got here (ncu evidence under profiles/, A/B numbers in DESIGN.md section 5):
+//   r1a  16 bytes/lane, per-chunk binary search, reverse complement in registers: issue-bound, 17 of 32 lanes active.
+//   r1c  the genome keeps a second, reverse-complemented plane, so a '-' interval is a plain forward read (mg_common.cuh);
+//        tile-relative tables in shared memory; the first two GENOME pieces of a chunk are handled branch-free.
+//   r1j  32 bytes/lane with 256-bit stores, 32 KB tiles.
+//   r1u  loads with .L2::64B (L2 otherwise fills whole 128-byte lines for ~96-byte pieces), staging cut to ~14 KB so that
+//        8 CTAs are resident and most of the SM's 256 KB stays L1, FASTA framing written by the same CTA after a barrier
+//        (no lane ever branches on framing, no second kernel), text sizes read from the device (mg_plan_prepare_async).
+//   K3   the 48-nibble codon window is filled by a loop over the record's pieces (one one-sided mask each); the codon
+//        table sits in shared memory in an order that makes a lookup one wavefront (mg_aa_slot).
 #include <algorithm>
 #include "mg_common.cuh"
 #include "mg_gather.cuh"
