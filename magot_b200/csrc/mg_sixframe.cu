@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
     __shared__ TileInfo ti;
     __shared__ int64_t s_warp[SIX_THREADS / 32];
     __shared__ int s_wlast[6][SIX_THREADS / 32];     // per-warp max of `last stop in thread`
-    __shared__ int64_t s_wprev[6][SIX_THREADS / 32]; // last stop of the stream before each warp (contig offset, -1 = none)
+    __shared__ int64_t s_carry[6];                   // last stop of each stream before the tile (contig offset, -1 = none)
     __shared__ int64_t s_tile;
     __shared__ long long s_base;
     if (threadIdx.x == 0) {
@@ -537,21 +537,45 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
         ex_local[s] = ex;
     }
     __syncthreads();
-    if (wid < 6) {                                    // warp s: publish the tile's last stop of stream s, look back for the carry
-        const int s = wid;
-        volatile unsigned long long *st = look + 1 + (int64_t)s * n_tiles;
-        // exclusive running max over the CTA's warps (lanes 0..7 hold one warp each)
-        int inc = lane < SIX_THREADS / 32 ? s_wlast[s][lane] : -1;
+    // Every warp: last stop of each stream in the warps before it (one 16-lane max-scan per stream, no barrier), so that only
+    // the few threads in front of a stream's first stop in the tile depend on the carry from earlier tiles.
+    constexpr int NW = SIX_THREADS / 32;
+    int64_t prev[6];                                  // contig offset of the last stop of the stream before this thread, -1 = none
+    unsigned int need = 0;                            // streams whose prev is the carry (not known yet)
+    int my_agg = -1;                                  // warp s < 6: the tile's last stop of stream s
 #pragma unroll
-        for (int d = 1; d < SIX_THREADS / 32; d <<= 1) {
+    for (int s = 0; s < 6; s++) {
+        int inc = lane < NW ? s_wlast[s][lane] : -1;
+#pragma unroll
+        for (int d = 1; d < NW; d <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d && t > inc) inc = t;
         }
-        const int agg = __shfl_sync(0xffffffffu, inc, SIX_THREADS / 32 - 1);
-        int exw = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) exw = -1;
-        const unsigned long long own = agg >= 0 ? (unsigned long long)(ti.gb + tile0 + agg + 1) : 0ull;
-        if (lane == 0) st[tile] = (agg >= 0 || tile == 0) ? (SIX_LOOK_PREFIX | own) : SIX_LOOK_SUM;
+        const int exw = __shfl_sync(0xffffffffu, inc, wid ? wid - 1 : 0);
+        const int agg = __shfl_sync(0xffffffffu, inc, NW - 1);
+        if (s == wid) my_agg = agg;
+        if (ex_local[s] >= 0) prev[s] = tile0 + ex_local[s];
+        else if (wid && exw >= 0) prev[s] = tile0 + exw;
+        else { prev[s] = -1; need |= 1u << s; }
+    }
+    // publish the tile's own last stops at once: the successor's look-back finds them while this tile is still counting
+    if (wid < 6 && lane == 0) {
+        volatile unsigned long long *st = look + 1 + (int64_t)wid * n_tiles;
+        const unsigned long long own = my_agg >= 0 ? (unsigned long long)(ti.gb + tile0 + my_agg + 1) : 0ull;
+        st[tile] = (my_agg >= 0 || tile == 0) ? (SIX_LOOK_PREFIX | own) : SIX_LOOK_SUM;
+    }
+    int my_cnt[6];
+    int mine = 0;
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        my_cnt[s] = (active && !((need >> s) & 1u))
+                        ? enumerate_stream<0>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, fl[s])
+                        : 0;
+        mine += my_cnt[s];
+    }
+    if (wid < 6) {                                    // warp s: look back for the carry of stream s (by now usually published)
+        const int s = wid;
+        volatile unsigned long long *st = look + 1 + (int64_t)s * n_tiles;
         unsigned long long best = 0;                  // 1 + last stop before this tile, 0 = none
         int64_t j = tile - 1 - lane;
         while (true) {
@@ -565,29 +589,28 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
             j -= 32;
         }
         const int64_t cg = (int64_t)best - 1;         // global base index; < gb: a stop of another contig
-        if (lane < SIX_THREADS / 32) s_wprev[s][lane] = exw >= 0 ? tile0 + exw : (cg >= ti.gb ? cg - ti.gb : -1);
         if (lane == 0) {
+            s_carry[s] = cg >= ti.gb ? cg - ti.gb : -1;
             carry_out[(int64_t)s * n_tiles + tile] = cg;
-            if (agg < 0 && tile > 0) st[tile] = SIX_LOOK_PREFIX | best;
+            if (my_agg < 0 && tile > 0) st[tile] = SIX_LOOK_PREFIX | best;
         }
     }
     __syncthreads();
-    int64_t prev[6];                                  // contig offset of the last stop of the stream before this thread, or -1
+    if (need && active) {                             // the threads in front of the first stop of a stream
 #pragma unroll
-    for (int s = 0; s < 6; s++) prev[s] = ex_local[s] >= 0 ? tile0 + ex_local[s] : s_wprev[s][wid];
-    int my_cnt[6];
-    int mine = 0;
-#pragma unroll
-    for (int s = 0; s < 6; s++) {
-        my_cnt[s] = active ? enumerate_stream<0>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, fl[s]) : 0;
-        mine += my_cnt[s];
+        for (int s = 0; s < 6; s++) {
+            if (!((need >> s) & 1u)) continue;
+            prev[s] = s_carry[s];
+            my_cnt[s] = enumerate_stream<0>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, fl[s]);
+            mine += my_cnt[s];
+        }
     }
     int tot[6], before[6], excl[6];                   // kept ORFs of the tile per stream; of the streams before s; of lower threads
     int run = 0;
     if (min_aa >= 16) {
         // a thread keeps at most two ORFs per stream (its first stop, the contig end): ranks from two ballots per stream and
         // the per-warp totals, one barrier; only the rare threads that hold an ORF read the totals back
-        __shared__ int s_wcnt[6][SIX_THREADS / 32];
+        __shared__ int s_wcnt[6][NW];
         const unsigned int lt = (1u << lane) - 1u;
         int ex_w[6];
 #pragma unroll
@@ -597,32 +620,23 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
             if (lane == 0) s_wcnt[s][wid] = __popc(b1) + __popc(b2);
         }
         __syncthreads();
-        if (mine == 0 && threadIdx.x >= 6) return;
+        if (threadIdx.x < 6) {
+            int t = 0;
 #pragma unroll
-        for (int s = 0; s < 6; s++) {
-            int t = 0, e = 0;
-#pragma unroll
-            for (int w = 0; w < SIX_THREADS / 32; w++) {
-                const int c = s_wcnt[s][w];
-                t += c;
-                if (w < wid) e += c;
-            }
-            tot[s] = t;
-            excl[s] = e + ex_w[s];
-            before[s] = run;
-            run += t;
+            for (int w = 0; w < NW; w++) t += s_wcnt[threadIdx.x][w];
+            cnt[layout_index(ti, tile_base, contig_lo, threadIdx.x)] = t;
         }
-        if (threadIdx.x < 6) cnt[layout_index(ti, tile_base, contig_lo, threadIdx.x)] = tot[threadIdx.x];
-        if (run == 0 || mine == 0) return;
-        // the tile's slice of the hit list: claimed once, by the lowest thread that holds an ORF, and found by the others
-        // through shared memory is not possible after the early return above, so every holder claims for its own ORFs
+        if (mine == 0) return;
+        // every holder claims room in the hit list for its own ORFs (their order in the list does not matter)
         const long long base = (long long)atomicAdd(hit_count, (unsigned long long)mine);
         if (base + mine > hit_cap) return;            // overflow: the host falls back to the two-pass emit
         int off = 0;
 #pragma unroll
         for (int s = 0; s < 6; s++) {
             if (my_cnt[s] == 0) continue;
-            enumerate_stream<2>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, base + off, excl[s], nullptr, nullptr, nullptr,
+            int e = ex_w[s];                          // kept ORFs of the stream in lower threads of the tile
+            for (int w = 0; w < wid; w++) e += s_wcnt[s][w];
+            enumerate_stream<2>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, base + off, e, nullptr, nullptr, nullptr,
                                 hits, (int32_t)tile, fl[s]);
             off += my_cnt[s];
         }
