@@ -534,8 +534,8 @@ def gpu_arm(args):
     ach = (ab_cds + ab_exon) / ((nuc_ms_cds + nuc_ms_exon) * 1e-3) / 1e9
     roofline = {"kernel": "k_emit_nuc (K2 splice + per-segment RC + FASTA framing)", "bound": "hbm", "achieved": round(ach, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": 599e6 if (GENOME_BP == 3_100_000_000 and N_TX == 200_000) else None,
-                "traffic_source": "dram__bytes_read+write per launch, mean of the CDS (255+214 MB) and exon (378+350 MB) launches, ncu --set full, profiles/r1u_emit_plan_raw.csv",
+                "traffic": 587e6 if (GENOME_BP == 3_100_000_000 and N_TX == 200_000) else None,
+                "traffic_source": "dram__bytes_read+write per launch, mean of the CDS (254+206 MB) and exon (377+337 MB) launches, ncu --set full, profiles/r1x_emit_plan_raw.csv",
                 "peak_source": peak_src,
                 "frac_of_nominal_8TBs": round(ach / 8000.0, 4),
                 "launches_per_step": 2, "avg_launch_ms": round((nuc_ms_cds + nuc_ms_exon) / 2, 4),
