@@ -471,17 +471,22 @@ def gpu_arm(args):
     six = None
     if not args.no_sixframe:
         try:
-            # contigs are independent: each rank scans a contiguous, length-balanced range of contigs (strong scaling,
-            # no exchange step); time = max over ranks, ORFs and residues summed
-            cb = engine.shard_bounds(np.array([l for _, l in layout], dtype=np.int64), world)
-            c_lo, c_hi = int(cb[rank]), int(cb[rank + 1])
-            my_bp = sum(l for _, l in layout[c_lo:c_hi])
+            # contigs are independent: each rank scans its LPT share of the contigs (longest first, each to the least loaded
+            # GPU; strong scaling, no exchange step); time = max over ranks, ORFs and residues summed
+            from magot_b200 import orfs as _orfs
+            shard = _orfs.lpt_shards([l for _, l in layout], world)[rank]
+            ids = np.ascontiguousarray(shard, dtype=np.int64)
+            my_bp = sum(layout[c][1] for c in shard)
             n_orf, n_bytes = ctypes.c_int64(0), ctypes.c_int64(0)
-            _lib.check(lib.mg_sixframe_count(g.handle, c_lo, c_hi, 100, ctypes.byref(n_orf), ctypes.byref(n_bytes), sp))   # warm-up
+
+            def six_count():
+                _lib.check(lib.mg_sixframe_count_list(g.handle, ids.size, ctypes.c_void_p(ids.ctypes.data), 100, ctypes.byref(n_orf),
+                                                      ctypes.byref(n_bytes), sp))
+            six_count()                                  # warm-up
             torch.cuda.synchronize()
             a0, a1, a2 = ev(), ev(), ev()
             a0.record(stream)
-            _lib.check(lib.mg_sixframe_count(g.handle, c_lo, c_hi, 100, ctypes.byref(n_orf), ctypes.byref(n_bytes), sp))
+            six_count()
             a1.record(stream)
             aa_dev = torch.empty((n_bytes.value + 31) // 32 * 32 + 32, dtype=torch.uint8, device=dev)
             a1b = ev()
@@ -499,7 +504,7 @@ def gpu_arm(args):
                 dist.all_reduce(ts, op=dist.ReduceOp.SUM)
                 tot_orf, tot_bytes = [int(x) for x in ts.tolist()]
             six = {"workload": "config 5: six-frame translation + ORF scan of the whole genome, min ORF 100 aa (reference semantics of Sequence.get_orfs)",
-                   "sharding": "contigs split into %d contiguous length-balanced ranges, one per GPU; largest shard %.3f Gbp; strong scaling, "
+                   "sharding": "contigs assigned to %d GPU(s) longest-first to the least loaded (LPT); largest share %.3f Gbp; strong scaling, "
                                "times are the max over ranks" % (world, max_bp / 1e9),
                    "orfs": tot_orf, "aa_bytes": tot_bytes, "scan_ms": round(t_scan, 3), "emit_ms": round(t_emit, 3),
                    "genome_Gbp_per_s": round(GENOME_BP / ((t_scan + t_emit) * 1e-3) / 1e9, 1),

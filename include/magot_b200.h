@@ -154,6 +154,10 @@ typedef struct {
 } mg_orf;
 int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig_hi, int64_t min_aa,
                       int64_t *n_orf, int64_t *n_bytes, void *stream);
+/* The same for a LIST of contigs in any order (e.g. one GPU's share of a length-balanced split): ORFs are emitted contig by
+ * contig in list order.                                                                        */
+int mg_sixframe_count_list(mg_genome *g, int64_t n_list, const int64_t *contig_ids, int64_t min_aa,
+                           int64_t *n_orf, int64_t *n_bytes, void *stream);
 /* Emits the result of the preceding mg_sixframe_count on this genome handle.  aa_out_host gets
  * n_bytes residues (ORFs back to back, no separators), recs_host n_orf records.  Either may
  * be NULL.  *_device variant leaves the residues in `aa_out_dev` (16-byte aligned, n_bytes

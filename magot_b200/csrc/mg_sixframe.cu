@@ -37,7 +37,8 @@ struct SixHit {                                      // one kept ORF found by th
 };
 
 struct mg_sixframe_state {
-    int64_t contig_lo = 0, contig_hi = 0, min_aa = 0;
+    int64_t min_aa = 0;
+    int32_t *d_cid = nullptr;                        // [nc] the contigs scanned, in output order
     int64_t n_tiles = 0;
     std::vector<int64_t> h_tile_base;                // [n_contig_in_range + 1], starts at 0
     int64_t *d_tile_base = nullptr;
@@ -70,11 +71,11 @@ struct mg_sixframe_state {
 // ---- per-stream geometry ------------------------------------------------------------------------------
 // stream index sidx = 2*frame + (plus ? 1 : 0): reference order is sidx ascending.
 __global__ void k_six_streams(const uint32_t *__restrict__ packed, const int64_t *__restrict__ contig_len,
-                              const int64_t *__restrict__ contig_base, int64_t contig_lo, int64_t nc,
+                              const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cid, int64_t nc,
                               int32_t *__restrict__ cs_out, int64_t *__restrict__ m_out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= nc * 6) return;
-    const int64_t c = contig_lo + i / 6;
+    const int64_t c = cid[i / 6];
     const int sidx = (int)(i % 6), f = sidx >> 1, plus = sidx & 1;
     const int64_t L = contig_len[c], gb = contig_base[c];
     int cs = 0;
@@ -199,7 +200,10 @@ __device__ __forceinline__ void stream_first_last48(uint64_t p_plus, uint64_t p_
 }
 
 struct TileInfo {
-    int64_t c, k, gb, L, Tc;                         // contig, tile index in contig, global base, length, tiles in contig
+    int64_t c, ci, k, gb, L, Tc;                     // contig, its index in the scanned list, tile index in contig, global base, length, tiles in contig
+    int64_t vb;                                      // scan coordinate of the contig's first base: tile_base[ci] * SIX_TILE.  Stops are
+                                                     // carried between tiles in this coordinate (it ascends with the tile index
+                                                     // whatever the order of the contig list; a genome index would not)
     int Lm3;
     int32_t cs[6];
     int64_t m[6];
@@ -219,11 +223,11 @@ __global__ void __launch_bounds__(256) k_six_tile_contig(const int64_t *__restri
 }
 
 // tile_info with the contig index already known (k_six_tile_contig): independent loads, no search
-__device__ __forceinline__ void tile_info_at(int64_t tile, int64_t lo, const int64_t *__restrict__ tile_base, int64_t contig_lo,
+__device__ __forceinline__ void tile_info_at(int64_t tile, int64_t lo, const int64_t *__restrict__ tile_base, const int32_t *__restrict__ cid,
                                              const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base,
                                              const int32_t *__restrict__ cs, const int64_t *__restrict__ m, struct TileInfo &ti);
 
-__device__ __forceinline__ void tile_info(int64_t tile, const int64_t *__restrict__ tile_base, int64_t nc, int64_t contig_lo,
+__device__ __forceinline__ void tile_info(int64_t tile, const int64_t *__restrict__ tile_base, int64_t nc, const int32_t *__restrict__ cid,
                                           const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base,
                                           const int32_t *__restrict__ cs, const int64_t *__restrict__ m, TileInfo &ti) {
     int64_t lo = 0, hi = nc;                          // largest ci with tile_base[ci] <= tile
@@ -232,10 +236,12 @@ __device__ __forceinline__ void tile_info(int64_t tile, const int64_t *__restric
         if (tile_base[mid] <= tile) lo = mid; else hi = mid;
     }
     // contigs without tiles (L == 0) share a tile_base value with their successor: take the last one
-    ti.c = contig_lo + lo;
+    ti.c = cid[lo];
+    ti.ci = lo;
     ti.k = tile - tile_base[lo];
     ti.Tc = tile_base[lo + 1] - tile_base[lo];
     ti.gb = contig_base[ti.c];
+    ti.vb = tile_base[lo] * SIX_TILE;
     ti.L = contig_len[ti.c];
     ti.Lm3 = (int)(ti.L % 3);
 #pragma unroll
@@ -245,13 +251,15 @@ __device__ __forceinline__ void tile_info(int64_t tile, const int64_t *__restric
     }
 }
 
-__device__ __forceinline__ void tile_info_at(int64_t tile, int64_t lo, const int64_t *__restrict__ tile_base, int64_t contig_lo,
+__device__ __forceinline__ void tile_info_at(int64_t tile, int64_t lo, const int64_t *__restrict__ tile_base, const int32_t *__restrict__ cid,
                                              const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base,
                                              const int32_t *__restrict__ cs, const int64_t *__restrict__ m, TileInfo &ti) {
-    ti.c = contig_lo + lo;
+    ti.c = cid[lo];
+    ti.ci = lo;
     ti.k = tile - tile_base[lo];
     ti.Tc = tile_base[lo + 1] - tile_base[lo];
     ti.gb = contig_base[ti.c];
+    ti.vb = tile_base[lo] * SIX_TILE;
     ti.L = contig_len[ti.c];
     ti.Lm3 = (int)(ti.L % 3);
 #pragma unroll
@@ -280,9 +288,9 @@ __device__ __forceinline__ void orf_of(int plus, int64_t L, int cs, int64_t m, i
     }
 }
 
-__device__ __forceinline__ int64_t layout_index(const TileInfo &ti, const int64_t *__restrict__ tile_base, int64_t contig_lo, int s) {
+__device__ __forceinline__ int64_t layout_index(const TileInfo &ti, const int64_t *__restrict__ tile_base, int s) {
     // output order: contig, then stream (reference order), then tiles ascending ('+') or descending ('-')
-    return tile_base[ti.c - contig_lo] * 6 + (int64_t)s * ti.Tc + ((s & 1) ? ti.k : ti.Tc - 1 - ti.k);
+    return tile_base[ti.ci] * 6 + (int64_t)s * ti.Tc + ((s & 1) ? ti.k : ti.Tc - 1 - ti.k);
 }
 
 // Enumerate the ORFs this thread owns in stream s (each ORF belongs to its higher stop).  WRITE == false: count.
@@ -388,7 +396,7 @@ __device__ __forceinline__ int64_t block_incl_sum(int64_t v, int64_t *s_warp, in
 
 template <bool EMIT>
 __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
-    const uint32_t *__restrict__ packed, const int64_t *__restrict__ tile_base, int64_t nc, int64_t contig_lo,
+    const uint32_t *__restrict__ packed, const int64_t *__restrict__ tile_base, int64_t nc, const int32_t *__restrict__ cid,
     const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
     const int64_t *__restrict__ m, int64_t n_tiles, const int64_t *__restrict__ carry, int64_t min_aa, int64_t two_T,
     int32_t *__restrict__ cnt, const int64_t *__restrict__ cnt_off, mg_orf *__restrict__ recs, int32_t *__restrict__ lens,
@@ -397,7 +405,7 @@ __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
     __shared__ int s_cnt[6];
     __shared__ int64_t s_warp[SIX_THREADS / 32];
     __shared__ int s_wlast[6][SIX_THREADS / 32];     // per-warp max of `last stop in thread`
-    if (threadIdx.x == 0) tile_info(blockIdx.x, tile_base, nc, contig_lo, contig_len, contig_base, cs, m, ti);
+    if (threadIdx.x == 0) tile_info(blockIdx.x, tile_base, nc, cid, contig_len, contig_base, cs, m, ti);
     if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const int64_t tile0 = ti.k * SIX_TILE;
@@ -434,8 +442,8 @@ __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
         for (int w = 0; w < wid; w++) ex = max(ex, s_wlast[s][w]);
         if (ex >= 0) prev[s] = tile0 + ex;            // contig offset
         else {
-            const int64_t cg = carry[(int64_t)s * n_tiles + blockIdx.x];   // global base index; < gb: other contig
-            prev[s] = (cg >= ti.gb) ? cg - ti.gb : -1;
+            const int64_t cg = carry[(int64_t)s * n_tiles + blockIdx.x];   // scan coordinate; < vb: other contig
+            prev[s] = (cg >= ti.vb) ? cg - ti.vb : -1;
         }
     }
 
@@ -453,7 +461,7 @@ __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
             if (lane == 0 && c) atomicAdd(&s_cnt[s], c);
         }
         __syncthreads();
-        if (threadIdx.x < 6) cnt[layout_index(ti, tile_base, contig_lo, threadIdx.x)] = s_cnt[threadIdx.x];
+        if (threadIdx.x < 6) cnt[layout_index(ti, tile_base, threadIdx.x)] = s_cnt[threadIdx.x];
     } else {
         // ranks inside the tile: block prefix sums of the per-thread counts, three 21-bit fields per word
         const int64_t pk0 = (int64_t)my_cnt[0] | ((int64_t)my_cnt[1] << 21) | ((int64_t)my_cnt[2] << 42);
@@ -470,7 +478,7 @@ __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
                 const int64_t tot = ((s < 3 ? tot0 : tot1) >> sh) & 0x1FFFFF;
                 // '+': ascending, my first ORF has rank = exclusive prefix; '-': descending, ranks count from the top
                 const int64_t rank0 = (s & 1) ? inc - my_cnt[s] : tot - inc;
-                const int64_t slot0 = cnt_off[layout_index(ti, tile_base, contig_lo, s)] + rank0;
+                const int64_t slot0 = cnt_off[layout_index(ti, tile_base, s)] + rank0;
                 enumerate_stream<1>(ti, sm, s, x0, prev[s], is_end_thread, min_aa, two_T, slot0, my_cnt[s], recs, lens, srcs);
             }
         }
@@ -492,7 +500,7 @@ __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
 #define SIX_LOOK_MASK (3ull << 62)
 
 __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
-    const uint32_t *__restrict__ packed, const int64_t *__restrict__ tile_base, int64_t nc, int64_t contig_lo,
+    const uint32_t *__restrict__ packed, const int64_t *__restrict__ tile_base, int64_t nc, const int32_t *__restrict__ cid,
     const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
     const int64_t *__restrict__ m, const int32_t *__restrict__ tile_contig, int64_t n_tiles, unsigned long long *look, int64_t *__restrict__ carry_out, int64_t min_aa,
     int64_t two_T, int32_t *__restrict__ cnt, SixHit *__restrict__ hits, int64_t hit_cap, unsigned long long *hit_count) {
@@ -505,7 +513,7 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
     if (threadIdx.x == 0) {
         const int64_t t = (int64_t)atomicAdd(look, 1ull);              // tiles in launch order: look-back never waits on a
         s_tile = t;                                                      // tile that has not started
-        tile_info_at(t, tile_contig[t], tile_base, contig_lo, contig_len, contig_base, cs, m, ti);
+        tile_info_at(t, tile_contig[t], tile_base, cid, contig_len, contig_base, cs, m, ti);
     }
     __syncthreads();
     const int64_t tile = s_tile;
@@ -561,7 +569,7 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
     // publish the tile's own last stops at once: the successor's look-back finds them while this tile is still counting
     if (wid < 6 && lane == 0) {
         volatile unsigned long long *st = look + 1 + (int64_t)wid * n_tiles;
-        const unsigned long long own = my_agg >= 0 ? (unsigned long long)(ti.gb + tile0 + my_agg + 1) : 0ull;
+        const unsigned long long own = my_agg >= 0 ? (unsigned long long)(ti.vb + tile0 + my_agg + 1) : 0ull;
         st[tile] = (my_agg >= 0 || tile == 0) ? (SIX_LOOK_PREFIX | own) : SIX_LOOK_SUM;
     }
     int my_cnt[6];
@@ -588,9 +596,9 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
             }
             j -= 32;
         }
-        const int64_t cg = (int64_t)best - 1;         // global base index; < gb: a stop of another contig
+        const int64_t cg = (int64_t)best - 1;         // scan coordinate; < vb: a stop of another contig
         if (lane == 0) {
-            s_carry[s] = cg >= ti.gb ? cg - ti.gb : -1;
+            s_carry[s] = cg >= ti.vb ? cg - ti.vb : -1;
             carry_out[(int64_t)s * n_tiles + tile] = cg;
             if (my_agg < 0 && tile > 0) st[tile] = SIX_LOOK_PREFIX | best;
         }
@@ -624,7 +632,7 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
             int t = 0;
 #pragma unroll
             for (int w = 0; w < NW; w++) t += s_wcnt[threadIdx.x][w];
-            cnt[layout_index(ti, tile_base, contig_lo, threadIdx.x)] = t;
+            cnt[layout_index(ti, tile_base, threadIdx.x)] = t;
         }
         if (mine == 0) return;
         // every holder claims room in the hit list for its own ORFs (their order in the list does not matter)
@@ -644,7 +652,7 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
     }
     const int any = __syncthreads_or(mine);
     if (!any) {
-        if (threadIdx.x < 6) cnt[layout_index(ti, tile_base, contig_lo, threadIdx.x)] = 0;
+        if (threadIdx.x < 6) cnt[layout_index(ti, tile_base, threadIdx.x)] = 0;
         return;
     }
     // general case: block prefix sums of the per-thread counts, three 21-bit fields per word
@@ -660,7 +668,7 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
         before[s] = run;
         run += tot[s];
     }
-    if (threadIdx.x < 6) cnt[layout_index(ti, tile_base, contig_lo, threadIdx.x)] = tot[threadIdx.x];
+    if (threadIdx.x < 6) cnt[layout_index(ti, tile_base, threadIdx.x)] = tot[threadIdx.x];
     if (threadIdx.x == 0) s_base = (long long)atomicAdd(hit_count, (unsigned long long)run);
     __syncthreads();
     const int64_t base = s_base;
@@ -675,7 +683,7 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
 
 // thread per hit: reference-order slot of the ORF and its record
 __global__ void __launch_bounds__(256) k_six_place(const SixHit *__restrict__ hits, int64_t n_hit, const int64_t *__restrict__ tile_base,
-                                                   int64_t nc, int64_t contig_lo, const int64_t *__restrict__ contig_len,
+                                                   int64_t nc, const int32_t *__restrict__ cid, const int64_t *__restrict__ contig_len,
                                                    const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
                                                    const int64_t *__restrict__ m, const int64_t *__restrict__ cnt_off, int64_t two_T,
                                                    mg_orf *__restrict__ recs, int32_t *__restrict__ lens, int64_t *__restrict__ srcs) {
@@ -683,9 +691,9 @@ __global__ void __launch_bounds__(256) k_six_place(const SixHit *__restrict__ hi
     if (i >= n_hit) return;
     const SixHit h = hits[i];
     TileInfo ti;
-    tile_info(h.tile, tile_base, nc, contig_lo, contig_len, contig_base, cs, m, ti);
+    tile_info(h.tile, tile_base, nc, cid, contig_len, contig_base, cs, m, ti);
     const int s = h.s, plus = s & 1;
-    const int64_t li = layout_index(ti, tile_base, contig_lo, s);
+    const int64_t li = layout_index(ti, tile_base, s);
     const int64_t o0 = cnt_off[li], n = cnt_off[li + 1] - o0;
     const int64_t slot = o0 + (plus ? h.rank : n - 1 - h.rank);
     int64_t st, ln;
@@ -801,25 +809,27 @@ static int six_alloc(mg_sixframe_state *s, T **p, int64_t n) {
     return MG_OK;
 }
 
-extern "C" int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig_hi, int64_t min_aa, int64_t *n_orf,
-                                 int64_t *n_bytes, void *stream) {
+// contigs given as a LIST (any order, e.g. the LPT share of one GPU): ORFs come out contig by contig in list order
+extern "C" int mg_sixframe_count_list(mg_genome *g, int64_t n_list, const int64_t *contig_ids, int64_t min_aa, int64_t *n_orf,
+                                      int64_t *n_bytes, void *stream) {
     MG_REQUIRE(g != nullptr, "genome handle is NULL");
     MG_REQUIRE(g->finalized, "mg_genome_finalize has not been called");
-    MG_REQUIRE(contig_lo >= 0 && contig_lo <= contig_hi && contig_hi <= g->n_contigs, "contig range out of bounds");
+    MG_REQUIRE(n_list >= 0 && (n_list == 0 || contig_ids != nullptr), "bad contig list");
     MG_REQUIRE(min_aa >= 0, "min_aa must be >= 0");
+    for (int64_t i = 0; i < n_list; i++) MG_REQUIRE(contig_ids[i] >= 0 && contig_ids[i] < g->n_contigs, "contig index out of range");
     MG_CUDA(cudaSetDevice(g->device));
     cudaStream_t st = (cudaStream_t)stream;
     mg_sixframe_free(g);
     mg_sixframe_state *s = new mg_sixframe_state();
     g->six = s;
     s->stream = st;
-    s->contig_lo = contig_lo;
-    s->contig_hi = contig_hi;
     s->min_aa = min_aa;
-    const int64_t nc = contig_hi - contig_lo;
+    const int64_t nc = n_list;
+    std::vector<int32_t> h_cid(nc);
+    for (int64_t i = 0; i < nc; i++) h_cid[i] = (int32_t)contig_ids[i];
     s->h_tile_base.assign(nc + 1, 0);
     for (int64_t c = 0; c < nc; c++) {
-        const int64_t L = g->h_contig_len[contig_lo + c];
+        const int64_t L = g->h_contig_len[h_cid[c]];
         MG_REQUIRE(L < (1ll << 31), "contigs of 2^31 bases or more are not supported by the ORF scan");
         s->h_tile_base[c + 1] = s->h_tile_base[c] + (L + SIX_TILE - 1) / SIX_TILE;
     }
@@ -832,6 +842,9 @@ extern "C" int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig
     if (s->n_tiles == 0) return MG_OK;
     int rc;
 #define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+    TRY(six_alloc(s, &s->d_cid, nc));
+    MG_CUDA(cudaMemcpyAsync(s->d_cid, h_cid.data(), nc * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    MG_CUDA(cudaStreamSynchronize(st));               // h_cid is a local
     TRY(six_alloc(s, &s->d_tile_base, nc + 1));
     MG_CUDA(cudaMemcpyAsync(s->d_tile_base, s->h_tile_base.data(), (nc + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     TRY(six_alloc(s, &s->d_cs, nc * 6));
@@ -845,12 +858,12 @@ extern "C" int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig
     if (const char *e = getenv("MG_SIX_HIT_CAP")) s->hit_cap = std::max<int64_t>(1, atoll(e));   // tests force the second pass
     TRY(six_alloc(s, &s->d_hits, s->hit_cap));
     MG_CUDA(cudaMemsetAsync(s->d_look, 0, (6 * s->n_tiles + 2) * sizeof(unsigned long long), st));
-    k_six_streams<<<(unsigned)((nc * 6 + 127) / 128), 128, 0, st>>>(g->d_packed, g->d_contig_len, g->d_contig_base, contig_lo, nc, s->d_cs, s->d_m);
+    k_six_streams<<<(unsigned)((nc * 6 + 127) / 128), 128, 0, st>>>(g->d_packed, g->d_contig_len, g->d_contig_base, s->d_cid, nc, s->d_cs, s->d_m);
     MG_LAUNCH_CHECK();
     TRY(six_alloc(s, &s->d_tile_contig, s->n_tiles));
     k_six_tile_contig<<<(unsigned)((s->n_tiles + 255) / 256), 256, 0, st>>>(s->d_tile_base, nc, s->n_tiles, s->d_tile_contig);
     MG_LAUNCH_CHECK();
-    k_six_scan<<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, contig_lo, g->d_contig_len, g->d_contig_base,
+    k_six_scan<<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, s->d_cid, g->d_contig_len, g->d_contig_base,
                                                               s->d_cs, s->d_m, s->d_tile_contig, s->n_tiles, s->d_look, s->d_carry, min_aa, 2 * g->total_bases,
                                                               s->d_cnt, s->d_hits, s->hit_cap, s->d_hit_count);
     MG_LAUNCH_CHECK();
@@ -865,11 +878,11 @@ extern "C" int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig
         TRY(six_alloc(s, &s->d_src, s->n_orf));
         TRY(six_alloc(s, &s->d_aa_off, s->n_orf + 1));
         if (s->n_orf <= s->hit_cap) {
-            k_six_place<<<(unsigned)((s->n_orf + 255) / 256), 256, 0, st>>>(s->d_hits, s->n_orf, s->d_tile_base, nc, contig_lo, g->d_contig_len,
+            k_six_place<<<(unsigned)((s->n_orf + 255) / 256), 256, 0, st>>>(s->d_hits, s->n_orf, s->d_tile_base, nc, s->d_cid, g->d_contig_len,
                                                                             g->d_contig_base, s->d_cs, s->d_m, s->d_cnt_off, 2 * g->total_bases,
                                                                             s->d_recs, s->d_len, s->d_src);
         } else {                                     // dense output (tiny min_aa): second pass over the genome
-            k_six_orfs<true><<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, contig_lo, g->d_contig_len,
+            k_six_orfs<true><<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, s->d_cid, g->d_contig_len,
                                                                           g->d_contig_base, s->d_cs, s->d_m, s->n_tiles, s->d_carry, min_aa,
                                                                           2 * g->total_bases, nullptr, s->d_cnt_off, s->d_recs, s->d_len, s->d_src);
         }
@@ -893,6 +906,15 @@ extern "C" int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig
     if (n_orf) *n_orf = s->n_orf;
     if (n_bytes) *n_bytes = s->n_bytes;
     return MG_OK;
+}
+
+extern "C" int mg_sixframe_count(mg_genome *g, int64_t contig_lo, int64_t contig_hi, int64_t min_aa, int64_t *n_orf,
+                                 int64_t *n_bytes, void *stream) {
+    MG_REQUIRE(g != nullptr, "genome handle is NULL");
+    MG_REQUIRE(contig_lo >= 0 && contig_lo <= contig_hi && contig_hi <= g->n_contigs, "contig range out of bounds");
+    std::vector<int64_t> ids(contig_hi - contig_lo);
+    for (int64_t i = 0; i < (int64_t)ids.size(); i++) ids[i] = contig_lo + i;
+    return mg_sixframe_count_list(g, (int64_t)ids.size(), ids.data(), min_aa, n_orf, n_bytes, stream);
 }
 
 extern "C" int mg_sixframe_emit_device(mg_genome *g, uint8_t *aa_out_dev, mg_orf *recs_dev, void *stream) {

@@ -462,6 +462,33 @@ def test_prepare_async_equals_prepare(mg):
     g.close()
 
 
+@pytest.mark.parametrize("min_aa", [0, 30])
+def test_sixframe_contig_list_any_order(mg, min_aa):
+    """mg_sixframe_count_list: contigs in arbitrary (descending, repeated) order -- the carry between tiles must not leak from a
+    contig that lies later in the genome into one that lies earlier; output = the per-contig results in list order."""
+    from magot_b200 import engine, orfs
+    rng = np.random.default_rng(900 + min_aa)
+    alpha = np.frombuffer(b"ACGTacgtNn", dtype=np.uint8)
+    contigs = [alpha[rng.integers(0, alpha.size, size=n)].tobytes() for n in (30000, 7, 60000, 24577, 0, 50001)]
+    g = engine.DeviceGenome([len(c) for c in contigs], device=0)
+    for i, c in enumerate(contigs):
+        g.pack(i, np.frombuffer(c, dtype=np.uint8))
+    g.finalize()
+    per = {}
+    for ci, c in enumerate(contigs):
+        a, r = coracle.sixframe(c, min_aa)
+        per[ci] = (a, [(int(x[0]), int(x[1]), int(x[2]), int(x[3])) for x in r])
+    for ids in ([5, 3, 2, 0], [2, 2, 1, 4, 0, 5, 3], [0, 1, 2, 3, 4, 5]):
+        recs, aa = orfs.sixframe_list(g, ids, min_aa)
+        assert aa == b"".join(per[c][0] for c in ids)
+        want = [(c,) + row for c in ids for row in per[c][1]]
+        got = [(int(r["contig"]), int(r["frame"]), int(r["minus"]), int(r["start"]), int(r["len"])) for r in recs]
+        assert got == want
+    shards = orfs.lpt_shards([len(c) for c in contigs], 3)
+    assert sorted(c for sh in shards for c in sh) == list(range(len(contigs)))
+    g.close()
+
+
 @pytest.mark.parametrize("min_aa", [0, 16])
 def test_sixframe_dense_output_second_pass(mg, min_aa, monkeypatch):
     """More kept ORFs than the scan pass's hit list holds: the records come from the second genome pass instead."""
