@@ -236,3 +236,19 @@ def test_aligner_readers_build_the_reference_object_model(kind):
     assert sorted(got) == sorted(want)
     for name in want:
         assert got[name] == want[name], name
+
+
+def test_lpt_contig_shards():
+    """Config-5 sharding rule: contigs longest-first to the least loaded GPU; every contig exactly once, ascending
+    inside a share, and -- for the human-scale layout -- the largest share within 3 % of the ideal 1/n."""
+    from magot_b200 import orfs
+    layout = synth.contig_layout("human", 3_100_000_000, 4)
+    lens = [l for _, l in layout]
+    for n in (1, 2, 4, 8):
+        shards = orfs.lpt_shards(lens, n)
+        assert len(shards) == n
+        assert sorted(c for sh in shards for c in sh) == list(range(len(lens)))
+        assert all(sh == sorted(sh) for sh in shards)
+        worst = max(sum(lens[c] for c in sh) for sh in shards)
+        assert worst <= 1.03 * sum(lens) / n, (n, worst)
+    assert orfs.lpt_shards([], 3) == [[], [], []]
