@@ -21,7 +21,12 @@
 #ifndef SIX_THREADS
 #define SIX_THREADS 512                              // 24576 bases per CTA: the per-tile prologue (ticket, tile info, look-back) is paid half as often (-12 %)
 #endif
-#define SIX_BPT 48                                   // bases per thread
+#define SIX_HALF 48                                  // bases per stop-mask computation (six_masks)
+#define SIX_HALVES 2
+#define SIX_BPT (SIX_HALF * SIX_HALVES)              // 96 bases per thread: the per-thread work that does not depend on the number
+                                                     // of bases (scans, ranks, ORF tests: about half of the instructions at 48
+                                                     // bases per thread) is paid half as often
+#define SIX_FAST_MIN_AA (SIX_BPT / 3)                // two stops of one stream inside a thread are closer than this many codons
 #define SIX_TILE (SIX_THREADS * SIX_BPT)             // bases per CTA (multiple of 3 and of 16)
 #ifndef SIX_SCAN_MINB
 #define SIX_SCAN_MINB 3                             // 42 registers, 48 resident warps per SM
@@ -162,26 +167,10 @@ __device__ __forceinline__ int stream_res(int sidx, int Lm3) {
     return (sidx & 1) ? rho : (Lm3 - rho + 3) % 3;
 }
 
-// first / last stop of stream in the thread (tile-local thread-relative position 0..47, or -1)
-__device__ __forceinline__ void stream_first_last(const SixMasks &s, int sidx, int Lm3, int &first, int &last) {
-    const int r = stream_res(sidx, Lm3);
-    const uint64_t *msk = (sidx & 1) ? s.pm : s.mm;
-    first = -1;
-    last = -1;
-#pragma unroll
-    for (int g = 0; g < 3; g++) {
-        const uint64_t x = msk[g] & res_mask((r - g + 3) % 3);
-        if (x) {
-            if (first < 0) first = 16 * g + ((__ffsll((long long)x) - 1) >> 2);
-            last = 16 * g + ((63 - __clzll((long long)x)) >> 2);
-        }
-    }
-}
-
-// ---- the same, from position-ordered masks ---------------------------------------------------------------------------
-// The nibble-spaced flags of one strand (3 x 64 bits) compressed to one bit per position (48 bits): first / last stop of
-// a stream are then one masked ffs / clz instead of three per stream.  (With the nibble-spaced masks this extraction was
-// 29 % of the scan kernel's instructions.)
+// ---- position-ordered stop masks --------------------------------------------------------------------------------------
+// The nibble-spaced flags of one strand (3 x 64 bits) are compressed to one bit per position (48 bits): first / last stop
+// of a stream are then one masked ffs / clz per half instead of three per stream on nibble-spaced words (that extraction
+// was 29 % of the scan kernel's instructions), and walking the stops of a stream is a plain bit loop.
 __device__ __forceinline__ uint32_t compress8(uint32_t x) {       // flags at bits 0, 4, .., 28 -> bits 0..7
     x = (x | (x >> 3)) & 0x03030303u;
     x = (x | (x >> 6)) & 0x000F000Fu;
@@ -193,11 +182,30 @@ __device__ __forceinline__ uint64_t pos48(const uint64_t m[3]) {
     const uint32_t hi = compress8((uint32_t)m[2]) | (compress8((uint32_t)(m[2] >> 32)) << 8);
     return ((uint64_t)hi << 32) | lo;
 }
-__device__ __forceinline__ void stream_first_last48(uint64_t p_plus, uint64_t p_minus, int sidx, int Lm3, int &first, int &last) {
-    const uint64_t x = ((sidx & 1) ? p_plus : p_minus) & (0x0000249249249249ull << stream_res(sidx, Lm3));
-    first = x ? __ffsll((long long)x) - 1 : -1;
-    last = x ? 63 - __clzll((long long)x) : -1;
+// stops of one thread's SIX_BPT positions, one bit per position: half h covers positions 48h .. 48h+47
+struct ThreadStops {
+    uint64_t p[SIX_HALVES], m[SIX_HALVES];           // plus / minus strand
+};
+// the stops of stream sidx (a residue class of one strand).  Both halves start at a multiple of 3, so one residue mask serves.
+__device__ __forceinline__ void stream_stops(const ThreadStops &ts, int sidx, int Lm3, uint64_t x[SIX_HALVES]) {
+    const uint64_t rm = 0x0000249249249249ull << stream_res(sidx, Lm3);
+#pragma unroll
+    for (int h = 0; h < SIX_HALVES; h++) x[h] = ((sidx & 1) ? ts.p[h] : ts.m[h]) & rm;
 }
+__device__ __forceinline__ void stops_first_last(const uint64_t x[SIX_HALVES], int &first, int &last) {
+    first = -1;
+    last = -1;
+#pragma unroll
+    for (int h = 0; h < SIX_HALVES; h++) {
+        if (x[h]) {
+            if (first < 0) first = SIX_HALF * h + __ffsll((long long)x[h]) - 1;
+            last = SIX_HALF * h + 63 - __clzll((long long)x[h]);
+        }
+    }
+}
+
+struct TileInfo;
+__device__ __forceinline__ void thread_stops(const uint32_t *__restrict__ packed, const TileInfo &ti, int64_t x0, ThreadStops &ts);
 
 struct TileInfo {
     int64_t c, ci, k, gb, L, Tc;                     // contig, its index in the scanned list, tile index in contig, global base, length, tiles in contig
@@ -269,6 +277,22 @@ __device__ __forceinline__ void tile_info_at(int64_t tile, int64_t lo, const int
     }
 }
 
+__device__ __forceinline__ void thread_stops(const uint32_t *__restrict__ packed, const TileInfo &ti, int64_t x0, ThreadStops &ts) {
+#pragma unroll
+    for (int h = 0; h < SIX_HALVES; h++) {
+        const int64_t xh = x0 + SIX_HALF * h;
+        if (xh < ti.L) {
+            SixMasks sm;
+            six_masks(packed, ti.gb, ti.L, xh, ti.cs, sm);
+            ts.p[h] = pos48(sm.pm);
+            ts.m[h] = pos48(sm.mm);
+        } else {
+            ts.p[h] = 0;
+            ts.m[h] = 0;
+        }
+    }
+}
+
 // ---- ORF enumeration shared by the single-pass scan (k_six_scan) and the dense-output second pass (k_six_orfs) ----
 // ORF between a lower stop xl and a higher stop xh of one stream (contig offsets; !xl_real = virtual stop at
 // the low end of the contig, !xh_real = virtual stop at the high end).  Residue index of a stop at x:
@@ -297,7 +321,7 @@ __device__ __forceinline__ int64_t layout_index(const TileInfo &ti, const int64_
 // WRITE == true: k-th kept ORF (ascending position) goes to slot0 + k ('+') or slot0 + (n_mine-1-k) ('-').
 // WRITE == 2: k-th kept ORF goes to hits[slot0 + k] with rank n_mine + k (n_mine = kept ORFs of lower threads).
 template <int WRITE>
-__device__ __forceinline__ int enumerate_stream(const TileInfo &ti, const SixMasks &sm, int s, int64_t x0, int64_t prev,
+__device__ __forceinline__ int enumerate_stream(const TileInfo &ti, const ThreadStops &ts, int s, int64_t x0, int64_t prev,
                                                 bool is_end_thread, int64_t min_aa, int64_t two_T, int64_t slot0, int n_mine,
                                                 mg_orf *__restrict__ recs, int32_t *__restrict__ lens, int64_t *__restrict__ srcs,
                                                 SixHit *__restrict__ hits = nullptr, int32_t tile = 0, int fl = -2) {
@@ -337,12 +361,13 @@ __device__ __forceinline__ int enumerate_stream(const TileInfo &ti, const SixMas
             k++;
         }
     };
-    if (min_aa >= 16) {
-        // Two stops of one stream inside a thread's 48 bases are < 16 codons apart, so only the FIRST stop of the thread
-        // (and the virtual stop at the contig end) can close an ORF of >= 16 residues: no loop over stops.
+    uint64_t x[SIX_HALVES];
+    if (min_aa >= SIX_FAST_MIN_AA) {
+        // Two stops of one stream inside a thread's SIX_BPT bases are < SIX_BPT/3 codons apart, so only the FIRST stop of the
+        // thread (and the virtual stop at the contig end) can close an ORF of that many residues: no loop over stops.
         int first, last;                              // fl: (first, last) packed by the caller, -2 = not known
         if (fl != -2) { first = (fl & 0xFF) - 1; last = ((fl >> 8) & 0xFF) - 1; }
-        else stream_first_last(sm, s, ti.Lm3, first, last);
+        else { stream_stops(ts, s, ti.Lm3, x); stops_first_last(x, first, last); }
         if (first >= 0) visit(prev, prev >= 0, x0 + first, true);
         if (is_end_thread) {
             const int64_t xl = last >= 0 ? x0 + last : prev;
@@ -350,21 +375,21 @@ __device__ __forceinline__ int enumerate_stream(const TileInfo &ti, const SixMas
         }
         return k;
     }
-    const int r = stream_res(s, ti.Lm3);
-    const uint64_t *msk = plus ? sm.pm : sm.mm;
+    stream_stops(ts, s, ti.Lm3, x);
     int64_t xl = prev;
     bool xl_real = prev >= 0;
-    for (int g = 0; g <= 3; g++) {
-        uint64_t x = g < 3 ? (msk[g] & res_mask((r - g + 3) % 3)) : (is_end_thread ? 1ull : 0ull);
-        while (x) {
-            const int t = 16 * g + ((__ffsll((long long)x) - 1) >> 2);
-            x &= x - 1;
-            const int64_t xh = x0 + t;
-            visit(xl, xl_real, xh, g < 3);
+#pragma unroll
+    for (int h = 0; h < SIX_HALVES; h++) {
+        uint64_t v = x[h];
+        while (v) {
+            const int64_t xh = x0 + SIX_HALF * h + __ffsll((long long)v) - 1;
+            v &= v - 1;
+            visit(xl, xl_real, xh, true);
             xl = xh;
             xl_real = true;
         }
     }
+    if (is_end_thread) visit(xl, xl_real, 0, false);  // the virtual stop at the contig's high end
     return k;
 }
 
@@ -412,9 +437,9 @@ __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
     const int64_t x0 = tile0 + (int64_t)threadIdx.x * SIX_BPT;
     const bool active = x0 < ti.L;
     const bool is_end_thread = active && (x0 + SIX_BPT >= ti.L);       // owns the virtual high-end stops
-    SixMasks sm;
-    if (active) six_masks(packed, ti.gb, ti.L, x0, ti.cs, sm);
-    else { sm.pm[0] = sm.pm[1] = sm.pm[2] = sm.mm[0] = sm.mm[1] = sm.mm[2] = 0; }
+    ThreadStops sm;                                   // the thread's stops, one bit per position
+    if (active) thread_stops(packed, ti, x0, sm);
+    else { for (int h = 0; h < SIX_HALVES; h++) { sm.p[h] = 0; sm.m[h] = 0; } }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
     // previous stop of each stream before this thread: exclusive max over lower threads, else the tile carry
@@ -422,7 +447,9 @@ __global__ void __launch_bounds__(SIX_THREADS) k_six_orfs(
 #pragma unroll
     for (int s = 0; s < 6; s++) {
         int first, last;
-        stream_first_last(sm, s, ti.Lm3, first, last);
+        uint64_t xs[SIX_HALVES];
+        stream_stops(sm, s, ti.Lm3, xs);
+        stops_first_last(xs, first, last);
         int inc = last < 0 ? -1 : (int)threadIdx.x * SIX_BPT + last;   // tile-local position
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -521,17 +548,18 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
     const int64_t x0 = tile0 + (int64_t)threadIdx.x * SIX_BPT;
     const bool active = x0 < ti.L;
     const bool is_end_thread = active && (x0 + SIX_BPT >= ti.L);       // owns the virtual high-end stops
-    SixMasks sm;
-    if (active) six_masks(packed, ti.gb, ti.L, x0, ti.cs, sm);
-    else { sm.pm[0] = sm.pm[1] = sm.pm[2] = sm.mm[0] = sm.mm[1] = sm.mm[2] = 0; }
+    ThreadStops sm;                                   // the thread's stops, one bit per position
+    if (active) thread_stops(packed, ti, x0, sm);
+    else { for (int h = 0; h < SIX_HALVES; h++) { sm.p[h] = 0; sm.m[h] = 0; } }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
     int ex_local[6], fl[6];                          // fl: (first + 1) | (last + 1) << 8 of the thread's stops per stream
-    const uint64_t p_plus = pos48(sm.pm), p_minus = pos48(sm.mm);
 #pragma unroll
     for (int s = 0; s < 6; s++) {
         int first, last;
-        stream_first_last48(p_plus, p_minus, s, ti.Lm3, first, last);
+        uint64_t xs[SIX_HALVES];
+        stream_stops(sm, s, ti.Lm3, xs);
+        stops_first_last(xs, first, last);
         fl[s] = (first + 1) | ((last + 1) << 8);
         int inc = last < 0 ? -1 : (int)threadIdx.x * SIX_BPT + last;   // tile-local position
 #pragma unroll
@@ -615,7 +643,7 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
     }
     int tot[6], before[6], excl[6];                   // kept ORFs of the tile per stream; of the streams before s; of lower threads
     int run = 0;
-    if (min_aa >= 16) {
+    if (min_aa >= SIX_FAST_MIN_AA) {
         // a thread keeps at most two ORFs per stream (its first stop, the contig end): ranks from two ballots per stream and
         // the per-warp totals, one barrier; only the rare threads that hold an ORF read the totals back
         __shared__ int s_wcnt[6][NW];
