@@ -510,7 +510,7 @@ def gpu_arm(args):
                    "genome_Gbp_per_s": round(GENOME_BP / ((t_scan + t_emit) * 1e-3) / 1e9, 1),
                    "six_frame_Gbp_per_s": round(6 * GENOME_BP / ((t_scan + t_emit) * 1e-3) / 1e9, 1),
                    "algorithmic_GBps": round((GENOME_BP * 0.5 + tot_bytes + 32 * tot_orf) / ((t_scan + t_emit) * 1e-3) / 1e9, 1),
-                   "bound": "instruction issue and CTA barriers (~32 thread-instructions per base), not HBM: see DESIGN.md section 4"}
+                   "bound": "instruction issue and CTA barriers, not HBM (the genome is read once: 1.56 GB): see DESIGN.md section 4"}
             del aa_dev
         except Exception as e:
             six = {"error": str(e)[:300]}

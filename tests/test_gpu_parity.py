@@ -393,13 +393,13 @@ def test_sixframe_matches_reference_get_orfs(mg, kat):
         assert got == r, (len(s), s[:40])
 
 
-@pytest.mark.parametrize("min_aa", [0, 1, 15, 16, 30, 31, 32, 33, 100])
+@pytest.mark.parametrize("min_aa", [0, 1, 15, 16, 30, 31, 32, 33, 47, 48, 49, 100])
 def test_sixframe_random_contigs(mg, min_aa):
     rng = np.random.default_rng(100 + min_aa)
     alpha = np.frombuffer(b"ACGTacgtNnR", dtype=np.uint8)
     p = np.array([30, 30, 30, 30, 10, 10, 10, 10, 2, 1, 1], dtype=float)
     contigs = []
-    for n in [0, 1, 2, 3, 4, 5, 6, 7, 8, 47, 48, 49, 95, 96, 97, 12287, 12288, 12289, 12290, 24575, 24576, 24577, 24578, 30000, 49151, 49152, 49153, 49154, 98305, 200001]:
+    for n in [0, 1, 2, 3, 4, 5, 6, 7, 8, 47, 48, 49, 95, 96, 97, 12287, 12288, 12289, 12290, 24575, 24576, 24577, 24578, 30000, 49151, 49152, 49153, 49154, 73727, 73728, 73729, 98305, 147457, 200001]:
         contigs.append(alpha[rng.choice(alpha.size, size=n, p=p / p.sum())].tobytes())
     # stop-poor contig (long ORFs crossing many tiles) and an N run in the middle of a contig
     contigs.append(np.frombuffer(b"ACG", dtype=np.uint8)[rng.integers(0, 3, size=60000)].tobytes())
@@ -469,7 +469,7 @@ def test_sixframe_contig_list_any_order(mg, min_aa):
     from magot_b200 import engine, orfs
     rng = np.random.default_rng(900 + min_aa)
     alpha = np.frombuffer(b"ACGTacgtNn", dtype=np.uint8)
-    contigs = [alpha[rng.integers(0, alpha.size, size=n)].tobytes() for n in (30000, 7, 60000, 24577, 0, 50001)]
+    contigs = [alpha[rng.integers(0, alpha.size, size=n)].tobytes() for n in (30000, 7, 160000, 73729, 0, 50001)]
     g = engine.DeviceGenome([len(c) for c in contigs], device=0)
     for i, c in enumerate(contigs):
         g.pack(i, np.frombuffer(c, dtype=np.uint8))
@@ -495,7 +495,7 @@ def test_sixframe_dense_output_second_pass(mg, min_aa, monkeypatch):
     monkeypatch.setenv("MG_SIX_HIT_CAP", "7")
     rng = np.random.default_rng(300 + min_aa)
     alpha = np.frombuffer(b"ACGTacgtNn", dtype=np.uint8)
-    contigs = [alpha[rng.integers(0, alpha.size, size=n)].tobytes() for n in (5, 49153, 120000)]
+    contigs = [alpha[rng.integers(0, alpha.size, size=n)].tobytes() for n in (5, 73729, 160000)]
     _sixframe_case(mg, contigs, min_aa)
 
 
