@@ -757,58 +757,106 @@ __global__ void __launch_bounds__(AA_THREADS) k_six_aa(const uint32_t *__restric
                                                        const int64_t *__restrict__ tile_first, int64_t total,
                                                        const uint8_t *__restrict__ aa4096, uint8_t *__restrict__ out) {
     __shared__ __align__(16) uint8_t s_aa[4096];
-    __shared__ int64_t s_off[AA_CAP + 1];
+    __shared__ int64_t s_off[AA_CAP + 1];             // residue offsets of the tile's ORFs ...
+    __shared__ int64_t s_src[AA_CAP];                 // ... and the index of their first base (either plane, a forward read)
     reinterpret_cast<uint4 *>(s_aa)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(aa4096) + threadIdx.x);
     const int64_t P0 = (int64_t)blockIdx.x * AA_TILE;
     const int64_t o_lo = tile_first[blockIdx.x];
     int64_t o_hi = tile_first[blockIdx.x + 1] + 1;
     if (o_hi > n_orf) o_hi = n_orf;
     const int ncache = (int)min((int64_t)AA_CAP, o_hi - o_lo);
-    for (int i = threadIdx.x; i <= ncache; i += AA_THREADS) s_off[i] = __ldg(aa_off + o_lo + i);
+    for (int i = threadIdx.x; i <= ncache; i += AA_THREADS) {
+        s_off[i] = __ldg(aa_off + o_lo + i);
+        if (i < ncache) s_src[i] = __ldg(srcs + o_lo + i);
+    }
     __syncthreads();
     const int64_t cached_end = s_off[ncache];
 #pragma unroll 1
     for (int cidx = 0; cidx < AA_TILE / 16 / AA_THREADS; cidx++) {
         const int64_t P = P0 + ((int64_t)(cidx * AA_THREADS + threadIdx.x) << 4);
         if (P >= total) break;
-        int64_t o;
-        if (P < cached_end) {
+        uint64_t blo = 0, bhi = 0;
+        int filled = 0;
+        int64_t pos = P;
+        if (P + 16 <= cached_end) {
+            // the whole chunk lies in ORFs staged in shared memory (always, unless a tile holds more than AA_CAP ORFs)
             int lo = 0, hi = ncache;
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
                 if (s_off[mid] <= P) lo = mid; else hi = mid;
             }
-            o = o_lo + lo;
-        } else {
-            o = mg_search_le(aa_off, o_lo + ncache, n_orf, P);
-        }
-        uint64_t blo = 0, bhi = 0;
-        int filled = 0;
-        int64_t pos = P;
-        int64_t off_o = __ldg(aa_off + o), off_n = __ldg(aa_off + o + 1);
-        while (filled < 16 && pos < total) {
-            while (off_n <= pos) { o++; off_o = off_n; off_n = __ldg(aa_off + o + 1); }
-            const int64_t a = pos - off_o;
-            int c = 16 - filled;
-            if (off_n - pos < c) c = (int)(off_n - pos);
-            const int64_t g0 = __ldg(srcs + o) + 3 * a;      // either plane, always a forward read
-            uint64_t acc[3];
-            acc[0] = mg_ld_nib16(packed, g0);
-            acc[1] = mg_ld_nib16(packed, g0 + 16);
-            acc[2] = mg_ld_nib16(packed, g0 + 32);
+            uint32_t bw[4] = {0, 0, 0, 0};
+            while (filled < 16 && pos < total) {
+                while (s_off[lo + 1] <= pos) lo++;
+                const int64_t a = pos - s_off[lo];
+                int c = 16 - filled;
+                if (s_off[lo + 1] - pos < c) c = (int)(s_off[lo + 1] - pos);
+                // 16 codons = 48 nibbles from one ORF: seven words, six funnel shifts (as K3), then 12-bit table indices
+                const int64_t g0 = s_src[lo] + 3 * a;
+                const uint32_t *pp = packed + (g0 >> 3);
+                const uint32_t sh0 = ((uint32_t)g0 & 7u) << 2;
+                uint32_t v[7], n[6];
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                if (k < c) {
-                    const int bit = 12 * k, w = bit >> 6, sh = bit & 63;
-                    uint32_t idx = (uint32_t)(acc[w] >> sh);
-                    if (sh > 52) idx |= (uint32_t)(acc[w + 1] << (64 - sh));
-                    const uint64_t b = s_aa[idx & 0xFFFu];
-                    const int t = filled + k;
-                    if (t < 8) blo |= b << (8 * t); else bhi |= b << (8 * (t - 8));
+                for (int k = 0; k < 7; k++) v[k] = __ldg(pp + k);
+#pragma unroll
+                for (int k = 0; k < 6; k++) n[k] = __funnelshift_r(v[k], v[k + 1], sh0);
+                uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int k = 0; k < 16; k++) {            // codon k = nibbles 3k..3k+2 = bits 12k.. of n[5]:..:n[0]
+                    const int bit = 12 * k, ww = bit >> 5, sh = bit & 31;
+                    uint32_t idx = n[ww] >> sh;
+                    if (sh > 20) idx |= n[ww + 1] << (32 - sh);
+                    w[k >> 2] |= (uint32_t)s_aa[idx & 0xFFFu] << ((k & 3) * 8);
                 }
+                if (c == 16) { bw[0] = w[0]; bw[1] = w[1]; bw[2] = w[2]; bw[3] = w[3]; }
+                else {                                    // c residues of this ORF land at chunk positions [filled, filled + c)
+                    const uint32_t m = ((1u << c) - 1u);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        // shift the c residues up by `filled` bytes inside the 16-byte chunk
+                        uint32_t lo32 = 0;
+                        const int byte0 = 4 * k - filled;     // source byte that lands on byte 4k
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const int sb = byte0 + b;
+                            if (sb >= 0 && sb < 16 && ((m >> sb) & 1u)) lo32 |= ((w[sb >> 2] >> ((sb & 3) * 8)) & 0xFFu) << (8 * b);
+                        }
+                        bw[k] |= lo32;
+                    }
+                }
+                filled += c;
+                pos += c;
             }
-            filled += c;
-            pos += c;
+            blo = ((uint64_t)bw[1] << 32) | bw[0];
+            bhi = ((uint64_t)bw[3] << 32) | bw[2];
+        } else {
+            int64_t o = P < cached_end ? o_lo : o_lo + ncache;
+            o = mg_search_le(aa_off, o, n_orf, P);
+            int64_t off_o = __ldg(aa_off + o), off_n = __ldg(aa_off + o + 1);
+            while (filled < 16 && pos < total) {
+                while (off_n <= pos) { o++; off_o = off_n; off_n = __ldg(aa_off + o + 1); }
+                const int64_t a = pos - off_o;
+                int c = 16 - filled;
+                if (off_n - pos < c) c = (int)(off_n - pos);
+                const int64_t g0 = __ldg(srcs + o) + 3 * a;      // either plane, always a forward read
+                uint64_t acc[3];
+                acc[0] = mg_ld_nib16(packed, g0);
+                acc[1] = mg_ld_nib16(packed, g0 + 16);
+                acc[2] = mg_ld_nib16(packed, g0 + 32);
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    if (k < c) {
+                        const int bit = 12 * k, w = bit >> 6, sh = bit & 63;
+                        uint32_t idx = (uint32_t)(acc[w] >> sh);
+                        if (sh > 52) idx |= (uint32_t)(acc[w + 1] << (64 - sh));
+                        const uint64_t b = s_aa[idx & 0xFFFu];
+                        const int t = filled + k;
+                        if (t < 8) blo |= b << (8 * t); else bhi |= b << (8 * (t - 8));
+                    }
+                }
+                filled += c;
+                pos += c;
+            }
         }
         mg_st16(out + P, (uint32_t)blo, (uint32_t)(blo >> 32), (uint32_t)bhi, (uint32_t)(bhi >> 32));
     }
