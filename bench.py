@@ -227,6 +227,33 @@ def cpu_reference_rate(steps, warmup, workers):
     return bp / dt / 1e9, dt, kind, sample
 
 
+def host_phases():
+    """Host-side annotation parsing (outside every timed region): the product's read_gff and the reference's own on GTF text of
+    the sample (the reference is ~1 ms per line, so it gets the first 2 000 lines only)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from magot_b200 import genome as mg_genome
+    layout, contigs, ann = build_sample()
+    gtf = ann.to_gtf([n for n, _ in layout])
+    n_lines = gtf.count("\n")
+    t0 = time.perf_counter()
+    mg_genome.read_gff(gtf)
+    t_prod = time.perf_counter() - t0
+    out = {"gtf_lines": n_lines, "product_read_gff_lines_per_s": round(n_lines / t_prod)}
+    try:
+        import contextlib
+        import io
+        import ref_runner
+        ref = ref_runner.ref()
+        head = "\n".join(gtf.split("\n")[:2000]) + "\n"
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref.read_gff(head)
+        out["reference_read_gff_lines_per_s"] = round(2000 / (time.perf_counter() - t0))
+    except Exception as e:
+        out["reference_read_gff_error"] = str(e)[:200]
+    return out
+
+
 def cpu_port_rate():
     """Single-threaded C restatement (oracle/oracle.c) on a larger sample: tight-loop CPU figure."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -561,6 +588,10 @@ def gpu_arm(args):
                     cpu["c_port_single_thread_Gbps"] = round(cpu_port_rate(), 4)
                 except Exception as e:      # the C port is extra information only
                     cpu["c_port_error"] = str(e)[:200]
+                try:
+                    cpu["host_annotation_parse"] = host_phases()
+                except Exception as e:
+                    cpu["host_annotation_parse"] = {"error": str(e)[:200]}
             except Exception as e:
                 cpu = {"value": None, "unit": "Gbp/s", "cores": 1, "kind": "port", "sample": "failed: %s" % str(e)[:300]}
         line = {
