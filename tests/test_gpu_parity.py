@@ -316,6 +316,60 @@ def test_dense_tiny_segments_overflow_the_tile_staging(mg, framing):
     g.close()
 
 
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_random_tables_differential(mg, seed):
+    """Randomised differential test of K1 + K2 + K3 against the C oracle: contigs of any length (incl. 0) over an alphabet with
+    soft-masked, IUPAC and out-of-alphabet bytes; records with 0-12 segments whose coordinates run off either contig end, are
+    zero or negative (Python slice rules, genome.py:606), both strands, and framing of 0-40 bytes per record."""
+    from magot_b200 import engine
+    rng = np.random.default_rng(5000 + seed)
+    alpha = np.frombuffer(b"ACGTACGTACGTacgtacgtNnRYKM-*xS", dtype=np.uint8)
+    n_contig = int(rng.integers(1, 6))
+    contigs = [alpha[rng.integers(0, alpha.size, size=int(n))].copy() for n in rng.choice([0, 1, 2, 3, 31, 32, 33, 100, 1000, 5000, 40000], size=n_contig)]
+    g = engine.DeviceGenome([a.size for a in contigs], device=0)
+    for i, a in enumerate(contigs):
+        g.pack(i, a)
+    g.finalize()
+    n_rec = int(rng.integers(1, 400))
+    n_seg = rng.integers(0, 13, size=n_rec)
+    rec_off = np.concatenate(([0], np.cumsum(n_seg)))
+    E = int(rec_off[-1])
+    cid = rng.integers(0, n_contig, size=E).astype(np.int32)
+    L = np.array([a.size for a in contigs], dtype=np.int64)[cid]
+    st = rng.integers(-20, L + 30)
+    en = st + rng.integers(-5, 700, size=E)
+    swap = en < st                                       # the GFF reader sorts each pair (genome.py:309-311)
+    st, en = np.where(swap, en, st), np.where(swap, st, en)
+    sd = rng.integers(0, 2, size=E).astype(np.int8)
+    pre = rng.integers(0, 30, size=n_rec).astype(np.int32)
+    suf = rng.integers(0, 12, size=n_rec).astype(np.int32)
+    if seed % 3 == 0:
+        pre[:] = 0
+        suf[:] = 0
+    lit = rng.integers(33, 127, size=int(pre.sum() + suf.sum()), dtype=np.uint8)
+    lit_off = np.concatenate(([0], np.cumsum(pre.astype(np.int64) + suf)[:-1]))
+    tbl = engine.RecordTable(rec_off, cid, st, en, sd, lit_off, pre, suf, lit)
+    lo = np.empty(E, dtype=np.int64)
+    hi = np.empty(E, dtype=np.int64)
+    for e in range(E):                                   # Python slice semantics of contig[start-1:end]
+        a, b, _ = slice(int(st[e]) - 1, int(en[e])).indices(int(L[e]))
+        lo[e], hi[e] = a, max(a, b)
+    nuc, off = coracle.splice([a.tobytes() for a in contigs], rec_off, cid, lo, hi, sd)
+    aa, aa_off, aa_len = coracle.splice_translate(nuc, off)
+    text, (got_n, got_a) = engine.run_table(g, tbl, want_lengths=True)
+    textp, _ = engine.run_table(g, tbl, protein=True)
+    assert np.array_equal(got_n, np.diff(off)) and np.array_equal(got_a, aa_len)
+    want, wantp = [], []
+    for r in range(n_rec):
+        p0 = int(lit_off[r])
+        head, tail = lit[p0:p0 + pre[r]].tobytes(), lit[p0 + pre[r]:p0 + pre[r] + suf[r]].tobytes()
+        want.append(head + nuc[off[r]:off[r + 1]].tobytes() + tail)
+        wantp.append(head + aa[aa_off[r]:aa_off[r + 1]].tobytes() + tail)
+    assert text == b"".join(want)
+    assert textp == b"".join(wantp)
+    g.close()
+
+
 def test_edge_records(mg):
     """Empty records, zero-length segments, 1-base segments, records <= 2 bases (translate -> None)."""
     from magot_b200 import engine
