@@ -34,6 +34,7 @@
                                                          // that 8 CTAs fit and most of the SM's 256 KB stays L1 cache (measured +7 %)
 #endif
 #define NUC_UNITS (MG_NUC_TILE / 32)
+#define NUC_LITCAP 256                                   // literal pieces listed per tile (config 4: ~50)
 #define NUC_CHUNKS (MG_NUC_TILE / 32 / NUC_THREADS)     // 4 chunks of 32 B per thread
 
 #define PROT_THREADS 256
@@ -216,12 +217,15 @@ __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_nuc(
     __shared__ uint16_t s_ng[NUC_CAP + 2];
     __shared__ uint8_t s_kind[NUC_CAP + 2];
     __shared__ uint16_t s_unit[NUC_UNITS];            // piece holding byte 32*u of the tile, i.e. the first byte of chunk u
+    __shared__ uint16_t s_lits[NUC_LITCAP];           // the tile's non-empty literal pieces (any order)
+    __shared__ int s_nlit;
     const int64_t P0 = (int64_t)blockIdx.x * MG_NUC_TILE;
     const int64_t p_lo = tile_first[blockIdx.x];
     int64_t p_hi = tile_first[blockIdx.x + 1] + 1;    // one past the last piece this tile can touch
     if (p_hi > n_piece) p_hi = n_piece;
     const int ncache = (int)min((int64_t)NUC_CAP, p_hi - p_lo);
     const int tile_len = (int)min((int64_t)MG_NUC_TILE, total - P0);
+    if (threadIdx.x == 0) s_nlit = 0;
     for (int i = threadIdx.x; i < ncache + 2; i += NUC_THREADS) {
         if (i < ncache) {
             const int64_t rel = __ldg(piece_off + p_lo + i) - P0;      // > -2^31: piece lengths are int32
@@ -247,6 +251,10 @@ __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_nuc(
             const int r0 = s_rel[i] < 0 ? 0 : s_rel[i], r1 = s_rel[i + 1] < 0 ? 0 : s_rel[i + 1];
             const int u1 = min((r1 + 31) >> 5, NUC_UNITS);
             for (int u = (r0 + 31) >> 5; u < u1; u++) s_unit[u] = (uint16_t)i;
+            if (s_kind[i] == PIECE_L && r1 > r0) {
+                const int slot = atomicAdd(&s_nlit, 1);
+                if (slot < NUC_LITCAP) s_lits[slot] = (uint16_t)i;
+            }
         }
     }
     __syncthreads();
@@ -303,14 +311,24 @@ __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_nuc(
         st32(out + P0 + p, w);
     }
 
-    // framing bytes of this tile, over the placeholders the chunks above left (same CTA, ordered by the barrier)
+    // framing bytes of this tile, over the placeholders the chunks above left (same CTA, ordered by the barrier): eight lanes
+    // per literal piece, so the ~50 pieces of a tile are written by all warps at once
     __syncthreads();
-    for (int i = threadIdx.x; i < ncache; i += NUC_THREADS) {                      // one thread per piece (~50 literal pieces per tile)
-        if (s_kind[i] != PIECE_L) continue;
-        const int r0 = max(s_rel[i], 0), r1 = min(s_rel[i + 1], tile_len);
-        const uint8_t *src = lit + s_base[i];
-        uint8_t *dst = out + P0;
-        for (int q = r0; q < r1; q++) dst[q] = __ldg(src + q);
+    const int nlit = s_nlit;
+    if (nlit <= NUC_LITCAP) {
+        for (int k = threadIdx.x; k < nlit * 8; k += NUC_THREADS) {
+            const int i = s_lits[k >> 3];
+            const int r1 = min(s_rel[i + 1], tile_len);
+            const uint8_t *src = lit + s_base[i];
+            for (int q = max(s_rel[i], 0) + (k & 7); q < r1; q += 8) out[P0 + q] = __ldg(src + q);
+        }
+    } else {                                          // more literal pieces than the list holds: one thread per piece
+        for (int i = threadIdx.x; i < ncache; i += NUC_THREADS) {
+            if (s_kind[i] != PIECE_L) continue;
+            const int r0 = max(s_rel[i], 0), r1 = min(s_rel[i + 1], tile_len);
+            const uint8_t *src = lit + s_base[i];
+            for (int q = r0; q < r1; q++) out[P0 + q] = __ldg(src + q);
+        }
     }
 }
 
