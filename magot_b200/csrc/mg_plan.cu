@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256) k_plan_pieces(int64_t n_piece, int64_t n_
                                                      const int32_t *__restrict__ rec_suf, const int64_t *__restrict__ contig_len,
                                                      const int64_t *__restrict__ contig_base, int64_t n_contigs, int64_t two_T,
                                                      unsigned long long *tmp, int64_t *__restrict__ piece_off,
-                                                     int64_t *__restrict__ piece_src, int64_t *__restrict__ total_out) {
+                                                     int64_t *__restrict__ piece_src, int64_t *__restrict__ total_out,
+                                                     int64_t *__restrict__ tile_first, int64_t tile_cap) {
     // The PLAN_TILE pieces of a block belong to at most PLAN_TILE/2 + 1 consecutive records starting at blk_r0[block]
     // (k_plan_block_rec): F(r) = rec_seg_off[r] + 2r of those records is staged in shared memory and every thread
     // searches there.
@@ -112,10 +113,26 @@ __global__ void __launch_bounds__(256) k_plan_pieces(int64_t n_piece, int64_t n_
     int64_t run = prefix + incl - mine;
 #pragma unroll
     for (int it = 0; it < PLAN_ITEMS; it++) {
-        if (p0 + it < n_piece) piece_off[p0 + it] = run;
+        if (p0 + it < n_piece) {
+            piece_off[p0 + it] = run;
+            // tile -> first piece by scatter (mg_plan_prepare_async: the table exists before the text size is known): the
+            // piece that holds byte t * MG_NUC_TILE writes itself into slot t; empty pieces hold no byte
+            if (tile_first && len[it] > 0) {
+                for (int64_t t = (run + MG_NUC_TILE - 1) / MG_NUC_TILE; t * MG_NUC_TILE < run + len[it] && t < tile_cap; t++)
+                    tile_first[t] = p0 + it;
+            }
+        }
         run += len[it];
     }
-    if (tile == gridDim.x - 1 && threadIdx.x == 0) { piece_off[n_piece] = prefix + total; *total_out = prefix + total; }
+    if (tile == gridDim.x - 1 && threadIdx.x == 0) {
+        const int64_t all = prefix + total;
+        piece_off[n_piece] = all;
+        *total_out = all;
+        if (tile_first) {                              // sentinel after the last tile, as k_plan_tiles writes it
+            const int64_t n_tile = min(tile_cap, (all + MG_NUC_TILE - 1) / MG_NUC_TILE);
+            tile_first[n_tile] = n_piece > 0 ? n_piece - 1 : 0;
+        }
+    }
 }
 
 // thread per record: spliced length -> amino-acid count (Sequence.translate, genome.py:810-821) and, with the same
@@ -125,7 +142,8 @@ __global__ void __launch_bounds__(256) k_plan_records(int64_t n_rec, const int64
                                                       const uint32_t *__restrict__ packed, const int8_t *__restrict__ rec_phase,
                                                       int flags, int32_t *__restrict__ rec_aa, int8_t *__restrict__ rec_skip,
                                                       unsigned long long *tmp, int64_t *__restrict__ prot_off,
-                                                      int64_t *__restrict__ total_out) {
+                                                      int64_t *__restrict__ total_out, int64_t *__restrict__ tile_first,
+                                                      int64_t tile_cap) {
     __shared__ int64_t s_warp[8];
     __shared__ int64_t s_prefix;
     __shared__ unsigned int s_tile;
@@ -162,8 +180,22 @@ __global__ void __launch_bounds__(256) k_plan_records(int64_t n_rec, const int64
     int64_t total;
     const int64_t incl = mg_block_incl_scan(plen, s_warp, &total);
     const int64_t prefix = mg_lookback(tmp, tile, total, &s_prefix);
-    if (r < n_rec) prot_off[r] = prefix + incl - plen;
-    if (tile == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) { prot_off[n_rec] = prefix + total; *total_out = prefix + total; }
+    if (r < n_rec) {
+        const int64_t off = prefix + incl - plen;
+        prot_off[r] = off;
+        if (tile_first && plen > 0) {                  // tile -> first record by scatter, see k_plan_pieces
+            for (int64_t t = (off + MG_PROT_TILE - 1) / MG_PROT_TILE; t * MG_PROT_TILE < off + plen && t < tile_cap; t++) tile_first[t] = r;
+        }
+    }
+    if (tile == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) {
+        const int64_t all = prefix + total;
+        prot_off[n_rec] = all;
+        *total_out = all;
+        if (tile_first) {
+            const int64_t n_tile = min(tile_cap, (all + MG_PROT_TILE - 1) / MG_PROT_TILE);
+            tile_first[n_tile] = n_rec > 0 ? n_rec - 1 : 0;
+        }
+    }
 }
 
 // thread per tile: index of the piece / record that contains the tile's first byte; nucleotide tiles first, then protein
@@ -280,7 +312,11 @@ extern "C" int mg_plan_destroy(mg_plan *p) {
 }
 
 // K1, first half: clamp + lengths + offsets of every piece and record; the two text sizes land in p->d_totals
-static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st) {
+static int plan_alloc_tiles(mg_plan *p, int64_t cap_nuc, int64_t cap_prot, cudaStream_t st);
+
+// scatter_tiles: the tile tables are sized for the caller's capacities and filled by the plan kernels themselves
+static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st, bool scatter_tiles = false, int64_t cap_nuc = 0,
+                             int64_t cap_prot = 0) {
     mg_genome *g = p->g;
     p->prot_flags = prot_flags;
     p->last_stream = st;
@@ -288,24 +324,31 @@ static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st) {
     unsigned long long *tmp_a = reinterpret_cast<unsigned long long *>(p->d_scan_tmp), *tmp_b = tmp_a + n_block + 1;
     p->d_totals = reinterpret_cast<int64_t *>(tmp_b + n_rblock + 1);
     MG_CUDA(cudaMemsetAsync(p->d_scan_tmp, 0, p->scan_tmp_cap * sizeof(int64_t), st));
+    int64_t *tf_nuc = nullptr, *tf_prot = nullptr;
+    if (scatter_tiles) {
+        int rc = plan_alloc_tiles(p, cap_nuc, cap_prot, st);
+        if (rc) return rc;
+        tf_nuc = p->d_nuc_tile;
+        tf_prot = p->d_prot_tile;
+    }
     if (p->n_rec == 0) return MG_OK;
     k_plan_block_rec<<<(unsigned)n_rblock, 256, 0, st>>>(n_block, p->n_rec, p->d_rec_seg_off, p->d_blk_r0);
     MG_LAUNCH_CHECK();
     k_plan_pieces<<<(unsigned)n_block, 256, 0, st>>>(
         p->n_piece, p->n_rec, p->d_rec_seg_off, p->d_blk_r0, p->d_seg_contig, p->d_seg_start, p->d_seg_end, p->d_seg_strand,
         p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, g->d_contig_len, g->d_contig_base, g->n_contigs, 2 * g->total_bases,
-        tmp_a, p->d_piece_off, p->d_piece_src, p->d_totals);
+        tmp_a, p->d_piece_off, p->d_piece_src, p->d_totals, tf_nuc, p->n_nuc_tile);
     MG_LAUNCH_CHECK();
     k_plan_records<<<(unsigned)n_rblock, 256, 0, st>>>(
         p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_piece_src, g->d_packed, p->d_rec_phase, prot_flags,
-        p->d_rec_aa, p->d_rec_skip, tmp_b, p->d_prot_off, p->d_totals + 1);
+        p->d_rec_aa, p->d_rec_skip, tmp_b, p->d_prot_off, p->d_totals + 1, tf_prot, p->n_prot_tile);
     MG_LAUNCH_CHECK();
     return MG_OK;
 }
 
 // K1, second half: tile -> first piece / first record, for texts of up to cap_nuc / cap_prot bytes (the real tile counts are
 // derived on the device from p->d_totals).  Removes every global binary search from the emit kernels.
-static int plan_launch_tiles(mg_plan *p, int64_t cap_nuc, int64_t cap_prot, cudaStream_t st) {
+static int plan_alloc_tiles(mg_plan *p, int64_t cap_nuc, int64_t cap_prot, cudaStream_t st) {
     p->n_nuc_tile = (cap_nuc + MG_NUC_TILE - 1) / MG_NUC_TILE;
     p->n_prot_tile = (cap_prot + MG_PROT_TILE - 1) / MG_PROT_TILE;
     const int64_t tile_need = p->n_nuc_tile + 1 + p->n_prot_tile + 1;
@@ -318,6 +361,12 @@ static int plan_launch_tiles(mg_plan *p, int64_t cap_nuc, int64_t cap_prot, cuda
     }
     p->d_nuc_tile = p->d_tile_buf;
     p->d_prot_tile = p->d_tile_buf + p->n_nuc_tile + 1;
+    return MG_OK;
+}
+
+static int plan_launch_tiles(mg_plan *p, int64_t cap_nuc, int64_t cap_prot, cudaStream_t st) {
+    int rc = plan_alloc_tiles(p, cap_nuc, cap_prot, st);
+    if (rc) return rc;
     if (p->n_rec > 0 && p->n_nuc_tile + p->n_prot_tile > 0) {
         k_plan_tiles<<<(unsigned)((p->n_nuc_tile + p->n_prot_tile + 2 + 255) / 256), 256, 0, st>>>(
             p->d_totals, p->d_piece_off, p->n_piece, MG_NUC_TILE, p->n_nuc_tile, p->d_nuc_tile, p->d_prot_off, p->n_rec, MG_PROT_TILE,
@@ -362,9 +411,7 @@ extern "C" int mg_plan_prepare_async(mg_plan *p, int prot_flags, int64_t nuc_cap
     MG_REQUIRE(nuc_capacity >= 0 && prot_capacity >= 0, "capacities must be >= 0");
     MG_CUDA(cudaSetDevice(p->device));
     p->prepared = false;
-    int rc = plan_launch_scans(p, prot_flags, (cudaStream_t)stream);
-    if (rc) return rc;
-    rc = plan_launch_tiles(p, nuc_capacity, prot_capacity, (cudaStream_t)stream);
+    int rc = plan_launch_scans(p, prot_flags, (cudaStream_t)stream, true, nuc_capacity, prot_capacity);
     if (rc) return rc;
     p->nuc_total = nuc_capacity;                     // until mg_plan_totals: what the caller's buffers can take
     p->prot_total = prot_capacity;
