@@ -64,15 +64,20 @@ __global__ void __launch_bounds__(256) k_plan_pieces(int64_t n_piece, int64_t n_
     // the pieces' (dependent) table loads makes them wait for each other
     int64_t len[PLAN_ITEMS];
     const int64_t p0 = pb + (int64_t)threadIdx.x * PLAN_ITEMS;
+    int lo = 0;                                        // record of the current piece, relative to r0
 #pragma unroll
     for (int it = 0; it < PLAN_ITEMS; it++) {
         const int64_t p = p0 + it;
         len[it] = 0;
         if (p < n_piece) {
-            int lo = 0, hi = PLAN_TILE / 2 + 1;        // F(r0) <= p < F(r0 + PLAN_TILE/2 + 1): F grows by >= 2 per record
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (s_F[mid] <= p) lo = mid; else hi = mid;
+            if (it == 0) {                              // the thread's first piece: search; its next ones: walk on
+                int hi = PLAN_TILE / 2 + 1;            // F(r0) <= p < F(r0 + PLAN_TILE/2 + 1): F grows by >= 2 per record
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_F[mid] <= p) lo = mid; else hi = mid;
+                }
+            } else {
+                while (s_F[lo + 1] <= p) lo++;
             }
             const int64_t r = r0 + lo;
             const int64_t s0 = s_F[lo] - 2 * r, s1 = s_F[lo + 1] - 2 * (r + 1);
