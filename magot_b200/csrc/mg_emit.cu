@@ -40,7 +40,7 @@
 #define PROT_THREADS 256
 #define PROT_CHUNKS (MG_PROT_TILE / 16 / PROT_THREADS)  // 4
 #ifndef PROT_MINB
-#define PROT_MINB 6
+#define PROT_MINB 7                                      // 36 registers; measured 5: 0.147, 6: 0.136, 7: 0.129, 8: 0.130 ms
 #endif
 #ifndef PROT_RCAP
 #define PROT_RCAP 256                                    // records staged per tile (a 16 KB tile of config 4 has ~45)
