@@ -134,7 +134,9 @@ struct mg_plan {
 #define MG_SRC_MASK ((1ull << MG_KIND_SHIFT) - 1ull)
 
 #define MG_NUC_TILE 32768          // bytes of nucleotide text per CTA tile
+#ifndef MG_PROT_TILE
 #define MG_PROT_TILE 16384         // bytes of protein text per CTA tile
+#endif
 
 // internal cross-file helpers
 int mg_scan_i32(const int32_t *d_in, int64_t *d_out, int64_t n, int64_t *d_tmp, int64_t tmp_cap, cudaStream_t st);

@@ -37,7 +37,9 @@
 #define NUC_LITCAP 256                                   // literal pieces listed per tile (config 4: ~50)
 #define NUC_CHUNKS (MG_NUC_TILE / 32 / NUC_THREADS)     // 4 chunks of 32 B per thread
 
+#ifndef PROT_THREADS
 #define PROT_THREADS 256
+#endif
 #define PROT_CHUNKS (MG_PROT_TILE / 16 / PROT_THREADS)  // 4
 #ifndef PROT_MINB
 #define PROT_MINB 7                                      // 36 registers; measured 5: 0.147, 6: 0.136, 7: 0.129, 8: 0.130 ms
