@@ -25,7 +25,8 @@ import numpy as np
 
 from . import _lib
 from . import engine
-from .py2dict import py2_order, py2_order_after_deepcopy
+from .py2dict import py2_order, py2_order_after_deepcopy, py2_instance_attr_order
+import weakref
 
 verbose = True                      # genome.py:22
 RECORD_ORDER = "py2"                # "py2" (reference-identical) | "insertion"
@@ -36,6 +37,61 @@ def _order(keys, deepcopy=False):
     if RECORD_ORDER != "py2":
         return list(keys)
     return py2_order_after_deepcopy(keys) if deepcopy else py2_order(keys)
+
+
+# AnnotationSets that read_gff created itself: the reference returns copy.deepcopy of them (genome.py:415), which
+# also changes the iteration order of every instance __dict__ (used by write_gff / "extended gff3").
+_DEEPCOPIED_SETS = weakref.WeakSet()
+
+
+def _attr_order(obj):
+    """Attribute names of obj in the order a CPython-2.7 instance __dict__ would iterate them."""
+    names = list(obj.__dict__)
+    if RECORD_ORDER != "py2":
+        return names
+    aset = obj if isinstance(obj, AnnotationSet) else getattr(obj, "annotation_set", None)
+    return py2_instance_attr_order(names, deepcopied=aset is not None and aset in _DEEPCOPIED_SETS)
+
+
+def _py2_str(value):
+    """str() as Python 2.7 prints it: floats with 12 significant digits (`score` column of get_gff)."""
+    if isinstance(value, float):
+        t = "%.12g" % value
+        if "." not in t and "e" not in t and "n" not in t:      # 'inf' / 'nan' carry an 'n'
+            t += ".0"
+        return t
+    return str(value)
+
+
+def _gff_columns(obj):
+    """The eight leading GFF columns of get_gff (genome.py:618-625 / :738-745): a missing attribute prints '.',
+    anything else (e.g. get_coords() of a childless parent being None) raises like the reference's eval."""
+    fields_list = []
+    for field in ('seqid', 'source', 'feature_type', 0, 1, 'score', 'strand', 'phase'):
+        try:
+            if isinstance(field, int):
+                fields_list.append(_py2_str(obj.get_coords()[field]))
+            else:
+                fields_list.append(_py2_str(getattr(obj, field)))
+        except AttributeError:
+            fields_list.append('.')
+    return fields_list
+
+
+_GFF3_FORMATS = ("simple gff3", "extended gff3", "exon added gff3")
+_NOT_EXTENDED = ('ID', 'Parent', 'score', 'strand', 'seqid', 'feature_type', 'phase', 'source')
+
+
+def _gff3_defline(obj, gff_format):
+    """ID=..;Parent=.. (+ every other str attribute in instance-dict order for "extended gff3"), genome.py:626-633."""
+    defline = 'ID=' + obj.ID
+    if obj.parent is not None:
+        defline = defline + ';Parent=' + obj.parent
+    if gff_format == "extended gff3":
+        for attribute in _attr_order(obj):
+            if type(obj.__dict__[attribute]).__name__ == 'str' and attribute not in _NOT_EXTENDED:
+                defline = defline + ';' + attribute + '=' + obj.__dict__[attribute]
+    return defline
 
 
 # ---------------------------------------------------------------------------------------------
@@ -365,6 +421,27 @@ class BaseAnnotation(object):
     def get_coords(self):
         return self.coords
 
+    def get_gff(self, gff_format="simple gff3"):
+        """genome.py:616-645 -- one GFF line ("exon added gff3": an exon twin line before every CDS line).
+        Returns None without an annotation_set; an unknown format or `gtf` without a parent raise as in the reference
+        (UnboundLocalError / TypeError)."""
+        if self.annotation_set is not None:
+            fields_list = _gff_columns(self)
+            if gff_format in _GFF3_FORMATS:
+                defline = _gff3_defline(self, gff_format)
+            elif gff_format[:13] == "augustus hint":
+                gff_format_fields = gff_format.split()
+                fields_list[2] = gff_format_fields[2]
+                defline = "src=" + gff_format_fields[3]
+                if len(gff_format_fields) > 4:
+                    defline = defline + ";pri=" + gff_format_fields[4]
+            elif gff_format == "gtf":
+                defline = 'transcript_id ' + self.parent + ';gene_id ' + self.annotation_set[self.parent].parent
+            fields_list.append(defline)
+            if gff_format == "exon added gff3" and fields_list[2] == "CDS":
+                return '\t'.join(fields_list).replace('\tCDS\t', '\texon\t').replace('ID=', 'ID=ExonOf') + "\n" + '\t'.join(fields_list)
+            return '\t'.join(fields_list)
+
     def get_seq(self):
         """genome.py:603-614: contig[start-1:end] (Python slice clamping), reverse-complemented on '-'.
         Prints and returns None on an invalid strand or any lookup failure, like the reference."""
@@ -412,6 +489,40 @@ class ParentAnnotation(object):
                 elif isinstance(child_object, BaseAnnotation):
                     coords_list = coords_list + list(child_object.coords)
             return (min(coords_list), max(coords_list))
+
+    def get_gff(self, gff_format="simple gff3"):
+        """genome.py:733-778 -- this feature's line (not for `gtf` / `augustus hint`) followed by its children's,
+        children sorted by coordinates (a repeated coordinate pair is keyed (start, end + number of children so
+        far)); "exon added gff3" moves every CDS line behind the other lines of the feature."""
+        if self.annotation_set is not None:
+            fields_list = _gff_columns(self)
+            parent_line = True
+            if gff_format in _GFF3_FORMATS:
+                defline = _gff3_defline(self, gff_format)
+            elif gff_format[:13] == "augustus hint" or gff_format == 'gtf':
+                parent_line = False
+            if parent_line:
+                fields_list.append(defline)
+                lines_list = ['\t'.join(fields_list)]
+            else:
+                lines_list = []
+            child_dict = {}
+            for child in self.child_list:
+                child_object = self.annotation_set[child]
+                cc = child_object.get_coords()
+                if cc not in child_dict:
+                    child_dict[cc] = child_object.get_gff(gff_format)
+                else:
+                    child_dict[(cc[0], cc[1] + len(child_dict))] = child_object.get_gff(gff_format)
+            for child_index in sorted(child_dict):
+                lines_list.append(child_dict[child_index])
+            if gff_format == "exon added gff3":
+                lines_list = '\n'.join(lines_list).split('\n')
+                for line in lines_list[:]:
+                    if line.split('\t')[2] == "CDS":
+                        lines_list.remove(line)
+                        lines_list.append(line)
+            return '\n'.join(lines_list)
 
     def get_fasta(self, seq_type="nucleotide", longest=False, genomic=False, name_from='ID'):
         """genome.py:677-731.  One device pass for this annotation and all its descendants."""
@@ -486,14 +597,43 @@ class AnnotationSet(object):
         return fl.run(seq_type)
 
 
+def write_gff(annotation_set, gff_format="simple gff3"):
+    """genome.py:228-238 -- GFF text of every feature table whose first entry has no parent, tables taken in the
+    iteration order of the set's instance dict, features in table (Python-2.7 dict) order."""
+    gff_lines = []
+    adict = annotation_set.__dict__
+    for attribute in _attr_order(annotation_set):
+        table = adict[attribute]
+        if type(table) == dict and len(table) > 0:
+            first = table[next(iter(table))]
+            if first.__class__.__name__ in ("ParentAnnotation", "BaseAnnotation") and first.parent is None:
+                for annotationID in table:
+                    gff_lines.append(table[annotationID].get_gff(gff_format))
+    return '\n'.join(gff_lines)
+
+
+_AUGUSTUS_IGNORE = ['gene', 'transcript', 'stop_codon', 'terminal', 'internal', 'initial', 'intron', 'start_codon', 'single']
+
+
 def read_gff(gff, annotation_set_to_modify=None, base_features=['CDS', 'match_part', 'similarity', 'region'],
              features_to_ignore=['exon'], gff_version="auto", parents_hierarchy=[], features_to_replace=[],
              IDfield="ID", parent_field="Parent", presets=None):
     """genome.py:242-415 -- GFF3 / GTF reader with the reference's ID, de-dup and implicit-parent
     semantics.  Returns a new AnnotationSet (dicts in the order the reference's deepcopy leaves
     them) unless annotation_set_to_modify is given."""
-    if presets is not None:
-        raise NotImplementedError("read_gff presets rely on Python-2 exec semantics and are out of scope")
+    # presets (genome.py:261-268): the reference exec()s these assignments, which rebinds the locals under Python 2;
+    # a name that is not a preset (e.g. convert_gff's input_format 'gtf') changes nothing.
+    if presets == "augustus":
+        features_to_ignore = list(_AUGUSTUS_IGNORE)
+        parent_field = None
+        parents_hierarchy = ['transcript_id', 'gene_id']
+        IDfield = None
+    elif presets == "RepeatMasker":
+        parent_field = None
+        IDfield = 'Target'
+    elif presets == "CEGMA":
+        # the preset text indexes a list literal with a tuple ([['First','CDS']['Internal','CDS']...]): the exec raises
+        raise TypeError("list indices must be integers, not tuple")
     parents_hierarchy = list(parents_hierarchy)
     version = gff_version
     gff_file = ensure_file(gff)
@@ -651,6 +791,7 @@ def read_gff(gff, annotation_set_to_modify=None, base_features=['CDS', 'match_pa
             tbl = adict[name]
             if tbl:
                 adict[name] = {k: tbl[k] for k in _order(list(tbl), deepcopy=True)}
+        _DEEPCOPIED_SETS.add(annotation_set)
         return annotation_set
 
 

@@ -8,7 +8,7 @@ reference) and every tool prints to stdout exactly what the reference prints.
 
 Kept (file:line in genome_tools.py): gff2fasta :324, cds2pep :664, coords2fasta :656,
 get_seq_from_fasta :483, exclude_from_fasta :377, extract_upstream_downstream :457,
-blast_csv2fasta :265, exonerate2fasta :274, mask_from_gff :394,
+blast_csv2fasta :265, exonerate2fasta :274, mask_from_gff :394, convert_gff :527,
 dna2orfs :145 (the reference's version cannot run -- it calls str.translate with keyword
 arguments -- this one does what it intended, on the device).  The dispatcher (main :25-45)
 keeps the grammar but looks the function up in a table instead of eval()-ing a string.
@@ -40,6 +40,23 @@ def gff2fasta(genome_sequence, gff, from_exons="False", seq_type="nucleotide", l
     else:
         my_genome.read_gff(gff)
     print(my_genome.annotations.get_fasta('gene', seq_type=seq_type, longest=_truth(longest), genomic=_truth(genomic)))
+
+
+def convert_gff(gff, input_format, output_format):
+    """genome_tools.py:527-545 -- re-write an annotation file: input `gff3` or a read_gff preset name (anything else, e.g.
+    `gtf`, reads with the defaults), output `gff3`, `gtf` or `exon_added_gff3`.  Host-only (no sequence is touched)."""
+    presets = None if input_format == 'gff3' else input_format
+    if output_format == 'gff3':
+        gff_format = "simple gff3"
+    elif output_format == 'gtf':
+        gff_format = 'gtf'
+    elif output_format == "exon_added_gff3":
+        gff_format = "exon added gff3"
+    else:
+        print("currently only writes 'gff3' and 'gtf' format")
+        return None
+    annotations = genome.read_gff(gff, presets=presets)
+    print(genome.write_gff(annotations, gff_format))
 
 
 def blast_csv2fasta(genome_sequence, blast_csv):
@@ -265,7 +282,8 @@ def dna2orfs(fasta_location, output_file, from_atg=False, longest=False, min_orf
 
 
 FUNCTIONS = {f.__name__: f for f in (gff2fasta, cds2pep, coords2fasta, get_seq_from_fasta, exclude_from_fasta,
-                                     extract_upstream_downstream, dna2orfs, blast_csv2fasta, exonerate2fasta, mask_from_gff)}
+                                     extract_upstream_downstream, dna2orfs, blast_csv2fasta, exonerate2fasta, mask_from_gff,
+                                     convert_gff)}
 
 
 def help_func():

@@ -95,6 +95,43 @@ def py2_order_after_deepcopy(keys):
     return py2_order(py2_order(keys))
 
 
+def py2_update_order(keys):
+    """Order of an EMPTY CPython-2.7 dict after `d.update(other)` where `keys` is other's iteration order
+    (PyDict_Merge, Objects/dictobject.c): one pre-resize to the first power of two > 2*len(other) when
+    len(other)*3 >= 16, then plain insertions with no further growth."""
+    keys = list(keys)
+    n = len(keys)
+    size = 8
+    if n * 3 >= 16:
+        while size <= 2 * n:
+            size <<= 1
+    mask = size - 1
+    slots = [-1] * size
+    for idx, h in enumerate(string_hashes(keys)):
+        i = h & mask
+        if slots[i] != -1:
+            perturb = h
+            j = i
+            while True:
+                j = ((j << 2) + j + perturb + 1) & _MASK
+                perturb >>= 5
+                i = j & mask
+                if slots[i] == -1:
+                    break
+        slots[i] = idx
+    return [keys[k] for k in slots if k != -1]
+
+
+def py2_instance_attr_order(names, deepcopied=False):
+    """Iteration order of an instance __dict__ whose attributes were first assigned in the order `names`.
+    copy.deepcopy of an instance (copy.py `_deepcopy_inst` / `_reconstruct`) deep-copies the state dict
+    (re-insertion in slot order) and then `y.__dict__.update(state)`."""
+    order = py2_order(names)
+    if deepcopied:
+        order = py2_update_order(py2_order(order))
+    return order
+
+
 def reorder_dict(d, deepcopy=False):
     """Return a new dict with d's items in CPython-2.7 order (keys must be str)."""
     order = py2_order_after_deepcopy(list(d)) if deepcopy else py2_order(list(d))

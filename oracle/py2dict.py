@@ -89,3 +89,26 @@ def py2_order(keys):
 def py2_order_after_deepcopy(keys):
     """Order after `copy.deepcopy` (genome.py:415): keys re-inserted in old slot order."""
     return py2_order(py2_order(keys))
+
+
+def py2_update_order(keys):
+    """Order of an empty py2 dict after `d.update(other)`, `keys` = other's iteration order.  dictobject.c:PyDict_Merge
+    grows the target ONCE up front (to the first power of two > 2*len(other), when len(other)*3 >= 2*8) and then
+    calls insertdict per entry, which never resizes."""
+    d = Py2Dict()
+    n = len(keys)
+    if n * 3 >= MINSIZE * 2:
+        d._resize(2 * n)
+    for k in keys:
+        d._insert_clean(d.slots, d.mask, py2_string_hash(k), k)
+    return d.keys()
+
+
+def py2_instance_dict_order(names, deepcopied):
+    """Iteration order of an old-style instance's __dict__ (attributes first set in the order `names`).
+    copy.py:_deepcopy_inst deep-copies the dict (`_deepcopy_dict`: re-insertion in slot order) and then does
+    `y.__dict__.update(state)`."""
+    order = py2_order(names)
+    if deepcopied:
+        order = py2_update_order(py2_order(order))
+    return order

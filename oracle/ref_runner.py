@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import make_ref                      # noqa: E402
-from py2dict import py2_order, py2_order_after_deepcopy   # noqa: E402
+from py2dict import py2_order, py2_order_after_deepcopy, py2_instance_dict_order   # noqa: E402
 
 _genome = None
 
@@ -60,6 +60,38 @@ def gff2fasta(fasta, gff, from_exons="False", seq_type="nucleotide", longest="Fa
     else:
         my = load_genome(fasta, gff)
     return my.annotations.get_fasta('gene', seq_type=seq_type, longest=eval(longest), genomic=eval(genomic)) + "\n"
+
+
+def reorder_instance_dicts(aset, deepcopied=True):
+    """Give the set's own __dict__ and every annotation object's __dict__ the iteration order Python 2.7 leaves them
+    in (write_gff genome.py:230 iterates the former, "extended gff3" genome.py:631 / :751 the latter)."""
+    objs = [aset]
+    for val in aset.__dict__.values():
+        if type(val) == dict:
+            objs.extend(val.values())
+    for o in objs:
+        d = o.__dict__
+        order = py2_instance_dict_order(list(d), deepcopied)
+        new = {k: d[k] for k in order}
+        d.clear()
+        d.update(new)
+    return aset
+
+
+def write_gff(gff, gff_format="simple gff3", **read_gff_kwargs):
+    """genome.write_gff(genome.read_gff(gff, ...), gff_format) of the reference, Python-2.7 orders restored."""
+    g = ref()
+    aset = g.read_gff(gff, **read_gff_kwargs)
+    reorder_annotation_set(aset)
+    reorder_instance_dicts(aset, deepcopied=True)
+    return g.write_gff(aset, gff_format)
+
+
+def convert_gff(gff, input_format, output_format):
+    """stdout of genome_tools.py:527-545 (input formats that are not exec-presets only: the shim cannot rebind locals)."""
+    fmt = {"gff3": "simple gff3", "gtf": "gtf", "exon_added_gff3": "exon added gff3"}[output_format]
+    assert input_format not in ("augustus", "RepeatMasker", "CEGMA")
+    return write_gff(gff, fmt) + "\n"
 
 
 def reorder_no_deepcopy(aset):

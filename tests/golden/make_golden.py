@@ -236,6 +236,43 @@ ALPHABETS = {
 }
 
 
+GFF_FORMATS = ["simple gff3", "extended gff3", "exon added gff3", "gtf", "augustus hint CDS b2h 4", "augustus hint CDSpart M"]
+AUGUSTUS_PRESET = dict(features_to_ignore=['gene', 'transcript', 'stop_codon', 'terminal', 'internal', 'initial', 'intron',
+                                           'start_codon', 'single'],
+                       parent_field=None, parents_hierarchy=['transcript_id', 'gene_id'], IDfield=None)
+
+
+def gff_writer_cases(cases):
+    """write_gff / get_gff / convert_gff (genome.py:228-238, :616-645, :733-778; genome_tools.py:527-545).
+    A case the reference crashes on is recorded as {"raises": <exception name>}."""
+    T = REF_DATA + "/"
+    # hard-coded by the reference's own test-suite (test_data/test_suite.py:15-17)
+    cases["suite:convert_gff_minimalGFF3_gff3_gtf"] = {"cksum": 1904390924, "bytes": 226225}
+    cases["suite:convert_gff_StandardGTF_gtf_gff3"] = {"cksum": 2934568300, "bytes": 276674}
+    cases["suite:convert_gff_StandardGTF_gtf_exon_added_gff3"] = {"cksum": 2624776569, "bytes": 512324}
+
+    def put(name, fn):
+        try:
+            c, n = cksum(fn())
+            cases[name] = {"cksum": c, "bytes": n}
+        except Exception as e:            # noqa: BLE001 -- the reference's own crash is the expected behaviour
+            cases[name] = {"raises": type(e).__name__}
+
+    for f in ("StandardGTF.gtf", "minimalGFF3.gff", "transcriptlessGTF.gtf", "O.biroi_NCBIrefseq_gff3Subset.gff"):
+        for fmt in GFF_FORMATS:
+            put("gffwrite:%s:%s" % (f, fmt), lambda: ref_runner.write_gff(T + f, fmt))
+    ob = T + "O.biroi_NCBIrefseq_gff3Subset.gff"
+    for fmt in ("simple gff3", "extended gff3"):
+        put("gffwrite:obiroi_exon_based:%s" % fmt,
+            lambda: ref_runner.write_gff(ob, fmt, base_features=['exon', 'match_part', 'similarity', 'region'],
+                                         features_to_ignore=['CDS']))
+    # presets='augustus' is an exec() of these assignments (genome.py:262-268); the shim cannot rebind locals under
+    # Python 3, so the reference is run with the same values passed explicitly
+    for fmt in ("simple gff3", "gtf"):
+        put("gffwrite:StandardGTF.gtf:augustus_preset:%s" % fmt,
+            lambda: ref_runner.write_gff(T + "StandardGTF.gtf", fmt, **AUGUSTUS_PRESET))
+
+
 def kat_vectors():
     g = ref_runner.ref()
     rnd = random.Random(20261018)
@@ -284,11 +321,20 @@ def kat_vectors():
 
 def main():
     import tempfile
+    if "--only-gff-writers" in sys.argv:      # add the writer cases to the existing manifest
+        with open(os.path.join(HERE, "manifest.json")) as fh:
+            cases = json.load(fh)
+        gff_writer_cases(cases)
+        with open(os.path.join(HERE, "manifest.json"), "w") as fh:
+            json.dump(cases, fh, indent=1, sort_keys=True)
+        print("manifest now holds", len(cases), "whole-file cases")
+        return
     copy_data()
     with tempfile.TemporaryDirectory() as tmp:
         cases = whole_file_cases(tmp)
     aligner_cases(cases)
     mask_cases(cases)
+    gff_writer_cases(cases)
     with open(os.path.join(HERE, "manifest.json"), "w") as fh:
         json.dump(cases, fh, indent=1, sort_keys=True)
     with open(os.path.join(HERE, "kat.json"), "w") as fh:

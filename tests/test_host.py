@@ -252,3 +252,79 @@ def test_lpt_contig_shards():
         worst = max(sum(lens[c] for c in sh) for sh in shards)
         assert worst <= 1.03 * sum(lens) / n, (n, worst)
     assert orfs.lpt_shards([], 3) == [[], [], []]
+
+
+# ---- GFF writers / convert_gff (host-only; genome.py:228-238, :616-645, :733-778; genome_tools.py:527-545)
+
+def _stdout_of(fn, *a, **k):
+    import contextlib
+    import io
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        fn(*a, **k)
+    return buf.getvalue()
+
+
+@pytest.mark.parametrize("args,key", [
+    (("minimalGFF3.gff", "gff3", "gtf"), "suite:convert_gff_minimalGFF3_gff3_gtf"),
+    (("StandardGTF.gtf", "gtf", "gff3"), "suite:convert_gff_StandardGTF_gtf_gff3"),
+    (("StandardGTF.gtf", "gtf", "exon_added_gff3"), "suite:convert_gff_StandardGTF_gtf_exon_added_gff3"),
+])
+def test_convert_gff_reference_suite_goldens(ref_data, manifest, args, key):
+    """The three cksums the reference's own test-suite holds (test_data/test_suite.py:15-17), through the CLI grammar."""
+    from cksum import cksum
+    from magot_b200 import genome_tools
+    out = _stdout_of(genome_tools.main, ["genome_tools.py", "convert_gff", os.path.join(ref_data, args[0]), args[1], args[2]])
+    c, n = cksum(out)
+    assert {"cksum": c, "bytes": n} == manifest[key]
+
+
+def test_write_gff_all_formats_match_reference(ref_data, manifest):
+    """Every format of get_gff x every annotation fixture against the reference's own output (tests/golden/make_golden.py:
+    gff_writer_cases), including the cases where the reference raises (childless parents, gtf without a grand-parent)."""
+    from cksum import cksum
+    from magot_b200 import genome
+    keys = [k for k in manifest if k.startswith("gffwrite:") and "augustus_preset" not in k and "obiroi_exon_based" not in k]
+    assert len(keys) == 24
+    for k in keys:
+        _, f, fmt = k.split(":")
+        exp = manifest[k]
+        if "raises" in exp:
+            with pytest.raises(Exception) as ei:
+                genome.write_gff(genome.read_gff(os.path.join(ref_data, f)), fmt)
+            assert type(ei.value).__name__ == exp["raises"], k
+        else:
+            c, n = cksum(genome.write_gff(genome.read_gff(os.path.join(ref_data, f)), fmt))
+            assert {"cksum": c, "bytes": n} == exp, k
+    ob = os.path.join(ref_data, "O.biroi_NCBIrefseq_gff3Subset.gff")
+    for fmt in ("simple gff3", "extended gff3"):
+        aset = genome.read_gff(ob, base_features=['exon', 'match_part', 'similarity', 'region'], features_to_ignore=['CDS'])
+        c, n = cksum(genome.write_gff(aset, fmt))
+        assert {"cksum": c, "bytes": n} == manifest["gffwrite:obiroi_exon_based:%s" % fmt]
+
+
+def test_read_gff_presets(ref_data, manifest):
+    """presets= (genome.py:261-268): 'augustus' equals the reference run with the preset's assignments passed explicitly,
+    an unknown name (convert_gff's 'gtf') is a no-op, 'CEGMA' raises like the reference's exec of its malformed list."""
+    from cksum import cksum
+    from magot_b200 import genome
+    gtf = os.path.join(ref_data, "StandardGTF.gtf")
+    for fmt in ("simple gff3", "gtf"):
+        c, n = cksum(genome.write_gff(genome.read_gff(gtf, presets="augustus"), fmt))
+        assert {"cksum": c, "bytes": n} == manifest["gffwrite:StandardGTF.gtf:augustus_preset:%s" % fmt]
+    assert genome.write_gff(genome.read_gff(gtf, presets="gtf")) == genome.write_gff(genome.read_gff(gtf))
+    with pytest.raises(TypeError):
+        genome.read_gff(gtf, presets="CEGMA")
+
+
+def test_py2_instance_dict_order_matches_oracle_emulator():
+    import random
+    from py2dict import py2_instance_dict_order
+    from magot_b200.py2dict import py2_instance_attr_order
+    rnd = random.Random(5)
+    pool = ["ID", "seqid", "coords", "feature_type", "annotation_set", "source", "score", "phase", "gene_id", "transcript_id",
+            "parent", "strand", "child_list", "Name", "product", "Dbxref", "gbkey", "Note", "gene", "protein_id"]
+    for _ in range(200):
+        names = rnd.sample(pool, rnd.randint(1, len(pool)))
+        for dc in (False, True):
+            assert py2_instance_attr_order(names, dc) == py2_instance_dict_order(names, dc)
