@@ -254,6 +254,48 @@ def host_phases():
     return out
 
 
+def fasta_ingest_rates(device):
+    """FASTA ingest (outside every timed region): a 256 Mbp record with 60-column lines through
+    mg_genome_pack_fasta (raw bytes to the device, line ends dropped there by K0f, packed by K0) next to what the host would
+    spend only stripping the line ends (bytes.translate) and to the reference's own GenomeSequence loader (genome.py:856-877)
+    on a 1/16 sample."""
+    import numpy as np
+    from magot_b200 import engine
+    n = 256 << 20
+    rng = np.random.default_rng(3)
+    rows = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, (n // 64, 61), dtype=np.uint8)]
+    rows[:, 60] = 10
+    raw = rows.reshape(-1)
+    bases = (n // 64) * 60
+    g = engine.DeviceGenome([bases], device=device)
+    t0 = time.perf_counter()
+    g.pack_fasta(0, raw)                                           # first pass: allocates the device buffers
+    t_dev = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    g.pack_fasta(0, raw)                                           # second pass: buffers exist, pages are warm
+    t_dev2 = time.perf_counter() - t0
+    g.finalize()
+    assert g.fetch(0, bases - 120, bases) == raw[-122:].tobytes().translate(None, b"\n")
+    g.close()
+    data = raw.tobytes()
+    t0 = time.perf_counter()
+    data.translate(None, b"\r\n")
+    t_host = time.perf_counter() - t0
+    out = {"raw_bytes": int(raw.size), "pack_fasta_GBps_first": round(raw.size / t_dev / 1e9, 2),
+           "pack_fasta_GBps": round(raw.size / t_dev2 / 1e9, 2), "host_strip_only_GBps": round(raw.size / t_host / 1e9, 2)}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_runner
+        ref = ref_runner.ref()
+        sample = ">c\n" + data[:raw.size // 16].decode("latin-1")
+        t0 = time.perf_counter()
+        ref.GenomeSequence(sample)
+        out["reference_GenomeSequence_GBps"] = round(len(sample) / (time.perf_counter() - t0) / 1e9, 4)
+    except Exception as e:
+        out["reference_error"] = str(e)[:200]
+    return out
+
+
 def cpu_port_rate():
     """Single-threaded C restatement (oracle/oracle.c) on a larger sample: tight-loop CPU figure."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -592,6 +634,10 @@ def gpu_arm(args):
                     cpu["host_annotation_parse"] = host_phases()
                 except Exception as e:
                     cpu["host_annotation_parse"] = {"error": str(e)[:200]}
+                try:
+                    cpu["fasta_ingest"] = fasta_ingest_rates(local)
+                except Exception as e:
+                    cpu["fasta_ingest"] = {"error": str(e)[:200]}
             except Exception as e:
                 cpu = {"value": None, "unit": "Gbp/s", "cores": 1, "kind": "port", "sample": "failed: %s" % str(e)[:300]}
         line = {

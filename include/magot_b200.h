@@ -54,6 +54,12 @@ int mg_genome_create(int device, int64_t n_contigs, const int64_t *contig_len, m
 int mg_genome_pack(mg_genome *g, int64_t contig, int64_t offset, const uint8_t *ascii, int64_t n, void *stream);
 /* Same, from a DEVICE pointer (used when the text is produced on the device).               */
 int mg_genome_pack_device(mg_genome *g, int64_t contig, int64_t offset, const uint8_t *ascii_dev, int64_t n, void *stream);
+/* K0f: the same from the RAW body of a FASTA record (`raw` = host bytes between the header line and the next
+ * header, line ends included): CR and LF are dropped on the device by a single-pass stream compaction, every other
+ * byte is kept -- replaces `seq = seq + line.replace('\n','').replace('\r','')` (genome.py:875) so that the host
+ * never touches the sequence bytes.  The number of kept bytes must equal the contig length given to
+ * mg_genome_create (count the line ends on the host), else MG_EINVAL.                          */
+int mg_genome_pack_fasta(mg_genome *g, int64_t contig, const uint8_t *raw, int64_t n_raw, void *stream);
 /* Sort the exception list and make the genome usable by every call below.                   */
 int mg_genome_finalize(mg_genome *g, int64_t *n_exceptions_out);
 int mg_genome_destroy(mg_genome *g);

@@ -81,6 +81,9 @@ struct mg_genome {
     bool finalized = false;
     uint8_t *d_stage = nullptr;               // H2D staging for pack / fetch
     int64_t stage_cap = 0;
+    uint8_t *d_raw = nullptr;                 // raw FASTA body chunk (mg_genome_pack_fasta)
+    unsigned long long *d_strip_tmp = nullptr;    // look-back words of k_fasta_strip + the kept-byte total
+    int64_t raw_cap = 0;
     uint8_t *h_pin = nullptr;                 // pinned bounce buffer
     int64_t pin_cap = 0;
     uint8_t *d_aa4096 = nullptr;              // 4096-entry nibble-triplet -> amino acid table

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include "mg_common.cuh"
+#include "mg_lookback.cuh"
 
 // ---- error plumbing / misc API -------------------------------------------------------------------
 static thread_local char t_err[512] = "";
@@ -129,6 +130,8 @@ extern "C" int mg_genome_destroy(mg_genome *g) {
     cudaFree(g->d_exc_byte);
     cudaFree(g->d_exc_count);
     cudaFree(g->d_stage);
+    cudaFree(g->d_raw);
+    cudaFree(g->d_strip_tmp);
     cudaFree(g->d_aa4096);
     cudaFree(g->d_aa4096h);
     if (g->h_pin) cudaFreeHost(g->h_pin);
@@ -267,6 +270,108 @@ extern "C" int mg_genome_pack(mg_genome *g, int64_t contig, int64_t offset, cons
         rc = pack_device_chunk(g, g->h_contig_base[contig] + offset + done, g->d_stage, m, st);
         if (rc) return rc;
         done += m;
+    }
+    return MG_OK;
+}
+
+// ---- K0f: FASTA body -> ASCII without line ends, on the device ----------------------------------------------------------
+// Replaces `seq = seq + line.replace('\n','').replace('\r','')` (genome.py:875) for a whole record body: a stream compaction
+// that drops every CR / LF byte and keeps everything else (spaces, case, any byte: the reference keeps them too).
+// One tile = 256 threads x 16 raw bytes.  Kept bytes are ranked with a warp/block scan, the tile's base comes from the
+// decoupled look-back (single pass, tiles in ticket order), the tile's survivors are staged in shared memory and written
+// as one contiguous run.  HBM: 1 B read + <= 1 B written per raw byte; the host never touches the sequence bytes.
+#define STRIP_THREADS 256
+#define STRIP_TILE (STRIP_THREADS * 16)
+__global__ void __launch_bounds__(STRIP_THREADS) k_fasta_strip(const uint8_t *__restrict__ raw, int64_t n, unsigned long long *tmp,
+                                                                uint8_t *__restrict__ dst, int64_t *__restrict__ kept_total) {
+    __shared__ int64_t s_warp[STRIP_THREADS / 32];
+    __shared__ int64_t s_prefix;
+    __shared__ unsigned int s_tile;
+    __shared__ uint8_t s_out[STRIP_TILE];
+    const int64_t tile = mg_next_tile(tmp, &s_tile);
+    const int64_t b0 = tile * STRIP_TILE + (int64_t)threadIdx.x * 16;
+    uint32_t w[4];
+    if (b0 + 16 <= n) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(raw + b0));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+        w[0] = w[1] = w[2] = w[3] = 0x0A0A0A0Au;       // past the end: line feeds, i.e. dropped
+        for (int k = 0; b0 + k < n; k++) {
+            const uint32_t c = raw[b0 + k];
+            w[k >> 2] = (w[k >> 2] & ~(0xFFu << ((k & 3) * 8))) | (c << ((k & 3) * 8));
+        }
+    }
+    uint32_t keep = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint32_t c = (w[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
+        keep |= (uint32_t)(c != 0x0Au && c != 0x0Du) << k;
+    }
+    const int cnt = __popc(keep);
+    int64_t total;
+    const int64_t incl = mg_block_incl_scan((int64_t)cnt, s_warp, &total);
+    const int64_t prefix = mg_lookback(tmp, tile, total, &s_prefix);
+    int pos = (int)(incl - cnt);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if ((keep >> k) & 1u) s_out[pos++] = (uint8_t)(w[k >> 2] >> ((k & 3) * 8));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)total; i += STRIP_THREADS) dst[prefix + i] = s_out[i];
+    if (tile == gridDim.x - 1 && threadIdx.x == 0) *kept_total = prefix + total;
+}
+
+extern "C" int mg_genome_pack_fasta(mg_genome *g, int64_t contig, const uint8_t *raw, int64_t n_raw, void *stream) {
+    MG_REQUIRE(g != nullptr, "genome handle is NULL");
+    MG_REQUIRE(contig >= 0 && contig < g->n_contigs, "contig index out of range");
+    MG_REQUIRE(n_raw >= 0 && (n_raw == 0 || raw != nullptr), "bad FASTA body");
+    MG_CUDA(cudaSetDevice(g->device));
+    g->finalized = false;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t RAW = 64ll << 20;                   // raw bytes per trip (multiple of the tile)
+    const int64_t clen = g->h_contig_len[contig];
+    const int64_t chunk_cap = std::min<int64_t>(RAW, (n_raw + STRIP_TILE - 1) / STRIP_TILE * STRIP_TILE);
+    if (g->raw_cap < chunk_cap) {
+        if (g->d_raw) MG_CUDA(cudaFree(g->d_raw));
+        if (g->d_strip_tmp) MG_CUDA(cudaFree(g->d_strip_tmp));
+        g->d_raw = nullptr; g->d_strip_tmp = nullptr; g->raw_cap = 0;
+        MG_CUDA(cudaMalloc(&g->d_raw, chunk_cap));
+        MG_CUDA(cudaMalloc(&g->d_strip_tmp, (chunk_cap / STRIP_TILE + 4) * sizeof(unsigned long long)));
+        g->raw_cap = chunk_cap;
+    }
+    int rc = mg_ensure_stage(g, chunk_cap + 256);     // ASCII staging: up to 31 carried bytes + one stripped chunk
+    if (rc) return rc;
+    int64_t *d_kept = reinterpret_cast<int64_t *>(g->d_strip_tmp + (g->raw_cap / STRIP_TILE + 2));
+    int64_t carry = 0, done_bases = 0;
+    for (int64_t done = 0; done < n_raw || (n_raw == 0 && done == 0);) {
+        const int64_t m = std::min<int64_t>(g->raw_cap, n_raw - done);
+        int64_t kept = 0;
+        if (m > 0) {
+            const int64_t nt = (m + STRIP_TILE - 1) / STRIP_TILE;
+            MG_CUDA(cudaMemcpyAsync(g->d_raw, raw + done, m, cudaMemcpyHostToDevice, st));
+            MG_CUDA(cudaMemsetAsync(g->d_strip_tmp, 0, (nt + 1) * sizeof(unsigned long long), st));
+            k_fasta_strip<<<(unsigned)nt, STRIP_THREADS, 0, st>>>(g->d_raw, m, g->d_strip_tmp, g->d_stage + carry, d_kept);
+            MG_LAUNCH_CHECK();
+            MG_CUDA(cudaMemcpyAsync(&kept, d_kept, sizeof(kept), cudaMemcpyDeviceToHost, st));
+            MG_CUDA(cudaStreamSynchronize(st));
+        }
+        done += m;
+        const bool last = done >= n_raw;
+        const int64_t avail = carry + kept;
+        const int64_t npack = last ? avail : avail / 32 * 32;
+        if (done_bases + npack > clen || (last && done_bases + npack != clen)) {
+            mg_set_error("FASTA body of contig %lld holds %s%lld bases, the genome was created with %lld", (long long)contig,
+                         last ? "" : "more than ", (long long)(done_bases + npack), (long long)clen);
+            return MG_EINVAL;
+        }
+        if (npack > 0) {
+            rc = pack_device_chunk(g, g->h_contig_base[contig] + done_bases, g->d_stage, npack, st);
+            if (rc) return rc;
+        }
+        carry = avail - npack;
+        if (carry > 0 && npack > 0) MG_CUDA(cudaMemcpyAsync(g->d_stage, g->d_stage + npack, carry, cudaMemcpyDeviceToDevice, st));
+        done_bases += npack;
+        if (n_raw == 0) break;
     }
     return MG_OK;
 }

@@ -61,6 +61,13 @@ class DeviceGenome(object):
             if n == 0:
                 break
 
+    def pack_fasta(self, contig, raw, lo=0, hi=None):
+        """Pack contig `contig` from the RAW body of its FASTA record, raw[lo:hi] (bytes / uint8 array, line ends
+        included): CR and LF are removed on the device (K0f), the host does not copy or scan the bases."""
+        a = raw if isinstance(raw, np.ndarray) else np.frombuffer(raw, dtype=np.uint8)
+        hi = a.size if hi is None else hi
+        check(lib.mg_genome_pack_fasta(self.handle, contig, ctypes.c_void_p(a.ctypes.data + lo), hi - lo, None))
+
     def pack_device(self, contig, dev_ptr, n, offset=0, stream=None):
         check(lib.mg_genome_pack_device(self.handle, contig, offset, ctypes.c_void_p(dev_ptr), n, stream))
 

@@ -290,9 +290,12 @@ class GenomeSequence(dict):
         self._index = {}
         data = _read_all_bytes(genome_sequence)
         if data is not None:
-            names, arrays = _parse_fasta(data, truncate_names)
+            # only the headers are parsed on the host; the record bodies go to the device as they are and K0f drops
+            # the line ends there (mg_genome_pack_fasta)
+            names, spans = _scan_fasta(data, truncate_names)
+            raw = np.frombuffer(data, dtype=np.uint8)
             for name in _order(names):
-                self._pending[name] = arrays[name]
+                self._pending[name] = _RawBody(raw, *spans[name])
                 dict.__setitem__(self, name, None)
             self._build()
 
@@ -307,7 +310,10 @@ class GenomeSequence(dict):
         for dev in self._devices:
             g = engine.DeviceGenome(lens, device=dev)
             for ci, a in enumerate(arrays):
-                g.pack(ci, a)
+                if isinstance(a, _RawBody):
+                    g.pack_fasta(ci, a.raw, a.lo, a.hi)
+                else:
+                    g.pack(ci, a)
             g.finalize()
             replicas.append(g)
         self._sharded = engine.ShardedGenome(replicas)
@@ -359,34 +365,40 @@ class GenomeSequence(dict):
             self._sharded = None
 
 
-def _parse_fasta(data, truncate_names):
-    """genome.py:856-877 on a bytes buffer.  Lines end at '\\n' only; '\\r' and '\\n' are removed from
-    sequence lines, every other byte is kept; records with an empty sequence are dropped; text
-    before the first header belongs to seqid ''; a repeated header replaces the earlier record.
-    Headers are located with bytes.find and newlines stripped with bytes.translate (both run at
-    memory speed in C), so a human-size FASTA parses in seconds."""
+class _RawBody(object):
+    """Body of one FASTA record as it sits in the file: raw[lo:hi] with line ends, `size` bases without them."""
+    __slots__ = ("raw", "lo", "hi", "size")
+
+    def __init__(self, raw, lo, hi, size):
+        self.raw, self.lo, self.hi, self.size = raw, lo, hi, size
+
+
+def _scan_fasta(data, truncate_names):
+    """genome.py:856-877 without touching the sequence bytes: header discovery (bytes.find) and, per record, the span
+    of its body and its length = body bytes minus CR/LF (bytes.count).  Empty
+    records are dropped, text before the first header belongs to seqid '', a repeated header replaces the earlier
+    record but keeps its place."""
     n = len(data)
     names = []
-    arrays = {}
+    spans = {}
 
     def put(name, lo, hi):
         if hi <= lo:
             return
-        seq = data[lo:hi].translate(None, b"\r\n")
-        if not seq:
+        size = (hi - lo) - data.count(b"\n", lo, hi) - data.count(b"\r", lo, hi)
+        if size <= 0:
             return
-        if name not in arrays:
+        if name not in spans:
             names.append(name)
-        arrays[name] = np.frombuffer(seq, dtype=np.uint8)
+        spans[name] = (lo, hi, size)
 
-    # a header is a '>' at the very start of the buffer or right after a '\n'
     pos = 0 if data[:1] == b">" else data.find(b"\n>")
     if pos < 0:
         put("", 0, n)
-        return names, arrays
+        return names, spans
     if pos > 0 or data[:1] != b">":
         put("", 0, pos + 1)
-        pos += 1                                   # index of the '>'
+        pos += 1
     while pos < n:
         eol = data.find(b"\n", pos)
         if eol < 0:
@@ -397,7 +409,7 @@ def _parse_fasta(data, truncate_names):
         body_hi = n if nxt < 0 else nxt + 1
         put(seqid, min(eol + 1, n), body_hi)
         pos = n if nxt < 0 else nxt + 1
-    return names, arrays
+    return names, spans
 
 
 # ---------------------------------------------------------------------------------------------

@@ -220,6 +220,48 @@ def test_pack_fetch_roundtrip_arbitrary_bytes(mg):
     gs.close()
 
 
+@pytest.mark.gpu
+def test_pack_fasta_strips_line_ends_on_device(mg):
+    """K0f (mg_genome_pack_fasta): raw record bodies with LF / CRLF / stray CR at random places, lengths around the 16-byte
+    lane, the 4096-byte tile and the 64 MB trip (carry of < 32 bases between trips), against bytes.translate on the host."""
+    from magot_b200 import engine, _lib
+    rng = np.random.default_rng(21)
+    alpha = np.frombuffer(b"ACGTacgtNn-RYKM *x", dtype=np.uint8)
+    raws = []
+    for n in [0, 1, 2, 15, 16, 17, 31, 32, 33, 4095, 4096, 4097, 8191, 70001, 300000]:
+        a = alpha[rng.integers(0, alpha.size, n)].copy()
+        k = rng.integers(0, n + 1)
+        if n:
+            a[rng.integers(0, n, k // 7)] = 10
+            a[rng.integers(0, n, k // 31)] = 13
+        raws.append(a)
+    raws.append(np.full(5000, 10, dtype=np.uint8))                     # nothing survives
+    raws.append(np.frombuffer(b"ACGT\r\n" * 3000 + b"AC", dtype=np.uint8))
+    big = alpha[rng.integers(0, 4, (64 << 20) + 4096 + 77)].copy()      # two trips
+    big[60::61] = 10
+    big[(64 << 20) - 40:(64 << 20) + 40:3] = 10                         # line ends right at the trip boundary
+    raws.append(big)
+    want = [a.tobytes().translate(None, b"\r\n") for a in raws]
+    g = engine.DeviceGenome([len(w) for w in want], device=0)
+    for i, a in enumerate(raws):
+        g.pack_fasta(i, a)
+    g.finalize()
+    for i, w in enumerate(want):
+        if len(w) <= 400000:
+            assert g.fetch(i, 0, len(w)) == w, i
+        else:
+            for lo in (0, 12345, (64 << 20) - 2_200_000, len(w) - 70000):
+                assert g.fetch(i, lo, lo + 70000) == w[lo:lo + 70000], (i, lo)
+    # a body whose number of bases differs from the declared contig length is refused
+    g2 = engine.DeviceGenome([10], device=0)
+    with pytest.raises(_lib.MagotError):
+        g2.pack_fasta(0, np.frombuffer(b"ACGT\nACGT\n", dtype=np.uint8))
+    with pytest.raises(_lib.MagotError):
+        g2.pack_fasta(0, np.frombuffer(b"ACGTACGTACGT\n", dtype=np.uint8))
+    g2.close()
+    g.close()
+
+
 # ---- synthetic twins of configs 3/4 against the C oracle --------------------------------------------------------
 
 def _oracle_products(contigs, tbl):

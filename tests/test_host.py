@@ -102,21 +102,32 @@ def test_read_gff_dedup_names(ref_data):
     assert a.transcript == {}
 
 
-def test_parse_fasta_matches_oracle(ref_data, tmp_path):
+def _bodies(data, names, spans):
+    """What K0f leaves of every record body: CR / LF removed, everything else kept."""
+    return {n: data[spans[n][0]:spans[n][1]].translate(None, b"\r\n").decode("latin-1") for n in names}
+
+
+def test_scan_fasta_matches_oracle(ref_data, tmp_path):
+    """Header discovery, record rules and lengths of the host FASTA scan (the bodies themselves are stripped on the device)."""
     for text in [">a desc here\nACGT\nacgtNN\n>b\n\n>c\r\nAC GT\r\nRYK-*\n>a desc here\nTTTT\n", "ACGT\n>x\nAC\n", ">only\n", "",
-                 ">t1 x\nAAAA\n>t2\tz\nCC\rCC\n"]:
-        names, arrays = genome._parse_fasta(text.encode("latin-1"), False)
+                 ">t1 x\nAAAA\n>t2\tz\nCC\rCC\n", ">e\n\r\n\n>f\nA", "\n\n>g\nAC\n>h"]:
+        data = text.encode("latin-1")
+        names, spans = genome._scan_fasta(data, False)
         seqs, order = mo.read_fasta(text) if text else ({}, [])
-        assert {n: arrays[n].tobytes().decode("latin-1") for n in names} == seqs
+        got = _bodies(data, names, spans)
+        assert got == seqs
+        assert all(spans[n][2] == len(seqs[n]) for n in names)
         assert py2dict.py2_order(names) == order
-    names, arrays = genome._parse_fasta(b">t1 x\nAAAA\n>t2\tz\nCC\n", True)
+    names, spans = genome._scan_fasta(b">t1 x\nAAAA\n>t2\tz\nCC\n", True)
     assert names == ["t1", "t2"]
     path = os.path.join(ref_data, "O.biroi_refseqGenomeSubset.fasta")
     with open(path, "rb") as fh:
-        names, arrays = genome._parse_fasta(fh.read(), False)
+        data = fh.read()
+    names, spans = genome._scan_fasta(data, False)
     seqs, order = mo.read_fasta(path)
     assert py2dict.py2_order(names) == order
-    assert all(arrays[n].tobytes().decode("latin-1") == seqs[n] for n in names)
+    assert _bodies(data, names, spans) == {n: seqs[n] for n in names}
+    assert all(spans[n][2] == len(seqs[n]) for n in names)
 
 
 class _FakeGS(object):
