@@ -143,6 +143,12 @@ int mg_revcomp(int device, const uint8_t *in_host, int64_t n, uint8_t *out_host,
 int mg_translate_ascii(int device, const uint8_t *in_host, const int64_t *off, int64_t n_seq,
                        int frame, int minus, int trimX, uint8_t *out_host, int64_t out_cap,
                        int64_t *out_off, int64_t *out_len, void *stream);
+/* Same with the caller's codon table: codon64[16*b0 + 4*b1 + b2] (A=0 C=1 G=2 T=3) is the byte emitted for the codon
+ * b0 b1 b2 ('X' where the library has no entry) -- Sequence.translate(library=...) (genome.py:795, :814-817).
+ * codon64 == NULL selects the reference's default table.                                      */
+int mg_translate_ascii_table(int device, const uint8_t *codon64, const uint8_t *in_host, const int64_t *off, int64_t n_seq,
+                             int frame, int minus, int trimX, uint8_t *out_host, int64_t out_cap, int64_t *out_off,
+                             int64_t *out_len, void *stream);
 
 /* ---- K4: six-frame translation + ORF scan -- replaces Sequence.get_orfs (genome.py:824-851)
  * over whole contigs [contig_lo, contig_hi).  Streams are visited in the reference's order

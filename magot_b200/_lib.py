@@ -64,6 +64,7 @@ SIGNATURES = {
     "mg_emit_prot_host": (_i32, [_vp, _vp, _vp]),
     "mg_revcomp": (_i32, [_i32, _vp, _i64, _vp, _vp]),
     "mg_translate_ascii": (_i32, [_i32, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "mg_translate_ascii_table": (_i32, [_i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
     "mg_sixframe_count": (_i32, [_vp, _i64, _i64, _i64, _pi64, _pi64, _vp]),
     "mg_sixframe_count_list": (_i32, [_vp, _i64, _vp, _i64, _pi64, _pi64, _vp]),
     "mg_sixframe_emit": (_i32, [_vp, _vp, _vp, _vp]),

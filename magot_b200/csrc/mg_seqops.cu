@@ -164,9 +164,9 @@ extern "C" int mg_revcomp(int device, const uint8_t *in_host, int64_t n, uint8_t
     return MG_OK;
 }
 
-extern "C" int mg_translate_ascii(int device, const uint8_t *in_host, const int64_t *off, int64_t n_seq, int frame,
-                                  int minus, int trimX, uint8_t *out_host, int64_t out_cap, int64_t *out_off,
-                                  int64_t *out_len, void *stream) {
+extern "C" int mg_translate_ascii_table(int device, const uint8_t *codon64, const uint8_t *in_host, const int64_t *off,
+                                        int64_t n_seq, int frame, int minus, int trimX, uint8_t *out_host, int64_t out_cap,
+                                        int64_t *out_off, int64_t *out_len, void *stream) {
     MG_REQUIRE(n_seq >= 0 && off != nullptr && out_off != nullptr, "bad arguments");
     MG_REQUIRE(frame >= 0 && frame <= 2, "frame must be 0, 1 or 2");
     int rc = check_device(device);
@@ -178,8 +178,10 @@ extern "C" int mg_translate_ascii(int device, const uint8_t *in_host, const int6
     MG_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t *aa = nullptr;
-    rc = get_aa_table(device, &aa);
-    if (rc) return rc;
+    if (codon64 == nullptr) {
+        rc = get_aa_table(device, &aa);
+        if (rc) return rc;
+    }
     const int64_t cap = (n + 2) / 3 + n_seq + 16;
     const int64_t scan_tmp = mg_scan_tmp_elems(n_seq) + 2;
     // one arena: in | off | out_off | out_len | len32 | drop | scan tmp | out
@@ -187,7 +189,16 @@ extern "C" int mg_translate_ascii(int device, const uint8_t *in_host, const int6
     const int64_t b_in = al(n + 16), b_off = al((n_seq + 1) * 8), b_len = al(n_seq * 8), b_l32 = al(n_seq * 4),
                   b_drop = al(n_seq), b_tmp = al(scan_tmp * 8), b_out = al(cap + 16);
     uint8_t *d = nullptr;
-    MG_CUDA(cudaMallocAsync((void **)&d, b_in + 2 * b_off + b_len + b_l32 + b_drop + b_tmp + b_out, st));
+    MG_CUDA(cudaMallocAsync((void **)&d, b_in + 2 * b_off + b_len + b_l32 + b_drop + b_tmp + b_out + 4096, st));
+    if (codon64 != nullptr) {                         // caller's codon table (Sequence.translate(library=...), genome.py:795)
+        uint8_t t[4096];
+        for (int i = 0; i < 4096; i++) {
+            const int n0 = i & 15, n1 = (i >> 4) & 15, n2 = (i >> 8) & 15;
+            t[i] = (n0 >= 8 || n1 >= 8 || n2 >= 8) ? 'X' : codon64[(n0 & 3) * 16 + (n1 & 3) * 4 + (n2 & 3)];
+        }
+        aa = d + b_in + 2 * b_off + b_len + b_l32 + b_drop + b_tmp + b_out;
+        MG_CUDA(cudaMemcpyAsync(aa, t, 4096, cudaMemcpyHostToDevice, st));   // pageable source: staged before the call returns
+    }
     uint8_t *d_in = d;
     int64_t *d_off = (int64_t *)(d_in + b_in);
     int64_t *d_ooff = (int64_t *)((uint8_t *)d_off + b_off);
@@ -221,4 +232,11 @@ extern "C" int mg_translate_ascii(int device, const uint8_t *in_host, const int6
     }
     MG_CUDA(cudaFreeAsync(d, st));
     return MG_OK;
+}
+
+extern "C" int mg_translate_ascii(int device, const uint8_t *in_host, const int64_t *off, int64_t n_seq, int frame,
+                                  int minus, int trimX, uint8_t *out_host, int64_t out_cap, int64_t *out_off,
+                                  int64_t *out_len, void *stream) {
+    return mg_translate_ascii_table(device, nullptr, in_host, off, n_seq, frame, minus, trimX, out_host, out_cap, out_off, out_len,
+                                    stream);
 }

@@ -133,7 +133,29 @@ def _device():
     return (DEFAULT_DEVICES or [0])[0]
 
 
-def _translate_many(seqs, frame=0, strand='+', trimX=True):
+def _codon_table(library):
+    """A caller's codon dict (genome.py:795 `library`) as the 64-byte table of mg_translate_ascii_table.  The reference
+    looks up the UPPER-CASED triplet and emits 'X' on a KeyError, so keys that are not upper case or longer than three
+    letters can never match and are ignored (1- and 2-letter keys can match the leading fragment of frames 1 and 2, see
+    _translate_many); what the device table cannot express is refused: values that are not one byte, and keys that
+    contain upper-case symbols other than A, C, G, T (the device path folds all of those into one class)."""
+    table = bytearray(b"X" * 64)
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    for key, value in library.items():
+        if not isinstance(key, str) or len(key) != 3 or key != key.upper():
+            continue
+        if any(ch not in code for ch in key):
+            raise NotImplementedError("codon library key %r: only A/C/G/T codons are supported on the device" % (key,))
+        if not isinstance(value, str) or len(value.encode("latin-1")) != 1:
+            raise NotImplementedError("codon library value %r: only one-byte residues are supported on the device" % (value,))
+        table[16 * code[key[0]] + 4 * code[key[1]] + code[key[2]]] = value.encode("latin-1")[0]
+    return bytes(table)
+
+
+_RC_SMALL = {'a': 't', 't': 'a', 'g': 'c', 'c': 'g', 'A': 'T', 'T': 'A', 'G': 'C', 'C': 'G', 'n': 'n', 'N': 'N', '-': '-'}
+
+
+def _translate_many(seqs, frame=0, strand='+', trimX=True, library=None):
     """Sequence.translate on a batch of byte strings in one launch; returns list of str | None."""
     import ctypes
     n_seq = len(seqs)
@@ -143,6 +165,11 @@ def _translate_many(seqs, frame=0, strand='+', trimX=True):
         raise ValueError("frame must be 0, 1 or 2")
     if strand not in ('+', '-'):
         raise UnboundLocalError("local variable 'seq' referenced before assignment")   # genome.py:806-810
+    table = None if library is None else _codon_table(library)
+    # In frames 1 and 2 the reference first looks up the 1- resp. 2-base fragment before the first full codon
+    # (genome.py:811-817, normally a KeyError -> 'X').  A library with such a short key answers it: the device then runs
+    # without trimX and the first residue is patched here from the fragment (at most two bases per sequence).
+    short_keys = library is not None and frame > 0 and any(isinstance(k, str) and len(k) == frame and k == k.upper() for k in library)
     lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=n_seq)
     off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
     data = np.frombuffer(b"".join(seqs), dtype=np.uint8)
@@ -152,17 +179,27 @@ def _translate_many(seqs, frame=0, strand='+', trimX=True):
     out_off = np.zeros(n_seq + 1, dtype=np.int64)
     out_len = np.zeros(n_seq, dtype=np.int64)
     _lib.require_device(_device())
-    _lib.check(_lib.lib.mg_translate_ascii(_device(), ctypes.c_void_p(data.ctypes.data) if total else None,
-                                           ctypes.c_void_p(off.ctypes.data), n_seq, frame, 1 if strand == '-' else 0,
-                                           1 if trimX else 0, ctypes.c_void_p(out.ctypes.data), cap,
-                                           ctypes.c_void_p(out_off.ctypes.data), ctypes.c_void_p(out_len.ctypes.data), None))
+    _lib.check(_lib.lib.mg_translate_ascii_table(_device(), table, ctypes.c_void_p(data.ctypes.data) if total else None,
+                                                 ctypes.c_void_p(off.ctypes.data), n_seq, frame, 1 if strand == '-' else 0,
+                                                 1 if (trimX and not short_keys) else 0, ctypes.c_void_p(out.ctypes.data), cap,
+                                                 ctypes.c_void_p(out_off.ctypes.data), ctypes.c_void_p(out_len.ctypes.data), None))
     buf = out.tobytes()
     res = []
     for i in range(n_seq):
         if out_len[i] < 0:
             res.append(None)
-        else:
-            res.append(buf[out_off[i]:out_off[i + 1]].decode("latin-1"))
+            continue
+        r = buf[out_off[i]:out_off[i + 1]].decode("latin-1")
+        if short_keys:
+            s = seqs[i].decode("latin-1")
+            if strand == '-':
+                frag = "".join(_RC_SMALL.get(c, 'n') for c in reversed(s[len(s) - 2 * frame:len(s) - frame]))
+            else:
+                frag = s[frame:2 * frame]
+            r = library.get(frag.upper(), 'X') + r[1:]
+            if trimX and r[0] == 'X':
+                r = r[1:]
+        res.append(r)
     return res
 
 
@@ -183,10 +220,8 @@ class Sequence(str):
 
     def translate(self, library=None, frame=0, strand='+', trimX=True):
         """genome.py:795-822 with the reference's frame quirk; returns None when len <= 2 + frame.
-        Only the reference's default codon table (NCBI table 1) is implemented on the device."""
-        if library is not None:
-            raise NotImplementedError("custom codon libraries are not supported by the device path")
-        return _translate_many([self.encode("latin-1")], frame=frame, strand=strand, trimX=trimX)[0]
+        `library` = a codon -> residue dict (default: the reference's table, NCBI table 1), see _codon_table."""
+        return _translate_many([self.encode("latin-1")], frame=frame, strand=strand, trimX=trimX, library=library)[0]
 
     def get_orfs(self, longest=False, strand='both', from_atg=False):
         """genome.py:824-851 (the `strand` argument is shadowed in the reference and ignored)."""

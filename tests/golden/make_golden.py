@@ -273,6 +273,36 @@ def gff_writer_cases(cases):
             lambda: ref_runner.write_gff(T + "StandardGTF.gtf", fmt, **AUGUSTUS_PRESET))
 
 
+def library_vectors():
+    """Sequence.translate(library=...) (genome.py:795, :814-817) with caller-supplied codon dicts, run by the reference:
+    the vertebrate mitochondrial code, a library with only three entries (everything else -> 'X'), and one whose extra
+    keys can never match an upper-cased triplet (lower case, wrong length)."""
+    g = ref_runner.ref()
+    rnd = random.Random(77)
+    std = dict(zip([a + b + c for a in "TCAG" for b in "TCAG" for c in "TCAG"],
+                   "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"))
+    mito = dict(std, AGA="*", AGG="*", ATA="M", TGA="W")
+    sparse = {"ATG": "m", "TAA": "#", "GGG": "X"}
+    odd = dict(std, atg="?", AT="?", ATGA="?", TTT="f")
+    libs = {"mito": mito, "sparse": sparse, "odd_keys": odd}
+    seqs = ["", "AT", "ATG", "ATGA", "NNNATGAGATAA", "atgagaTGAata", "TTTtttTTNAGG"]
+    for alpha in ("ACGT", "ACGTacgtNn-RY"):
+        for n in (3, 7, 32, 100, 999):
+            seqs.append("".join(rnd.choice(alpha) for _ in range(n)))
+    out = {"libraries": libs, "vectors": []}
+    for lname, lib in libs.items():
+        for s in seqs:
+            for frame in (0, 1, 2):
+                for strand in "+-":
+                    for trimX in (True, False):
+                        try:
+                            r = g.Sequence(s).translate(library=lib, frame=frame, strand=strand, trimX=trimX)
+                        except IndexError:
+                            r = "!IndexError"
+                        out["vectors"].append([lname, s, frame, strand, trimX, r])
+    return out
+
+
 def kat_vectors():
     g = ref_runner.ref()
     rnd = random.Random(20261018)
@@ -321,6 +351,14 @@ def kat_vectors():
 
 def main():
     import tempfile
+    if "--only-library-kat" in sys.argv:      # add the custom-codon-table vectors to the existing kat.json
+        with open(os.path.join(HERE, "kat.json")) as fh:
+            kat = json.load(fh)
+        kat["translate_library"] = library_vectors()
+        with open(os.path.join(HERE, "kat.json"), "w") as fh:
+            json.dump(kat, fh, indent=0)
+        print("kat.json: +", len(kat["translate_library"]["vectors"]), "library vectors")
+        return
     if "--only-gff-writers" in sys.argv:      # add the writer cases to the existing manifest
         with open(os.path.join(HERE, "manifest.json")) as fh:
             cases = json.load(fh)
@@ -338,7 +376,9 @@ def main():
     with open(os.path.join(HERE, "manifest.json"), "w") as fh:
         json.dump(cases, fh, indent=1, sort_keys=True)
     with open(os.path.join(HERE, "kat.json"), "w") as fh:
-        json.dump(kat_vectors(), fh, indent=0)
+        kat = kat_vectors()
+        kat["translate_library"] = library_vectors()
+        json.dump(kat, fh, indent=0)
     print("wrote", len(cases), "whole-file cases")
 
 

@@ -46,6 +46,21 @@ def test_kat_translate_all_frames(mg, kat):
         assert mg.Sequence(s).translate(frame=frame, strand=strand, trimX=trimx) == r, (s[:30], frame, strand, trimx)
 
 
+def test_kat_translate_custom_library(mg, kat):
+    """Sequence.translate(library=...) against the reference's own answers (tests/golden/make_golden.py:library_vectors)."""
+    libs = kat["translate_library"]["libraries"]
+    n = 0
+    for lname, s, frame, strand, trimx, r in kat["translate_library"]["vectors"]:
+        if r == "!IndexError":
+            continue
+        assert mg.Sequence(s).translate(library=libs[lname], frame=frame, strand=strand, trimX=trimx) == r, (lname, s[:30], frame, strand)
+        n += 1
+    assert n > 500
+    for bad in ({"ATN": "Q"}, {"ATG": "Met"}):
+        with pytest.raises(NotImplementedError):
+            mg.Sequence("ATGATG").translate(library=bad)
+
+
 def test_kat_get_orfs(mg, kat):
     for s, mode, r in kat["get_orfs"][:90]:
         if mode == "longest":
