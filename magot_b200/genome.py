@@ -619,9 +619,35 @@ class AnnotationSet(object):
             idx.update(self.__dict__[name])
         return idx
 
+    def get_seqid(self, seqid):
+        """genome.py:550-559 -- a new AnnotationSet holding the features that sit on `seqid` (same objects), one table
+        per table of this set; features are filed under their own feature_type."""
+        seqid_annotation_set = AnnotationSet()
+        for name in self._dict_names():
+            setattr(seqid_annotation_set, name, {})
+            for feature, feature_obj in self.__dict__[name].items():
+                if feature_obj.seqid == seqid:
+                    getattr(seqid_annotation_set, feature_obj.feature_type)[feature] = feature_obj
+        for name in seqid_annotation_set._dict_names():
+            tbl = seqid_annotation_set.__dict__[name]
+            seqid_annotation_set.__dict__[name] = {k: tbl[k] for k in _order(list(tbl))}
+        return seqid_annotation_set
+
+    def get_all_seqids(self):
+        """genome.py:561-567 -- list(set(...)) of every feature's seqid, in the order a Python-2.7 set iterates
+        (same table discipline as the 2.7 dict: setobject.c set_add_entry / set_table_resize)."""
+        seen = {}
+        for name in self._dict_names():
+            for feature_obj in self.__dict__[name].values():
+                seen.setdefault(feature_obj.seqid, None)
+        return _order(list(seen))
+
     def read_gff(self, gff, *args, **kwargs):
         kwargs["annotation_set_to_modify"] = self
         read_gff(gff, *args, **kwargs)
+
+    def read_cegma_gff(self, cegma_gff):
+        read_cegma_gff(cegma_gff, annotation_set_to_modify=self)
 
     def read_exonerate(self, exonerate_output):
         read_exonerate(exonerate_output, annotation_set_to_modify=self)
@@ -842,6 +868,13 @@ def read_gff(gff, annotation_set_to_modify=None, base_features=['CDS', 'match_pa
         return annotation_set
 
 
+def read_cegma_gff(cegma_gff, annotation_set_to_modify=None):
+    """genome.py:418-422.  The reference's CEGMA preset text is malformed, so this raises TypeError there and here."""
+    annotation_set = read_gff(cegma_gff, annotation_set_to_modify=annotation_set_to_modify, presets="CEGMA")
+    if annotation_set_to_modify is None:
+        return annotation_set
+
+
 def _py2_reorder(annotation_set):
     """Leave every feature dict in the order a CPython-2.7 dict would iterate after these insertions (no deepcopy on
     the read_blast_csv / read_exonerate paths: both fill the set they are given, genome.py:88-120, :425-499)."""
@@ -1023,7 +1056,8 @@ class Genome(object):
                 self.annotations = read_exonerate(annotations)
                 self.annotations.genome = self
             elif annotation_format == 'cegma_gff':
-                raise NotImplementedError("annotation_format 'cegma_gff' needs read_gff presets (Python-2 exec), out of scope")
+                self.annotations = read_cegma_gff(annotations)
+                self.annotations.genome = self
         else:
             self.annotations = annotations
 
@@ -1044,11 +1078,7 @@ class Genome(object):
             for seqid in self.genome_sequence:
                 seqid_list.append(seqid)
         if self.annotations is not None and from_annotations:
-            seen = set()
-            for name in self.annotations._dict_names():
-                for feature in self.annotations.__dict__[name].values():
-                    seen.add(feature.seqid)
-            for seqid in seen:
+            for seqid in self.annotations.get_all_seqids():
                 if seqid not in seqid_list:
                     seqid_list.append(seqid)
                     warning = True
@@ -1069,6 +1099,14 @@ class Genome(object):
             self.annotations.read_exonerate(exonerate_output)
         else:
             self.annotations = read_exonerate(exonerate_output)
+            self.annotations.genome = self
+
+    def read_cegma_gff(self, cegma_gff):
+        """genome.py:963-968"""
+        if getattr(self, "annotations", None) is not None:
+            self.annotations.read_cegma_gff(cegma_gff)
+        else:
+            self.annotations = read_cegma_gff(cegma_gff)
             self.annotations.genome = self
 
     def read_blast_csv(self, blast_csv, hierarchy=['match', 'match_part'], source='blast', find_truncated_locname=False):

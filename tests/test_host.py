@@ -339,3 +339,23 @@ def test_py2_instance_dict_order_matches_oracle_emulator():
         names = rnd.sample(pool, rnd.randint(1, len(pool)))
         for dc in (False, True):
             assert py2_instance_attr_order(names, dc) == py2_instance_dict_order(names, dc)
+
+
+def test_annotation_set_seqid_helpers_and_cegma(ref_data):
+    """AnnotationSet.get_all_seqids / get_seqid (genome.py:550-567), Genome.get_seqids(from_annotations=True) (:935-948) and
+    read_cegma_gff (:418-422: the reference's CEGMA preset text cannot be exec'd, TypeError)."""
+    a = genome.read_gff(os.path.join(ref_data, "O.biroi_NCBIrefseq_gff3Subset.gff"))
+    ids = a.get_all_seqids()
+    first_seen = list(dict.fromkeys(o.seqid for n in a._dict_names() for o in a.__dict__[n].values()))
+    assert ids == oracle_py2.py2_order(first_seen) and len(ids) == 6
+    sub = a.get_seqid(ids[0])
+    for n in a._dict_names():
+        want = [k for k, o in a.__dict__[n].items() if o.seqid == ids[0]]
+        assert sorted(sub.__dict__[n]) == sorted(want)
+        assert list(sub.__dict__[n]) == oracle_py2.py2_order(want)
+        assert all(sub.__dict__[n][k] is a.__dict__[n][k] for k in want)
+    my = genome.Genome.__new__(genome.Genome)
+    my.genome_sequence, my.annotations = None, a
+    assert my.get_seqids(from_annotations=True) == ids
+    with pytest.raises(TypeError):
+        genome.read_cegma_gff(os.path.join(ref_data, "StandardGTF.gtf"))
