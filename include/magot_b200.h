@@ -78,6 +78,16 @@ int mg_genome_fetch(mg_genome *g, int64_t contig, int64_t lo, int64_t hi, int mi
 int mg_genome_mask(mg_genome *g, int64_t n_intervals, const int32_t *contig, const int64_t *lo, const int64_t *hi,
                    int hard, int upper_first, void *stream);
 
+/* ---- K6: per-base flags and sliding-window sums -- the device side of position_dic (genome.py:981-1100).
+ * mg_genome_at_flags: out_host[i] = 1 where base lo+i of `contig` is one of "ATat", else 0
+ *   (position_dic.at_content, genome.py:1030-1034); lo must be a multiple of 8.
+ * mg_window_sums: sums_host[k] = sum(values[k*jump : k*jump + window]) for k < n_windows, slices clamped at n like
+ *   numpy's (numpy.sum at genome.py:1055) -- one single-pass prefix scan (warp/block scans + decoupled look-back) and
+ *   one gather per window instead of n_windows * window additions.  elem_size 1 = uint8 / numpy bool, 8 = int64.  */
+int mg_genome_at_flags(mg_genome *g, int64_t contig, int64_t lo, int64_t hi, uint8_t *out_host, void *stream);
+int mg_window_sums(int device, const void *values_host, int elem_size, int64_t n, int64_t window, int64_t jump,
+                   int64_t n_windows, int64_t *sums_host, void *stream);
+
 /* ---- K1: interval tables -- replaces the per-child work of ParentAnnotation.get_fasta
  * (genome.py:687-705) and the slice arithmetic of BaseAnnotation.get_seq (genome.py:603-608).
  * A plan is a list of n_rec output records.  Record r owns segments

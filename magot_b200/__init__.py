@@ -9,6 +9,6 @@ there is no CPU fallback.
 from . import _lib  # noqa: F401  (fails loudly when the CUDA library has not been built)
 from . import genome  # noqa: F401
 from .genome import (Sequence, GenomeSequence, Genome, AnnotationSet, ParentAnnotation,  # noqa: F401
-                     BaseAnnotation, read_gff)
+                     BaseAnnotation, read_gff, write_gff, position_dic)
 
 __version__ = "0.1.0"

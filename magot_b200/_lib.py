@@ -50,6 +50,8 @@ SIGNATURES = {
     "mg_genome_finalize": (_i32, [_vp, _pi64]),
     "mg_genome_destroy": (_i32, [_vp]),
     "mg_genome_bytes": (_i64, [_vp]),
+    "mg_genome_at_flags": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "mg_window_sums": (_i32, [_i32, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp]),
     "mg_genome_fetch": (_i32, [_vp, _i64, _i64, _i64, _i32, _vp, _vp]),
     "mg_plan_create": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _pp]),
     "mg_plan_destroy": (_i32, [_vp]),

@@ -1,5 +1,5 @@
 // mg_lookback.cuh -- block-level inclusive scan and decoupled look-back across tiles (single-pass prefix sums).
-// Tile status words live in st[0..n_tile) as (status << 62) | value: status 1 = the tile's own sum, 2 = inclusive prefix up
+// Tile status words live in st[0..n_tile) as (status << 62) | (value as a 62-bit two's complement number): status 1 = the tile's own sum, 2 = inclusive prefix up
 // to and including the tile; tmp[0] is a ticket counter that hands out tiles in launch order, so a tile only ever waits
 // for tiles that are already running.  tmp[] must be zeroed before the launch.
 #pragma once
@@ -47,7 +47,7 @@ __device__ __forceinline__ int64_t mg_next_tile(unsigned long long *tmp, unsigne
 // Publishes this tile's sum and returns the sum of all earlier tiles (whole block must call; ends with a barrier).
 __device__ __forceinline__ int64_t mg_lookback(unsigned long long *tmp, int64_t tile, int64_t total, int64_t *s_prefix) {
     volatile unsigned long long *st = tmp + 1;
-    if (threadIdx.x == 0) st[tile] = (tile == 0 ? MG_ST_PREFIX : MG_ST_SUM) | (unsigned long long)total;
+    if (threadIdx.x == 0) st[tile] = (tile == 0 ? MG_ST_PREFIX : MG_ST_SUM) | ((unsigned long long)total & ~MG_ST_MASK);
     if (threadIdx.x < 32) {                                     // warp 0 looks back over 32 predecessors at a time
         int64_t prefix = 0;
         int64_t j = tile - 1 - (int64_t)threadIdx.x;
@@ -56,7 +56,7 @@ __device__ __forceinline__ int64_t mg_lookback(unsigned long long *tmp, int64_t 
             if (j >= 0) { do { w = st[j]; } while ((w & MG_ST_MASK) == 0); }
             const unsigned int done = __ballot_sync(0xffffffffu, (w & MG_ST_MASK) == MG_ST_PREFIX);
             const int first = done ? __ffs(done) - 1 : 32;      // nearest predecessor that already has its inclusive prefix
-            int64_t add = (int)threadIdx.x <= first ? (int64_t)(w & ~MG_ST_MASK) : 0;
+            int64_t add = (int)threadIdx.x <= first ? ((int64_t)(w << 2) >> 2) : 0;   // 62-bit two's complement: sums may be negative
 #pragma unroll
             for (int d = 16; d; d >>= 1) add += __shfl_xor_sync(0xffffffffu, add, d);
             prefix += add;
@@ -64,7 +64,7 @@ __device__ __forceinline__ int64_t mg_lookback(unsigned long long *tmp, int64_t 
             j -= 32;
         }
         if (threadIdx.x == 0) {
-            if (tile > 0) st[tile] = MG_ST_PREFIX | (unsigned long long)(prefix + total);
+            if (tile > 0) st[tile] = MG_ST_PREFIX | ((unsigned long long)(prefix + total) & ~MG_ST_MASK);
             *s_prefix = prefix;
         }
     }

@@ -1026,6 +1026,195 @@ def read_blast_csv(blast_csv, annotation_set_to_modify=None, hierarchy=['match',
     if annotation_set_to_modify is None:
         return annotation_set
 
+# ---------------------------------------------------------------------------------------------
+# position_dic (genome.py:981-1100): per-base arrays; AT content and window sums run on the device (K6)
+# ---------------------------------------------------------------------------------------------
+
+class position_dic(dict):
+    """seqid -> numpy array with one element per base (genome.py:981).  The arrays live on the host, as in the reference
+    (callers index and assign them directly); `at_content` reads the packed genome on the device and
+    `sliding_window_calculate` sums windows through a device prefix scan instead of one numpy.sum per window."""
+
+    def __init__(self, genome_sequence, dtype=bool):
+        seqids = list(genome_sequence)
+        for seqid in _order(seqids):                 # a position_dic is a Python-2.7 dict itself: its own slot order
+            self[seqid] = np.zeros(len(genome_sequence[seqid]), dtype=dtype)
+
+    @staticmethod
+    def _positions(arr, coords):
+        """Index array of `for position in range(coords[0] - 1, coords[1])` on a numpy array, up to the first position
+        numpy would refuse (negative positions wrap like numpy's), and that position (or None)."""
+        n = len(arr)
+        lo, hi = coords[0] - 1, coords[1]
+        bad = None
+        if lo < -n:
+            bad, hi = lo, lo
+        elif hi > n:
+            bad, hi = max(n, lo), max(n, lo)
+        return np.arange(lo, max(hi, lo)), bad, n
+
+    def fill_from_annotations(self, annotation_set, feature, fill_type="coords", fill_with="1"):
+        """genome.py:986-1004.  accepts "start" and "coords" for fill_type; fill_with is evaluated like the reference's
+        eval(), once per annotation unless it mentions `position`."""
+        table = getattr(annotation_set, feature)
+        for annotation in table:
+            annotation_obj = table[annotation]
+            seqid = annotation_obj.seqid
+            coords = annotation_obj.get_coords()
+            try:
+                parent = annotation_obj.parent
+            except Exception:
+                parent = None
+            ID = annotation_obj.ID
+            scope = dict(globals())
+            scope.update(self=self, annotation_set=annotation_set, feature=feature, fill_type=fill_type, fill_with=fill_with,
+                         annotation=annotation, annotation_obj=annotation_obj, seqid=seqid, coords=coords, parent=parent, ID=ID,
+                         numpy=np)
+            if fill_type == "coords":
+                arr = self[seqid]
+                idx, bad, n = self._positions(arr, coords)
+                if "position" in fill_with:
+                    for position in idx.tolist():
+                        scope["position"] = position
+                        arr[position] = eval(fill_with, scope)
+                elif idx.size:
+                    arr[idx] = eval(fill_with, scope)
+                if bad is not None:
+                    raise IndexError("index %d is out of bounds for axis 0 with size %d" % (bad, n))
+            elif fill_type == "start":
+                scope["position"] = None
+                self[seqid][coords[0] - 1] = eval(fill_with, scope)
+
+    def count_from_annotations(self, annotation_set, feature):
+        """genome.py:1006-1027 -- [featureID, positions equal to 0, positions equal to 1] per annotation."""
+        count_list = []
+        table = getattr(annotation_set, feature)
+        for annotation in table:
+            annotation_obj = table[annotation]
+            arr = self[annotation_obj.seqid]
+            idx, bad, n = self._positions(arr, annotation_obj.get_coords())
+            if bad is not None:
+                raise IndexError("index %d is out of bounds for axis 0 with size %d" % (bad, n))
+            vals = arr[idx]
+            count_list.append([annotation_obj.ID, int(np.count_nonzero(vals == 0)), int(np.count_nonzero(vals == 1))])
+        return count_list
+
+    def at_content(self, genome_sequence):
+        """genome.py:1030-1034 -- set position to 1 wherever the base is one of "ATat" (nothing is cleared)."""
+        import ctypes
+        gs = genome_sequence
+        if not isinstance(gs, GenomeSequence):
+            gs = GenomeSequence()
+            for k in genome_sequence:
+                gs[k] = genome_sequence[k]
+        for seqid in self:
+            arr = self[seqid]
+            L = len(gs[seqid])
+            m = min(len(arr), L)
+            if m:
+                flags = np.empty(m, dtype=np.uint8)
+                eng = gs._engine().primary
+                _lib.check(_lib.lib.mg_genome_at_flags(eng.handle, gs.contig_index(seqid), 0, m, ctypes.c_void_p(flags.ctypes.data), None))
+                arr[:m][flags != 0] = 1
+            if len(arr) > L:
+                raise IndexError("string index out of range")
+
+    @staticmethod
+    def _window_sums(arr, window_size, window_jump, n_windows):
+        """numpy.sum(arr[s:s + window_size]) for s = k * window_jump, k < n_windows, on the device (mg_window_sums)."""
+        import ctypes
+        if arr.dtype.kind not in "bui":
+            raise NotImplementedError("the device path sums boolean and integer position_dics only (dtype %s)" % arr.dtype)
+        if arr.dtype.itemsize == 1 and arr.dtype.kind in "bu":
+            vals, elem = np.ascontiguousarray(arr).view(np.uint8), 1
+        else:
+            vals, elem = np.ascontiguousarray(arr, dtype=np.int64), 8
+        sums = np.empty(n_windows, dtype=np.int64)
+        _lib.require_device(_device())
+        _lib.check(_lib.lib.mg_window_sums(_device(), ctypes.c_void_p(vals.ctypes.data) if vals.size else None, elem, vals.size,
+                                           window_size, window_jump, n_windows, ctypes.c_void_p(sums.ctypes.data), None))
+        return sums.astype(np.uint64) if arr.dtype.kind == "u" else sums       # numpy.sum's result type
+
+    def sliding_window_calculate(self, window_size, window_jump=1, operation="sum", output="dict", threshold=1,
+                                 seqs_to_exclude=[]):
+        """genome.py:1036-1100.  operation may be "sum", "average", or "set". Output may be "dict", "coords",
+        "annotation_set" or a file-like object.  Quirks kept: the last `window_size` positions never start a window, a new
+        region is compared by WINDOW INDEX against the previous region's end COORDINATE, "coords" cannot work (the
+        reference misspells `threshold`)."""
+        is_file = hasattr(output, "write")
+        if output == "dict":
+            new_dic = {}
+        elif output == "annotation_set":
+            annotation_set = AnnotationSet()
+            annotation_set.region = {}
+        elif output == "coords":
+            coords_list = []
+        for seqid in self:
+            arr = self[seqid]
+            if len(arr) > window_size and seqid not in seqs_to_exclude:
+                if output == "dict":
+                    new_dic[seqid] = []
+                coords_list = []
+                n_windows = len(range(len(arr))[:-1 * window_size]) // window_jump
+                if operation == "set":
+                    for position in range(n_windows):
+                        window_start = position * window_jump
+                        new_dic[seqid].append(set(arr[window_start:window_start + window_size].tolist()))
+                else:
+                    sums = self._window_sums(arr, window_size, window_jump, n_windows) if n_windows > 0 else np.zeros(0, np.int64)
+                    if operation == "sum":
+                        values = sums
+                    elif operation == "average":
+                        values = sums * 1.0 / window_size
+                    if n_windows > 0 and operation not in ("sum", "average"):
+                        raise UnboundLocalError("local variable 'value' referenced before assignment")
+                    if output == "dict":
+                        new_dic[seqid].extend(list(values))
+                    elif output == "annotation_set":
+                        above = np.asarray(values >= threshold)
+                        edges = np.flatnonzero(np.diff(np.concatenate(([False], above, [False])).astype(np.int8)))
+                        for first, past in zip(edges[0::2].tolist(), edges[1::2].tolist()):
+                            # window `first` is the first of a run at or above the threshold, `past` the first below again
+                            if len(coords_list) == 0 or first > coords_list[-1][1]:
+                                coords_list.append([1 + first * window_jump])
+                            if past < n_windows:
+                                if len(coords_list[-1]) == 1:
+                                    coords_list[-1].append(past * window_jump + window_size)
+                                else:
+                                    coords_list[-1][1] = past * window_jump + window_size
+                    elif output == "coords":
+                        if n_windows > 0:
+                            if bool(np.any(threshold[0] <= values)):
+                                raise NameError("global name 'thredshold' is not defined")
+                    elif is_file:
+                        output.write("".join(seqid + '\t' + _py2_str(v.item()) + '\n' for v in values))
+                    if verbose:
+                        step = 10000000 // np.gcd(10000000, window_jump)
+                        for position in range(0, n_windows, int(step)):
+                            print("processed " + seqid + " to position " + str(position))
+                if output == "annotation_set":
+                    if len(coords_list) > 0:
+                        if len(coords_list[-1]) == 1:
+                            coords_list[-1].append(len(arr))
+                        for coords in coords_list:
+                            ID = seqid + "-window" + str(coords[0])
+                            annotation_set.region[ID] = BaseAnnotation(ID, seqid, tuple(coords), "region", annotation_set=annotation_set)
+                if verbose:
+                    print("processed " + seqid)
+                    if output == 'annotation_set':
+                        for region in _order(list(annotation_set.region)):
+                            if annotation_set.region[region].seqid == seqid:
+                                print(str(annotation_set.region[region].coords))
+        if output == "dict":
+            return {k: new_dic[k] for k in _order(list(new_dic))}        # a Python-2.7 dict filled in this order
+        elif output == "annotation_set":
+            # the reference returns copy.deepcopy(annotation_set): the region table ends up re-inserted in slot order
+            annotation_set.region = {k: annotation_set.region[k] for k in _order(list(annotation_set.region), deepcopy=True)}
+            _DEEPCOPIED_SETS.add(annotation_set)
+            return annotation_set
+        elif output == "coords":
+            return coords_list
+
 
 # ---------------------------------------------------------------------------------------------
 # Genome (genome.py:880-978)

@@ -20,11 +20,13 @@ The rewrite rules are purely syntactic and never touch an algorithm:
   2. `import StringIO`          ->  `import io as StringIO`
      (genome.py:17, magot_smallfuncs.py:9)
   3. `type(output) == file`     ->  `False`            (genome.py:1078)
-  4. a prologue line `from _py2compat import open` so that text files are read
+  4. `len(self[seqid][:-1 * window_size]) / window_jump` -> `//` (genome.py:1052: Python 2's `/` on two ints IS floor
+     division; the rule only names that one expression)
+  5. a prologue line `from _py2compat import open` so that text files are read
      as Python 2 reads them: bytes one-to-one (latin-1) and *no* universal
      newline translation (a lone '\r' stays inside its line).
 Semantic differences that remain (all OFF the hot path): `presets=` of read_gff
-(`exec` cannot rebind locals in Py3), `/` in sliding_window_calculate,
+(`exec` cannot rebind locals in Py3),
 `ensure_file` on already-open file objects, and dict iteration order (Python 3
 dicts iterate in insertion order; CPython 2.7 iterates in hash-slot order -- the
 order emulator lives in oracle/py2dict.py and is applied by the callers).
@@ -72,6 +74,7 @@ def shim_source(text):
     text = "\n".join(out)
     text = text.replace("import StringIO", "import io as StringIO")
     text = text.replace("type(output) == file", "False")
+    text = text.replace("len(self[seqid][:-1 * window_size]) / window_jump", "len(self[seqid][:-1 * window_size]) // window_jump")
     return "from _py2compat import open\n" + text
 
 

@@ -273,6 +273,94 @@ def gff_writer_cases(cases):
             lambda: ref_runner.write_gff(T + "StandardGTF.gtf", fmt, **AUGUSTUS_PRESET))
 
 
+def position_dic_cases():
+    """position_dic (genome.py:981-1100) run by the reference on a small genome: at_content, fill / count from
+    annotations, sliding_window_calculate (sum / average -> dict, annotation_set with its region-merging quirks, verbose
+    output).  Inputs travel inside the fixture.  Python-2.7 orders are restored where a dict is iterated."""
+    import contextlib
+    import io
+    import numpy
+    from py2dict import py2_order
+    g = ref_runner.ref()
+    rnd = random.Random(4242)
+
+    def contig(n, at):
+        out = []
+        while len(out) < n:
+            rich = rnd.random() < 0.3
+            run = rnd.randint(20, 400)
+            p = at if not rich else 0.9
+            out.extend(rnd.choice("ATat" if rnd.random() < p else "CGcgNn") for _ in range(run))
+        return "".join(out[:n])
+
+    seqs = {"ctgA": contig(5003, 0.5), "ctgB some text": contig(1203, 0.35), "ctgC": contig(64, 0.5), "ctgD": contig(300, 0.2)}
+    fasta = "".join(">%s\n%s\n" % (k, "\n".join(v[i:i + 70] for i in range(0, len(v), 70))) for k, v in seqs.items())
+    gff_lines = []
+    k = 0
+    for seqid, L in (("ctgA", 5003), ("ctgB some text", 1203), ("ctgD", 300)):
+        for gi in range(3):
+            k += 1
+            a = rnd.randint(1, L - 200)
+            gff_lines.append("%s\tsyn\tgene\t%d\t%d\t.\t+\t.\tID=g%d" % (seqid, a, a + 180, k))
+            gff_lines.append("%s\tsyn\tmRNA\t%d\t%d\t.\t+\t.\tID=t%d;Parent=g%d" % (seqid, a, a + 180, k, k))
+            gff_lines.append("%s\tsyn\tCDS\t%d\t%d\t.\t+\t0\tID=c%da;Parent=t%d" % (seqid, a, a + 60, k, k))
+            gff_lines.append("%s\tsyn\tCDS\t%d\t%d\t.\t+\t0\tID=c%db;Parent=t%d" % (seqid, a + 100, a + 180, k, k))
+    gff = "\n".join(gff_lines) + "\n"
+
+    def fresh(dtype=bool):
+        gs = g.GenomeSequence(fasta)
+        ref_runner.reorder_genome_sequence(gs)
+        pd = g.position_dic(gs, dtype=dtype)
+        items = {kk: pd[kk] for kk in py2_order(list(pd))}       # a position_dic is a py2 dict itself
+        pd.clear()
+        pd.update(items)
+        return gs, pd
+
+    aset = g.read_gff(gff)
+    ref_runner.reorder_annotation_set(aset)
+    out = {"fasta": fasta, "gff": gff, "order": None, "at_content": {}, "fill": {}, "count": {}, "windows": []}
+    gs, pd = fresh()
+    out["order"] = list(pd)
+    pd.at_content(gs)
+    out["at_content"] = {kk: "".join("1" if x else "0" for x in v) for kk, v in pd.items()}
+    at_pd = pd
+    for feature, fill_type in (("CDS", "coords"), ("gene", "coords"), ("CDS", "start")):
+        _, pd = fresh()
+        pd.fill_from_annotations(aset, feature, fill_type=fill_type)
+        out["fill"]["%s:%s" % (feature, fill_type)] = {kk: "".join("1" if x else "0" for x in v) for kk, v in pd.items()}
+    _, pd = fresh(dtype=int)
+    pd.fill_from_annotations(aset, "CDS", fill_with="coords[0] % 3")
+    out["fill"]["CDS:coords:int:coords[0] % 3"] = {kk: [int(x) for x in v] for kk, v in pd.items()}
+    _, pd = fresh()
+    pd.fill_from_annotations(aset, "CDS")
+    out["count"]["gene_over_CDS_fill"] = pd.count_from_annotations(aset, "gene")
+    out["count"]["mRNA_over_at"] = at_pd.count_from_annotations(aset, "mRNA")
+    for (w, j, op, output, thr, excl) in [(50, 1, "sum", "dict", 1, []), (100, 25, "sum", "dict", 1, []),
+                                          (64, 64, "average", "dict", 1, ["ctgD"]), (7, 3, "sum", "dict", 1, []),
+                                          (63, 1, "sum", "dict", 1, []), (64, 1, "sum", "dict", 1, []),
+                                          (50, 1, "sum", "annotation_set", 40, []), (50, 10, "sum", "annotation_set", 35, []),
+                                          (40, 5, "average", "annotation_set", 0.8, []), (30, 7, "sum", "annotation_set", 0, []),
+                                          (100, 1, "sum", "annotation_set", 101, []), (20, 20, "sum", "annotation_set", 12, ["ctgA"])]:
+        for verbose in (False, True):
+            g.verbose = verbose
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                r = at_pd.sliding_window_calculate(w, window_jump=j, operation=op, output=output, threshold=thr, seqs_to_exclude=excl)
+            g.verbose = True
+            if output == "dict":
+                res = {kk: [float(x) if op == "average" else int(x) for x in v] for kk, v in r.items()}
+                key_order = py2_order(list(r))
+            else:
+                ref_runner.reorder_annotation_set(r)
+                res = [[kk, list(v.coords), v.seqid] for kk, v in r.region.items()]
+                key_order = None
+            if verbose and output == "annotation_set":
+                continue            # the reference prints the regions in the order of a py2 dict the shim cannot replay
+            out["windows"].append({"window": w, "jump": j, "operation": op, "output": output, "threshold": thr, "exclude": excl,
+                                   "verbose": verbose, "result": res, "key_order": key_order, "stdout": buf.getvalue()})
+    return out
+
+
 def library_vectors():
     """Sequence.translate(library=...) (genome.py:795, :814-817) with caller-supplied codon dicts, run by the reference:
     the vertebrate mitochondrial code, a library with only three entries (everything else -> 'X'), and one whose extra
@@ -351,6 +439,11 @@ def kat_vectors():
 
 def main():
     import tempfile
+    if "--only-position-dic" in sys.argv:
+        with open(os.path.join(HERE, "position_dic.json"), "w") as fh:
+            json.dump(position_dic_cases(), fh, indent=0)
+        print("wrote position_dic.json")
+        return
     if "--only-library-kat" in sys.argv:      # add the custom-codon-table vectors to the existing kat.json
         with open(os.path.join(HERE, "kat.json")) as fh:
             kat = json.load(fh)
@@ -379,6 +472,8 @@ def main():
         kat = kat_vectors()
         kat["translate_library"] = library_vectors()
         json.dump(kat, fh, indent=0)
+    with open(os.path.join(HERE, "position_dic.json"), "w") as fh:
+        json.dump(position_dic_cases(), fh, indent=0)
     print("wrote", len(cases), "whole-file cases")
 
 

@@ -200,3 +200,42 @@ def test_config5_full_size_properties(big):
                 ok = True
                 break
         assert ok, (int(i), c, f, minus, st, ln)
+
+
+def test_config3_fasta_text_ingest_on_device(insect):
+    """K0f at config-3 size: the 500 Mbp genome written out as FASTA text (60-column lines, CRLF on every 7th scaffold) and read
+    back through GenomeSequence -- headers parsed on the host, bodies stripped and packed on the device -- must decode to the
+    same bases as the genome it was written from (whole-contig CRC for the largest scaffolds, sampled ranges for all)."""
+    from magot_b200 import genome as mg
+    g, layout, _ = insect
+    parts = []
+    for ci, (name, L) in enumerate(layout):
+        seq = np.frombuffer(g.fetch(ci, 0, L), dtype=np.uint8)
+        eol = b"\r\n" if ci % 7 == 0 else b"\n"
+        full = L // 60
+        rows = np.empty((full, 60 + len(eol)), dtype=np.uint8)
+        rows[:, :60] = seq[:full * 60].reshape(full, 60)
+        rows[:, 60:] = np.frombuffer(eol, dtype=np.uint8)
+        parts.append(b">" + name.encode() + b" synthetic scaffold\n" + rows.tobytes() + seq[full * 60:].tobytes() + eol)
+    text = b"".join(parts)
+    del parts
+    gs = mg.GenomeSequence(text)
+    try:
+        assert len(gs) == len(layout)
+        eng = gs._engine().primary
+        rng = np.random.default_rng(5)
+        order = np.argsort([-l for _, l in layout])
+        for ci in range(len(layout)):
+            name, L = layout[ci]
+            key = name + " synthetic scaffold"
+            assert len(gs[key]) == L
+            cj = gs.contig_index(key)
+            if ci in order[:8]:
+                assert zlib.crc32(eng.fetch(cj, 0, L)) == zlib.crc32(g.fetch(ci, 0, L)), name
+            else:
+                lo = int(rng.integers(0, max(L - 500, 1)))
+                hi = min(L, lo + 500)
+                assert eng.fetch(cj, lo, hi) == g.fetch(ci, lo, hi), (name, lo)
+                assert eng.fetch(cj, max(L - 70, 0), L, True) == g.fetch(ci, max(L - 70, 0), L, True), name
+    finally:
+        gs.close()

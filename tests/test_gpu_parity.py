@@ -667,3 +667,74 @@ def test_synthetic_annotation_text_through_api(mg, tmp_path, flavour):
     aset.genome = seqs
     assert g.annotations.get_fasta('gene') == mo.annotation_set_get_fasta(aset, 'gene')
     assert g.annotations.get_fasta('gene', longest=True) == mo.annotation_set_get_fasta(aset, 'gene', longest=True)
+
+
+# ---- K6: position_dic on the device (genome.py:981-1100) ------------------------------------------------------------
+
+def _position_dic_fixture():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "position_dic.json")) as fh:
+        return json.load(fh)
+
+
+def test_position_dic_at_content_and_windows_match_reference(mg, capsys):
+    """at_content (K6 k_at_flags on the packed genome) and sliding_window_calculate (device prefix scan + window gather) against
+    the reference's own results: window sums / averages as dicts (with the verbose progress lines), merged regions as an
+    AnnotationSet (IDs, coordinates, table order), and mRNA-interval counts over the AT flags."""
+    fx = _position_dic_fixture()
+    gs = mg.GenomeSequence(fx["fasta"])
+    aset = mg.read_gff(fx["gff"])
+    pd = mg.position_dic(gs)
+    assert list(pd) == fx["order"]
+    pd.at_content(gs)
+    assert {k: "".join("1" if x else "0" for x in v) for k, v in pd.items()} == fx["at_content"]
+    assert pd.count_from_annotations(aset, "mRNA") == fx["count"]["mRNA_over_at"]
+    for case in fx["windows"]:
+        mg.genome.verbose = case["verbose"]
+        capsys.readouterr()
+        try:
+            r = pd.sliding_window_calculate(case["window"], window_jump=case["jump"], operation=case["operation"],
+                                            output=case["output"], threshold=case["threshold"], seqs_to_exclude=case["exclude"])
+        finally:
+            mg.genome.verbose = True
+        assert capsys.readouterr().out == case["stdout"], case
+        if case["output"] == "dict":
+            assert list(r) == case["key_order"]
+            if case["operation"] == "average":
+                assert {k: [float(x) for x in v] for k, v in r.items()} == case["result"]      # sums * 1.0 / window: exact
+            else:
+                assert {k: [int(x) for x in v] for k, v in r.items()} == case["result"]
+                assert all(isinstance(x, np.integer) for v in r.values() for x in v[:3])
+        else:
+            assert [[k, list(v.coords), v.seqid] for k, v in r.region.items()] == case["result"], case
+    # "coords" output cannot work in the reference (misspelt name) -- same exceptions here
+    with pytest.raises(TypeError):
+        pd.sliding_window_calculate(50, output="coords")
+    with pytest.raises(NameError):
+        pd.sliding_window_calculate(50, output="coords", threshold=[0, 10])
+    gs.close()
+
+
+@pytest.mark.parametrize("dtype", [bool, np.uint8, np.int64, np.int32])
+def test_window_sums_random_against_numpy(mg, dtype):
+    """mg_window_sums over tile boundaries (4096 / 1024 elements per tile) and several (window, jump) pairs against numpy.sum
+    per window, as the reference computes it (genome.py:1055)."""
+    rng = np.random.default_rng(12)
+    for n in (1, 17, 4095, 4096, 4097, 100_003, 1_300_001):
+        if dtype is bool:
+            a = rng.random(n) < 0.4
+        elif dtype is np.uint8:
+            a = rng.integers(0, 256, n).astype(np.uint8)
+        else:
+            a = rng.integers(-1000, 1000, n).astype(dtype)
+        for w, j in ((1, 1), (5, 2), (64, 64), (1000, 37), (n, 1), (n + 5, 3)):
+            if n > 200_000 and j < 30:
+                continue
+            nw = len(range(n)[:-w]) // j if n > w else 0
+            if nw == 0:
+                continue
+            got = mg.position_dic._window_sums(a, w, j, nw)
+            want = np.array([int(a[k * j:k * j + w].sum()) for k in range(nw)], dtype=np.int64)
+            assert np.array_equal(got.astype(np.int64), want), (n, w, j)
+            assert got.dtype == (np.uint64 if dtype is np.uint8 else np.int64)

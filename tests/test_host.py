@@ -359,3 +359,46 @@ def test_annotation_set_seqid_helpers_and_cegma(ref_data):
     assert my.get_seqids(from_annotations=True) == ids
     with pytest.raises(TypeError):
         genome.read_cegma_gff(os.path.join(ref_data, "StandardGTF.gtf"))
+
+
+# ---- position_dic (genome.py:981-1100), host half: fill / count from annotations
+
+def _position_dic_fixture():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "position_dic.json")) as fh:
+        fx = json.load(fh)
+    seqs = {}
+    for rec in fx["fasta"].split(">")[1:]:
+        head, _, body = rec.partition("\n")
+        seqs[head] = body.replace("\n", "")
+    return fx, {k: seqs[k] for k in py2dict.py2_order(list(seqs))}         # GenomeSequence iterates in Python-2.7 order
+
+
+def test_position_dic_fill_and_count_match_reference():
+    """fill_from_annotations ("coords" / "start", constant and coords-dependent fill_with) and count_from_annotations against
+    the reference's own arrays (tests/golden/make_golden.py:position_dic_cases); no device needed for these."""
+    fx, seqs = _position_dic_fixture()
+    aset = genome.read_gff(fx["gff"])
+    assert list(genome.position_dic(seqs)) == fx["order"]
+    bits = lambda pd: {k: "".join("1" if x else "0" for x in v) for k, v in pd.items()}      # noqa: E731
+    for feature, fill_type in (("CDS", "coords"), ("gene", "coords"), ("CDS", "start")):
+        pd = genome.position_dic(seqs)
+        pd.fill_from_annotations(aset, feature, fill_type=fill_type)
+        assert bits(pd) == fx["fill"]["%s:%s" % (feature, fill_type)]
+    pd = genome.position_dic(seqs, dtype=int)
+    pd.fill_from_annotations(aset, "CDS", fill_with="coords[0] % 3")
+    assert {k: [int(x) for x in v] for k, v in pd.items()} == fx["fill"]["CDS:coords:int:coords[0] % 3"]
+    pd = genome.position_dic(seqs)
+    pd.fill_from_annotations(aset, "CDS")
+    assert pd.count_from_annotations(aset, "gene") == fx["count"]["gene_over_CDS_fill"]
+    # numpy index semantics of the reference's per-position loop: position -1 is the last element, past the end raises
+    pd = genome.position_dic({"c": "ACGTACGTAC"})
+    b = genome.BaseAnnotation("x", "c", (0, 3), "CDS", None, "+", {}, genome.AnnotationSet())
+    fake = genome.AnnotationSet()
+    fake.CDS = {"x": b}
+    pd.fill_from_annotations(fake, "CDS")
+    assert pd["c"].astype(int).tolist() == [1, 1, 1, 0, 0, 0, 0, 0, 0, 1]
+    b.coords = (8, 12)
+    with pytest.raises(IndexError):
+        pd.fill_from_annotations(fake, "CDS")
+    assert pd["c"].astype(int).tolist() == [1, 1, 1, 0, 0, 0, 0, 1, 1, 1]
