@@ -738,3 +738,23 @@ def test_window_sums_random_against_numpy(mg, dtype):
             want = np.array([int(a[k * j:k * j + w].sum()) for k in range(nw)], dtype=np.int64)
             assert np.array_equal(got.astype(np.int64), want), (n, w, j)
             assert got.dtype == (np.uint64 if dtype is np.uint8 else np.int64)
+
+
+# ---- in-process multi-GPU: the genome replicated on every device, the record table cut into byte-balanced batches ----------
+
+def test_sharded_genome_on_all_devices_matches_goldens(mg, ref_data, manifest, monkeypatch):
+    """SURVEY 8e through the Python API: with DEFAULT_DEVICES = every GPU of the box, gff2fasta (nucleotide and protein) still
+    prints the reference suite's goldens -- one host thread per GPU, texts joined in record order.  Skipped on a 1-GPU box."""
+    from magot_b200 import genome_tools as gt, _lib
+    n = _lib.device_count()
+    if n < 2:
+        pytest.skip("needs at least two CUDA devices")
+    monkeypatch.setattr(mg.genome, "DEFAULT_DEVICES", list(range(n)))
+    fa, gtf = os.path.join(ref_data, "C14.fasta"), os.path.join(ref_data, "StandardGTF.gtf")
+    assert _ck(_stdout_of(gt.main, ["genome_tools.py", "gff2fasta", fa, gtf])) == manifest["suite:gff2fasta_C14_StandardGTF"]
+    assert _ck(_stdout_of(gt.main, ["genome_tools.py", "gff2fasta", fa, gtf, "seq_type=protein"])) == manifest["suite:gff2fasta_C14_StandardGTF_protein"]
+    my = mg.Genome(fa)
+    assert len(my.genome_sequence._engine().replicas) == n
+    my.read_gff(gtf)
+    assert _ck(my.annotations.get_fasta('gene', longest=True) + "\n") == manifest["c14:StandardGTF.gtf:longest"]
+    my.genome_sequence.close()
