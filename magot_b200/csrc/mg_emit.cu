@@ -37,6 +37,9 @@
 #define NUC_LITCAP 256                                   // literal pieces listed per tile (config 4: ~50)
 #define NUC_CHUNKS (MG_NUC_TILE / 32 / NUC_THREADS)     // 4 chunks of 32 B per thread
 
+#ifndef PROT_WIDE_SLOT
+#define PROT_WIDE_SLOT 1
+#endif
 #ifndef PROT_THREADS
 #define PROT_THREADS 256
 #endif
@@ -513,6 +516,23 @@ __global__ void __launch_bounds__(PROT_THREADS, PROT_MINB) k_emit_prot(
                 }
             }
             uint32_t w[4] = {0, 0, 0, 0};
+#if PROT_WIDE_SLOT
+            // mg_aa_slot for all 16 codons at once: slot = c ^ ((c >> 6) & 0xC) moves bits 8-9 of every 12-bit codon onto its
+            // bits 2-3, i.e. the whole 192-bit window XORs itself shifted right by 6 under a mask with period 12
+            {
+                constexpr uint32_t M0 = 0x0C00C00Cu, M1 = 0xC00C00C0u, M2 = 0x00C00C00u;   // bits b with b % 12 in {2, 3}, words 0..2 (period 3 words)
+                const uint32_t x0 = n[0] ^ (__funnelshift_r(n[0], n[1], 6) & M0), x1 = n[1] ^ (__funnelshift_r(n[1], n[2], 6) & M1),
+                               x2 = n[2] ^ (__funnelshift_r(n[2], n[3], 6) & M2), x3 = n[3] ^ (__funnelshift_r(n[3], n[4], 6) & M0),
+                               x4 = n[4] ^ (__funnelshift_r(n[4], n[5], 6) & M1), x5 = n[5] ^ ((n[5] >> 6) & M2);
+                n[0] = x0; n[1] = x1; n[2] = x2; n[3] = x3; n[4] = x4; n[5] = x5;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) {            // codon k = nibbles 3k..3k+2 = bits 12k.. of n[5]:..:n[0]
+                const int bit = 12 * k, ww = bit >> 5, sh = bit & 31;
+                const uint32_t idx = (sh > 20 ? __funnelshift_r(n[ww], n[ww + 1], sh) : (n[ww] >> sh)) & 0xFFFu;
+                w[k >> 2] |= (uint32_t)s_aa[idx] << ((k & 3) * 8);
+            }
+#else
 #pragma unroll
             for (int k = 0; k < 16; k++) {            // codon k = nibbles 3k..3k+2 = bits 12k.. of n[5]:..:n[0]
                 const int bit = 12 * k, ww = bit >> 5, sh = bit & 31;
@@ -520,6 +540,7 @@ __global__ void __launch_bounds__(PROT_THREADS, PROT_MINB) k_emit_prot(
                 if (sh > 20) idx |= n[ww + 1] << (32 - sh);
                 w[k >> 2] |= (uint32_t)s_aa[mg_aa_slot(idx)] << ((k & 3) * 8);
             }
+#endif
             const uint32_t m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
             if (m == 0xFFFFu) { bw[0] = w[0]; bw[1] = w[1]; bw[2] = w[2]; bw[3] = w[3]; }
             else {
