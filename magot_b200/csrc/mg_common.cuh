@@ -136,7 +136,9 @@ struct mg_plan {
 #define MG_KIND_SHIFT 62
 #define MG_SRC_MASK ((1ull << MG_KIND_SHIFT) - 1ull)
 
+#ifndef MG_NUC_TILE
 #define MG_NUC_TILE 32768          // bytes of nucleotide text per CTA tile
+#endif
 #ifndef MG_PROT_TILE
 #define MG_PROT_TILE 16384         // bytes of protein text per CTA tile
 #endif

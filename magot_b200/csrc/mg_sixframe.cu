@@ -49,6 +49,7 @@ struct mg_sixframe_state {
     int32_t *d_cid = nullptr;                        // [nc] the contigs scanned, in output order
     int64_t n_tiles = 0;
     std::vector<int64_t> h_tile_base;                // [n_contig_in_range + 1], starts at 0
+    std::vector<int32_t> h_cid;                      // contig ids of the list (kept here so that their upload stays asynchronous)
     int64_t *d_tile_base = nullptr;
     int32_t *d_tile_contig = nullptr;                // [n_tiles] contig (index in the range) of each tile
     int32_t *d_cs = nullptr;                         // [nc*6] first-codon offset of each stream
@@ -904,7 +905,8 @@ extern "C" int mg_sixframe_count_list(mg_genome *g, int64_t n_list, const int64_
     s->stream = st;
     s->min_aa = min_aa;
     const int64_t nc = n_list;
-    std::vector<int32_t> h_cid(nc);
+    std::vector<int32_t> &h_cid = s->h_cid;
+    h_cid.resize(nc);
     for (int64_t i = 0; i < nc; i++) h_cid[i] = (int32_t)contig_ids[i];
     s->h_tile_base.assign(nc + 1, 0);
     for (int64_t c = 0; c < nc; c++) {
@@ -923,7 +925,6 @@ extern "C" int mg_sixframe_count_list(mg_genome *g, int64_t n_list, const int64_
 #define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
     TRY(six_alloc(s, &s->d_cid, nc));
     MG_CUDA(cudaMemcpyAsync(s->d_cid, h_cid.data(), nc * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    MG_CUDA(cudaStreamSynchronize(st));               // h_cid is a local
     TRY(six_alloc(s, &s->d_tile_base, nc + 1));
     MG_CUDA(cudaMemcpyAsync(s->d_tile_base, s->h_tile_base.data(), (nc + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     TRY(six_alloc(s, &s->d_cs, nc * 6));
