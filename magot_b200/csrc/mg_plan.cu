@@ -35,7 +35,10 @@ __global__ void __launch_bounds__(256) k_plan_block_rec(int64_t n_block, int64_t
 
 // thread per piece: find its record, clamp like a Python slice, write src and -- through a block scan of the lengths plus a
 // decoupled look-back across blocks (mg_lookback.cuh) -- the piece's offset in the nucleotide text, all in one launch
-__global__ void __launch_bounds__(256) k_plan_pieces(int64_t n_piece, int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
+#ifndef PLAN_MINB
+#define PLAN_MINB 8                                  // 32 registers: one plan block fits next to the 7 CTAs of k_emit_prot on an SM (step 0.5075 -> 0.4995 ms)
+#endif
+__global__ void __launch_bounds__(256, PLAN_MINB) k_plan_pieces(int64_t n_piece, int64_t n_rec, const int64_t *__restrict__ rec_seg_off,
                                                      const int64_t *__restrict__ blk_r0,
                                                      const int32_t *__restrict__ seg_contig, const int64_t *__restrict__ seg_start,
                                                      const int64_t *__restrict__ seg_end, const int8_t *__restrict__ seg_strand,
