@@ -174,7 +174,10 @@ __global__ void __launch_bounds__(256) k_plan_records(int64_t n_rec, const int64
         if (flags & MG_PROT_TRIMX) {                     // drop exactly one leading X (genome.py:819-821)
             uint64_t acc[3];
             const int64_t S = pay0 + skip;
-            const int64_t j = mg_search_le(piece_off, f0 + 1, f1 - 1, S);
+            // the piece that holds S: nearly always the record's first segment piece (a walk over the same cache line;
+            // a binary search over the record's pieces was three dependent global loads)
+            int64_t j = f0 + 1;
+            while (j + 1 < f1 - 1 && __ldg(piece_off + j + 1) <= S) j++;
             mg_gather_nib(packed, piece_off, piece_src, j, S, 3, acc);
             const uint32_t n3 = (uint32_t)acc[0] & 0xFFFu;
             if (n3 & 0x888u) { naa -= 1; skip += 3; }
