@@ -29,6 +29,9 @@
 #ifndef NUC_LD64
 #define NUC_LD64 1
 #endif
+#ifndef FRAME_BATCH
+#define FRAME_BATCH 1
+#endif
 #ifndef NUC_MINB
 #define NUC_MINB 8                                       // 32 registers, 64 resident warps per SM
 #endif
@@ -369,7 +372,19 @@ __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_nuc(
             const int i = s_lits[k >> 3];
             const int r1 = min(s_rel[i + 1], tile_len);
             const uint8_t *src = lit + s_base[i];
+#if FRAME_BATCH
+            // four loads in flight per lane before the first store (a header of <= 32 bytes is ONE load latency, not three,
+            // at the very end of the CTA's life)
+            for (int q = max(s_rel[i], 0) + (k & 7); q < r1; q += 32) {
+                uint8_t b[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) b[j] = q + 8 * j < r1 ? __ldg(src + q + 8 * j) : (uint8_t)0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (q + 8 * j < r1) out[P0 + q + 8 * j] = b[j];
+            }
+#else
             for (int q = max(s_rel[i], 0) + (k & 7); q < r1; q += 8) out[P0 + q] = __ldg(src + q);
+#endif
         }
     } else {                                          // more literal pieces than the list holds: one thread per piece
         for (int i = threadIdx.x; i < ncache; i += NUC_THREADS) {
@@ -396,7 +411,20 @@ __device__ __forceinline__ void prot_write_framing(int64_t r_lo, int64_t r_hi, i
         const int64_t a = __ldg(prot_off + r) - P0;            // tile-relative start of the record
         const uint8_t *src = lit + rec_lit_off[r];
         const int64_t e = a + pre + naa;                       // suffix position
+#if FRAME_BATCH
+        {   // prefix and suffix in batches of eight bytes: eight loads in flight, then eight stores
+            const int q0 = (int)max(a, (int64_t)0), q1 = (int)min(a + pre, (int64_t)tile_len);
+            for (int q = q0; q < q1; q += 8) {
+                uint8_t b[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) b[j] = q + j < q1 ? __ldg(src + (q + j - a)) : (uint8_t)0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (q + j < q1) out[P0 + q + j] = b[j];
+            }
+        }
+#else
         for (int64_t q = max(a, (int64_t)0); q < min(a + pre, (int64_t)tile_len); q++) out[P0 + q] = __ldg(src + (q - a));
+#endif
         for (int64_t q = max(e, (int64_t)0); q < min(e + suf, (int64_t)tile_len); q++) out[P0 + q] = __ldg(src + pre + (q - e));
     }
 }
