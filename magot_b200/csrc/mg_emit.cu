@@ -25,7 +25,9 @@
 #include "mg_common.cuh"
 #include "mg_gather.cuh"
 
+#ifndef NUC_THREADS
 #define NUC_THREADS 256
+#endif
 #ifndef NUC_LD64
 #define NUC_LD64 1
 #endif
@@ -41,7 +43,7 @@
 #endif
 #define NUC_UNITS (MG_NUC_TILE / 32)
 #define NUC_LITCAP 256                                   // literal pieces listed per tile (config 4: ~50)
-#define NUC_CHUNKS (MG_NUC_TILE / 32 / NUC_THREADS)     // 4 chunks of 32 B per thread
+#define NUC_CHUNKS ((MG_NUC_TILE / 32 + NUC_THREADS - 1) / NUC_THREADS)   // 4 chunks of 32 B per thread
 
 #ifndef PROT_WIDE_SLOT
 #define PROT_WIDE_SLOT 1
