@@ -34,6 +34,9 @@
 #ifndef FRAME_BATCH
 #define FRAME_BATCH 1
 #endif
+#ifndef FRAME_LANES4
+#define FRAME_LANES4 1
+#endif
 #ifndef NUC_MINB
 #define NUC_MINB 8                                       // 32 registers, 64 resident warps per SM
 #endif
@@ -406,6 +409,30 @@ __device__ __forceinline__ void prot_write_framing(int64_t r_lo, int64_t r_hi, i
                                                    const int64_t *__restrict__ rec_lit_off, const int32_t *__restrict__ rec_pre,
                                                    const int32_t *__restrict__ rec_suf, const uint8_t *__restrict__ lit,
                                                    uint8_t *__restrict__ out) {
+#if FRAME_LANES4
+    // four lanes per record: a header of <= 32 bytes is one batch of loads (lane s takes bytes s, s + 4, ..), the suffix goes
+    // with the last lane, so the CTA's epilogue is two load latencies (record fields, literal bytes) whatever the header length
+    for (int64_t idx = threadIdx.x; idx < (r_hi - r_lo) * 4; idx += blockDim.x) {
+        const int64_t r = r_lo + (idx >> 2);
+        const int sub = (int)(idx & 3);
+        const int pre = rec_pre[r], suf = rec_suf[r];
+        int32_t naa = rec_aa[r];
+        if (naa < 0) naa = 0;
+        const int64_t a = __ldg(prot_off + r) - P0;            // tile-relative start of the record
+        const uint8_t *src = lit + rec_lit_off[r];
+        const int64_t e = a + pre + naa;                       // suffix position
+        const int q0 = (int)max(a, (int64_t)0), q1 = (int)min(a + pre, (int64_t)tile_len);
+        for (int q = q0 + sub; q < q1; q += 32) {
+            uint8_t b[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) b[j] = q + 4 * j < q1 ? __ldg(src + (q + 4 * j - a)) : (uint8_t)0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (q + 4 * j < q1) out[P0 + q + 4 * j] = b[j];
+        }
+        if (sub == 3)
+            for (int64_t q = max(e, (int64_t)0); q < min(e + suf, (int64_t)tile_len); q++) out[P0 + q] = __ldg(src + pre + (q - e));
+    }
+#else
     for (int64_t r = r_lo + threadIdx.x; r < r_hi; r += blockDim.x) {
         const int pre = rec_pre[r], suf = rec_suf[r];
         int32_t naa = rec_aa[r];
@@ -413,8 +440,7 @@ __device__ __forceinline__ void prot_write_framing(int64_t r_lo, int64_t r_hi, i
         const int64_t a = __ldg(prot_off + r) - P0;            // tile-relative start of the record
         const uint8_t *src = lit + rec_lit_off[r];
         const int64_t e = a + pre + naa;                       // suffix position
-#if FRAME_BATCH
-        {   // prefix and suffix in batches of eight bytes: eight loads in flight, then eight stores
+        {   // prefix in batches of eight bytes: eight loads in flight, then eight stores
             const int q0 = (int)max(a, (int64_t)0), q1 = (int)min(a + pre, (int64_t)tile_len);
             for (int q = q0; q < q1; q += 8) {
                 uint8_t b[8];
@@ -424,11 +450,9 @@ __device__ __forceinline__ void prot_write_framing(int64_t r_lo, int64_t r_hi, i
                 for (int j = 0; j < 8; j++) if (q + j < q1) out[P0 + q + j] = b[j];
             }
         }
-#else
-        for (int64_t q = max(a, (int64_t)0); q < min(a + pre, (int64_t)tile_len); q++) out[P0 + q] = __ldg(src + (q - a));
-#endif
         for (int64_t q = max(e, (int64_t)0); q < min(e + suf, (int64_t)tile_len); q++) out[P0 + q] = __ldg(src + pre + (q - e));
     }
+#endif
 }
 
 // ---- K3 -------------------------------------------------------------------------------------------------------
