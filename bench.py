@@ -631,7 +631,7 @@ def gpu_arm(args):
     roofline = {"kernel": "k_emit_nuc (K2 splice + per-segment RC + FASTA framing)", "bound": "hbm", "achieved": round(ach, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                 "traffic": 567e6 if (GENOME_BP == 3_100_000_000 and N_TX == 200_000) else None,
-                "traffic_source": "dram__bytes_read+write per launch, mean of the CDS (241+192 MB) and exon (369+332 MB) launches, ncu --set full, profiles/r1af_emit_plan_raw.csv",
+                "traffic_source": "dram__bytes_read+write per launch, mean of the CDS (241+192 MB) and exon (369+332 MB) launches, ncu --set full, profiles/r1ag_emit_plan_raw.csv",
                 "peak_source": peak_src,
                 "frac_of_nominal_8TBs": round(ach / 8000.0, 4),
                 "launches_per_step": 2, "avg_launch_ms": round((nuc_ms_cds + nuc_ms_exon) / 2, 4),
