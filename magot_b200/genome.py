@@ -691,6 +691,22 @@ _AUGUSTUS_IGNORE = ['gene', 'transcript', 'stop_codon', 'terminal', 'internal', 
 def read_gff(gff, annotation_set_to_modify=None, base_features=['CDS', 'match_part', 'similarity', 'region'],
              features_to_ignore=['exon'], gff_version="auto", parents_hierarchy=[], features_to_replace=[],
              IDfield="ID", parent_field="Parent", presets=None):
+    """genome.py:242-415, see _read_gff.  The cyclic garbage collector is paused while the object model is built: millions
+    of long-lived objects are created and every generation-2 pass walks all of them for nothing (20-25 % of the time)."""
+    import gc
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        return _read_gff(gff, annotation_set_to_modify, base_features, features_to_ignore, gff_version, parents_hierarchy,
+                         features_to_replace, IDfield, parent_field, presets)
+    finally:
+        if was_enabled:
+            gc.enable()
+
+
+def _read_gff(gff, annotation_set_to_modify=None, base_features=['CDS', 'match_part', 'similarity', 'region'],
+              features_to_ignore=['exon'], gff_version="auto", parents_hierarchy=[], features_to_replace=[],
+              IDfield="ID", parent_field="Parent", presets=None):
     """genome.py:242-415 -- GFF3 / GTF reader with the reference's ID, de-dup and implicit-parent
     semantics.  Returns a new AnnotationSet (dicts in the order the reference's deepcopy leaves
     them) unless annotation_set_to_modify is given."""
@@ -734,10 +750,13 @@ def read_gff(gff, annotation_set_to_modify=None, base_features=['CDS', 'match_pa
     phase_ok = ('0', '1', '2')
     for original_line in gff_file:
         if original_line[0] != "#" and original_line.count('\t') == 8:
-            line = original_line.replace("\n", "").replace("\r", "")
-            for a, b in extra_replace:
-                line = line.replace(a, b)
-            fields = line.split('\t')
+            if extra_replace or '\r' in original_line or original_line.find('\n') != len(original_line) - 1:
+                line = original_line.replace("\n", "").replace("\r", "")
+                for a, b in extra_replace:
+                    line = line.replace(a, b)
+                fields = line.split('\t')
+            else:                                       # the usual line: one '\n', at the end, nothing to replace
+                fields = original_line[:-1].split('\t')
             f8 = fields[8]
             if version == "auto":
                 if "=" in f8:
@@ -762,10 +781,11 @@ def read_gff(gff, annotation_set_to_modify=None, base_features=['CDS', 'match_pa
                 continue
             c0, c1 = int(fields[3]), int(fields[4])
             coords = (c0, c1) if c0 <= c1 else (c1, c0)
-            try:
-                other_attributes['score'] = float(fields[5])
-            except ValueError:
-                pass
+            if fields[5] != '.':                        # '.' is float()'s ValueError of the reference, without raising it
+                try:
+                    other_attributes['score'] = float(fields[5])
+                except ValueError:
+                    pass
             strand = fields[6]
             if fields[7] in phase_ok:
                 other_attributes['phase'] = int(fields[7])
