@@ -148,6 +148,8 @@ int mg_scan_i32(const int32_t *d_in, int64_t *d_out, int64_t n, int64_t *d_tmp, 
 int64_t mg_scan_tmp_elems(int64_t n);
 int mg_ensure_stage(mg_genome *g, int64_t bytes);
 int mg_ensure_pin(mg_genome *g, int64_t bytes);
+int mg_emit_mode();                                   // 0 = per-lane global loads (mg_emit.cu), 1 = bulk-copy staged (mg_emit_tma.cu); env MAGOT_EMIT=ldg|tma
+int mg_launch_nuc_tma(mg_plan *p, uint8_t *out_dev, cudaStream_t st);
 
 #ifdef __CUDACC__
 // ---- device primitives -----------------------------------------------------------------------------

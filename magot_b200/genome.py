@@ -366,10 +366,13 @@ class GenomeSequence(dict):
 
     def _rebuild_from_values(self):
         pend = {}
+        old = self._sharded.primary if self._sharded is not None else None
         for k in dict.keys(self):
             v = dict.__getitem__(self, k)
-            if isinstance(v, DeviceContig) and v._gs is self and self._sharded is not None:
-                pend[k] = np.frombuffer(str(v).encode("latin-1"), dtype=np.uint8)
+            if isinstance(v, DeviceContig) and v._gs is self and old is not None:
+                # straight from the old replica (str(v) would come back here through _engine() while _dirty is set);
+                # _build() closes the old replicas only after every contig has been read
+                pend[k] = np.frombuffer(old.fetch(v._index, 0, v._len), dtype=np.uint8)
             else:
                 pend[k] = np.frombuffer(str(v).encode("latin-1"), dtype=np.uint8)
         self._pending = pend

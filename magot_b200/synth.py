@@ -13,7 +13,7 @@ for the small twins, also as GFF3/GTF text so the whole API path can be exercise
 """
 import numpy as np
 
-from .engine import RecordTable
+from .tables import RecordTable
 
 GRCH38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
           133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,

@@ -758,3 +758,73 @@ def test_sharded_genome_on_all_devices_matches_goldens(mg, ref_data, manifest, m
     my.read_gff(gtf)
     assert _ck(my.annotations.get_fasta('gene', longest=True) + "\n") == manifest["c14:StandardGTF.gtf:longest"]
     my.genome_sequence.close()
+
+
+# ---- plan flags: MG_PROT_USE_PHASE and trimX=False ------------------------------------------------------------
+
+@pytest.mark.parametrize("trimx", [True, False])
+@pytest.mark.parametrize("use_phase", [True, False])
+def test_plan_phase_and_trimx_flags(mg, trimx, use_phase):
+    """K1/K3 with MG_PROT_USE_PHASE (the first segment's GFF phase, genome.py:317 keeps it, north_star: "takes the phase
+    from the GFF") and with trimX off: record r must be Sequence.translate(trimX=...) (genome.py:795-822) of
+    spliced[phase:], phase in {0, 1, 2}; values outside that range count as 0.  The first codon is made of N / IUPAC
+    bytes in every third record so that the trimX branch is taken with and without a phase offset."""
+    from magot_b200 import engine
+    rng = np.random.default_rng(77 + 2 * int(trimx) + int(use_phase))
+    alpha = np.frombuffer(b"ACGTACGTACGTacgtNnR", dtype=np.uint8)
+    contigs = [alpha[rng.integers(0, alpha.size, size=n)].copy() for n in (5000, 30000, 777)]
+    n_rec = 600
+    n_seg = rng.integers(1, 7, size=n_rec)
+    rec_off = np.concatenate(([0], np.cumsum(n_seg)))
+    E = int(rec_off[-1])
+    cid = rng.integers(0, 3, size=E).astype(np.int32)
+    L = np.array([a.size for a in contigs], dtype=np.int64)[cid]
+    st = rng.integers(1, L - 1)
+    en = np.minimum(st + rng.integers(0, 300, size=E), L)
+    short = rng.random(n_rec) < 0.1                      # records of 0-5 bases: translate -> None around the phase offset
+    for r in np.nonzero(short)[0]:
+        e0 = rec_off[r]
+        en[e0] = st[e0] + rng.integers(0, 5)
+        en[e0 + 1:rec_off[r + 1]] = st[e0 + 1:rec_off[r + 1]] - 1      # the other segments are empty
+    sd = rng.integers(0, 2, size=E).astype(np.int8)
+    phase = rng.choice(np.array([0, 1, 2, 0, 1, 2, -1, 5], dtype=np.int8), size=n_rec)
+    for r in range(0, n_rec, 3):                         # N inside the first codon after the phase offset
+        e0 = rec_off[r]
+        if sd[e0] == 0 and en[e0] - st[e0] > 8:
+            contigs[cid[e0]][st[e0] - 1 + max(int(phase[r]), 0) % 3 + int(rng.integers(0, 3))] = ord("N")
+    g = engine.DeviceGenome([a.size for a in contigs], device=0)
+    for i, a in enumerate(contigs):
+        g.pack(i, a)
+    g.finalize()
+    pre = rng.integers(0, 14, size=n_rec).astype(np.int32)
+    suf = np.ones(n_rec, dtype=np.int32)
+    lit = rng.integers(33, 127, size=int(pre.sum() + suf.sum()), dtype=np.uint8)
+    lit_off = np.concatenate(([0], np.cumsum(pre.astype(np.int64) + suf)[:-1]))
+    tbl = engine.RecordTable(rec_off, cid, st, en, sd, lit_off, pre, suf, lit, rec_phase=phase)
+    nuc, off = coracle.splice([a.tobytes() for a in contigs], rec_off, cid, st - 1, np.maximum(en, st - 1), sd)
+    text, (_, got_a) = engine.run_table(g, tbl, protein=True, trimx=trimx, use_phase=use_phase, want_lengths=True)
+    want, want_len = [], []
+    for r in range(n_rec):
+        ph = int(phase[r]) if (use_phase and 0 <= phase[r] <= 2) else 0
+        t = coracle.translate(nuc[off[r]:off[r + 1]].tobytes()[ph:], 0, False, trimx)
+        want_len.append(-1 if t is None else len(t))
+        p0 = int(lit_off[r])
+        want.append(lit[p0:p0 + pre[r]].tobytes() + (t or b"") + lit[p0 + pre[r]:p0 + pre[r] + 1].tobytes())
+    assert list(got_a) == want_len
+    assert text == b"".join(want)
+    assert -1 in want_len and any(w[pre[r]:pre[r] + 1] == b"X" for r, w in enumerate(want))
+    g.close()
+
+
+def test_setitem_on_built_genome(mg):
+    """Assigning a contig to a GenomeSequence that is already on the device re-packs it on next use (the reference's
+    GenomeSequence is a plain dict, genome.py:854): old contigs keep their text, the new one is served from the device."""
+    gs = mg.GenomeSequence(">a\nACGTNNacgt\nTTGA\n>b\nGGGCCC\n")
+    assert gs["a"][0:6] == "ACGTNN"
+    gs["c"] = "TTTTRYAAAA"
+    assert gs["a"][2:12] == "GTNNacgtTT" and str(gs["b"]) == "GGGCCC"
+    assert str(gs["c"]) == "TTTTRYAAAA" and gs["c"][4:6] == "RY"
+    gs["a"] = "CCCC"                                      # replacing an existing contig keeps its place in the dict
+    assert str(gs["a"]) == "CCCC" and str(gs["c"]) == "TTTTRYAAAA" and len(gs) == 3
+    assert str(mg.Sequence(gs["c"][0:6]).reverse_compliment()) == "nnAAAA"
+    gs.close()
