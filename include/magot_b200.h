@@ -189,6 +189,10 @@ int mg_sixframe_emit_device(mg_genome *g, uint8_t *aa_out_dev, mg_orf *recs_dev,
 
 /* ---- timing / sync helpers ----------------------------------------------------------------- */
 int mg_stream_sync(int device, void *stream);
+/* Stream-ordered copy of n bytes from a device buffer (e.g. the output of an mg_emit_*_device call) to host memory (pinned
+ * for full PCIe speed): the output side of `print annotation_set.get_fasta(...)` (genome_tools.py:324-330) when the caller
+ * places the texts of several shards / GPUs in one host buffer itself.                                                */
+int mg_copy_d2h_async(int device, void *dst_host, const void *src_dev, int64_t n, void *stream);
 /* Number of kernels launched by this library since load (per process), for bench accounting. */
 int64_t mg_kernel_launches(void);
 

@@ -72,6 +72,7 @@ SIGNATURES = {
     "mg_sixframe_emit": (_i32, [_vp, _vp, _vp, _vp]),
     "mg_sixframe_emit_device": (_i32, [_vp, _vp, _vp, _vp]),
     "mg_stream_sync": (_i32, [_i32, _vp]),
+    "mg_copy_d2h_async": (_i32, [_i32, _vp, _vp, _i64, _vp]),
     "mg_kernel_launches": (_i64, []),
 }
 

@@ -115,6 +115,9 @@ struct mg_plan {
     int64_t *d_nuc_tile = nullptr;            // first piece of each nucleotide tile
     int64_t *d_prot_tile = nullptr;           // first record of each protein tile
     int64_t n_nuc_tile = 0, n_prot_tile = 0;
+    int32_t *d_blk1k = nullptr;               // first piece of every 1 KB block of the nucleotide text (+ sentinel), for k_emit_nuc_stream
+    int64_t blk1k_cap = 0;                    // entries the table can take (from the host-side upper bound of the text size)
+    int64_t nuc_upper = 0;                    // host-side upper bound of the nucleotide text size: sum(max(0, end-start+1)) + framing
     int64_t *d_tile_buf = nullptr;
     int64_t tile_cap = 0;
     cudaStream_t last_stream = 0;             // frees are ordered after the last use on this stream
@@ -148,8 +151,9 @@ int mg_scan_i32(const int32_t *d_in, int64_t *d_out, int64_t n, int64_t *d_tmp, 
 int64_t mg_scan_tmp_elems(int64_t n);
 int mg_ensure_stage(mg_genome *g, int64_t bytes);
 int mg_ensure_pin(mg_genome *g, int64_t bytes);
-int mg_emit_mode();                                   // 0 = per-lane global loads (mg_emit.cu), 1 = bulk-copy staged (mg_emit_tma.cu); env MAGOT_EMIT=ldg|tma
+int mg_emit_mode();                                   // K2 variant, env MAGOT_EMIT: 0 = ldg (mg_emit.cu, default: the fastest), 1 = tma (mg_emit_tma.cu), 2 = stream (mg_emit_stream.cu)
 int mg_launch_nuc_tma(mg_plan *p, uint8_t *out_dev, cudaStream_t st);
+int mg_launch_nuc_stream(mg_plan *p, uint8_t *out_dev, cudaStream_t st);
 
 #ifdef __CUDACC__
 // ---- device primitives -----------------------------------------------------------------------------

@@ -38,6 +38,9 @@
 #ifndef FRAME_LANES4
 #define FRAME_LANES4 1
 #endif
+#ifndef NUC_FASTDEC
+#define NUC_FASTDEC 1                                    // ACGT/acgt-only chunks take a two-look-up decode (mg_decode32)
+#endif
 #ifndef NUC_MINB
 #define NUC_MINB 8                                       // 32 registers, 64 resident warps per SM
 #endif
@@ -243,8 +246,12 @@ __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_nuc(
             continue;
         }
         uint32_t w[8];
+#if NUC_FASTDEC
+        mg_decode32(n, w);
+#else
 #pragma unroll
         for (int k = 0; k < 4; k++) mg_decode8(n[k], w[2 * k], w[2 * k + 1]);
+#endif
         st32(out + P0 + p, w);
     }
 
@@ -474,6 +481,7 @@ extern "C" int mg_emit_nuc_device(mg_plan *p, uint8_t *out_dev, void *stream) {
     mg_genome *g = p->g;
     cudaStream_t st = (cudaStream_t)stream;
     p->last_stream = st;
+    if (mg_emit_mode() == 2) return mg_launch_nuc_stream(p, out_dev, st);
     if (mg_emit_mode() == 1) return mg_launch_nuc_tma(p, out_dev, st);
     k_emit_nuc<<<(unsigned)p->n_nuc_tile, NUC_THREADS, 0, st>>>(g->d_packed, p->d_piece_off, p->d_piece_src, p->n_piece, p->d_nuc_tile,
                                                               p->d_totals, p->nuc_total, g->total_bases, p->d_lit, g->d_exc_pos, g->d_exc_byte, g->n_exc, out_dev);

@@ -84,6 +84,23 @@ __device__ __forceinline__ void st32(uint8_t *p, const uint32_t w[8]) {         
                  "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 
+// 32 nibbles -> 32 ASCII bytes.  Chunks without N / IUPAC / '-' codes (bit 3 clear in every nibble: A C G T a c g t) need two
+// table look-ups per word; the general decode needs four plus the two select masks (and, at 32 registers, re-materialises
+// its four table constants: 70 instructions per chunk in the round-1 SASS against ~20 here).
+__device__ __forceinline__ void mg_decode32(const uint32_t n[4], uint32_t w[8]) {
+    if (((n[0] | n[1] | n[2] | n[3]) & 0x88888888u) == 0) {
+        const uint32_t LA = 0x54474341u, LB = 0x74676361u;    // "ACGT", "acgt"
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            w[2 * k] = __byte_perm(LA, LB, n[k]);
+            w[2 * k + 1] = __byte_perm(LA, LB, n[k] >> 16);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) mg_decode8(n[k], w[2 * k], w[2 * k + 1]);
+    }
+}
+
 // ---- generic (slow, always correct) assembly of one 32-byte chunk straight from global memory -------------------
 // Walks the piece table from piece j (piece_off[j] <= P), genome and literal pieces alike.  Used by the literal-chunk
 // kernel (every chunk that contains framing bytes) and by K2 for tiles whose piece list overflows its staging.

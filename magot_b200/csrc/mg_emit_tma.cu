@@ -374,7 +374,7 @@ int mg_emit_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char *e = getenv("MAGOT_EMIT");
-        mode = (e && !strcmp(e, "ldg")) ? 0 : 1;
+        mode = (e && !strcmp(e, "tma")) ? 1 : (e && !strcmp(e, "stream")) ? 2 : 0;
     }
     return mode;
 }

@@ -43,6 +43,13 @@ extern "C" int mg_stream_sync(int device, void *stream) {
     return MG_OK;
 }
 
+extern "C" int mg_copy_d2h_async(int device, void *dst_host, const void *src_dev, int64_t n, void *stream) {
+    MG_REQUIRE(n >= 0 && (n == 0 || (dst_host && src_dev)), "bad copy arguments");
+    MG_CUDA(cudaSetDevice(device));
+    if (n > 0) MG_CUDA(cudaMemcpyAsync(dst_host, src_dev, (size_t)n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return MG_OK;
+}
+
 // ---- 4096-entry translation table -----------------------------------------------------------------
 // index = n0 | n1<<4 | n2<<8 (n0 = first base of the codon, nibble codes as above).  Any nibble >= 8
 // (N, n, '-', IUPAC, exception) gives 'X' (genome.py:816-817); case bit 2 is ignored, which is the

@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256, PLAN_MINB) k_plan_pieces(int64_t n_piece,
                                                      const int64_t *__restrict__ contig_base, int64_t n_contigs, int64_t two_T,
                                                      unsigned long long *tmp, int64_t *__restrict__ piece_off,
                                                      int64_t *__restrict__ piece_src, int64_t *__restrict__ total_out,
-                                                     int64_t *__restrict__ tile_first, int64_t tile_cap) {
+                                                     int64_t *__restrict__ tile_first, int64_t tile_cap,
+                                                     int32_t *__restrict__ blk1k, int64_t blk1k_cap) {
     // The PLAN_TILE pieces of a block belong to at most PLAN_TILE/2 + 1 consecutive records starting at blk_r0[block]
     // (k_plan_block_rec): F(r) = rec_seg_off[r] + 2r of those records is staged in shared memory and every thread
     // searches there.
@@ -129,6 +130,11 @@ __global__ void __launch_bounds__(256, PLAN_MINB) k_plan_pieces(int64_t n_piece,
                 for (int64_t t = (run + MG_NUC_TILE - 1) / MG_NUC_TILE; t * MG_NUC_TILE < run + len[it] && t < tile_cap; t++)
                     tile_first[t] = p0 + it;
             }
+            // the same at 1 KB granularity (one warp of k_emit_nuc_stream = one 1 KB block): a piece of ~190 bytes holds the first
+            // byte of a block once in five times
+            if (len[it] > 0) {
+                for (int64_t t = (run + 1023) >> 10; (t << 10) < run + len[it] && t < blk1k_cap; t++) blk1k[t] = (int32_t)(p0 + it);
+            }
         }
         run += len[it];
     }
@@ -140,6 +146,8 @@ __global__ void __launch_bounds__(256, PLAN_MINB) k_plan_pieces(int64_t n_piece,
             const int64_t n_tile = min(tile_cap, (all + MG_NUC_TILE - 1) / MG_NUC_TILE);
             tile_first[n_tile] = n_piece > 0 ? n_piece - 1 : 0;
         }
+        const int64_t n_blk = (all + 1023) >> 10;
+        if (n_blk < blk1k_cap) blk1k[n_blk] = (int32_t)(n_piece > 0 ? n_piece - 1 : 0);
     }
 }
 
@@ -269,6 +277,7 @@ extern "C" int mg_plan_create(mg_genome *g, int64_t n_rec, const int64_t *rec_se
     MG_REQUIRE(n_seg == 0 || (seg_contig && seg_start && seg_end && seg_strand), "segment arrays are NULL");
     MG_REQUIRE(n_rec == 0 || (rec_lit_off && rec_pre_len && rec_suf_len), "record arrays are NULL");
     MG_REQUIRE(rec_seg_off[0] == 0 && rec_seg_off[n_rec] == n_seg, "rec_seg_off must start at 0 and end at n_seg");
+    MG_REQUIRE(n_seg + 2 * n_rec < 0x7fffffff, "more than 2^31 pieces in one plan: split the table");
     MG_CUDA(cudaSetDevice(g->device));
     cudaStream_t st = (cudaStream_t)stream;
     mg_plan *p = new mg_plan();
@@ -300,6 +309,20 @@ extern "C" int mg_plan_create(mg_genome *g, int64_t n_rec, const int64_t *rec_se
     }
     if (rec_phase) TRY(upload(p, &p->d_rec_phase, rec_phase, n_rec, st));
     TRY(dalloc(p, &p->d_blk_r0, (p->n_piece + PLAN_TILE - 1) / PLAN_TILE + 1, st));
+    {   // upper bound of the nucleotide text size from the host tables (clamping on the device can only shorten a segment)
+        int64_t up = 0;
+        for (int64_t e = 0; e < n_seg; e++) {
+            int64_t d = seg_end[e] - seg_start[e] + 1;
+            const int32_t c = seg_contig[e];
+            const int64_t L = (c >= 0 && c < g->n_contigs) ? g->h_contig_len[c] : 0;
+            if (seg_start[e] > seg_end[e] || d > L) d = L;          // unsorted pairs can wrap around (Python slice rules): bound by the contig
+            if (d > 0) up += d < 0x7fffffff ? d : 0x7fffffff;
+        }
+        for (int64_t r = 0; r < n_rec; r++) up += (int64_t)rec_pre_len[r] + rec_suf_len[r];
+        p->nuc_upper = up;
+        p->blk1k_cap = (up >> 10) + 3;
+        TRY(dalloc(p, &p->d_blk1k, p->blk1k_cap, st));
+    }
     TRY(dalloc(p, &p->d_piece_src, p->n_piece, st));
     TRY(dalloc(p, &p->d_piece_off, p->n_piece + 1, st));
     TRY(dalloc(p, &p->d_prot_off, n_rec + 1, st));
@@ -348,7 +371,7 @@ static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st, bool s
     k_plan_pieces<<<(unsigned)n_block, 256, 0, st>>>(
         p->n_piece, p->n_rec, p->d_rec_seg_off, p->d_blk_r0, p->d_seg_contig, p->d_seg_start, p->d_seg_end, p->d_seg_strand,
         p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, g->d_contig_len, g->d_contig_base, g->n_contigs, 2 * g->total_bases,
-        tmp_a, p->d_piece_off, p->d_piece_src, p->d_totals, tf_nuc, p->n_nuc_tile);
+        tmp_a, p->d_piece_off, p->d_piece_src, p->d_totals, tf_nuc, p->n_nuc_tile, p->d_blk1k, p->blk1k_cap);
     MG_LAUNCH_CHECK();
     k_plan_records<<<(unsigned)n_rblock, 256, 0, st>>>(
         p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_piece_src, g->d_packed, p->d_rec_phase, prot_flags,
