@@ -193,6 +193,20 @@ int mg_stream_sync(int device, void *stream);
  * for full PCIe speed): the output side of `print annotation_set.get_fasta(...)` (genome_tools.py:324-330) when the caller
  * places the texts of several shards / GPUs in one host buffer itself.                                                */
 int mg_copy_d2h_async(int device, void *dst_host, const void *src_dev, int64_t n, void *stream);
+/* CUDA graphs: capture everything queued on `stream` (and on streams joined to it with mg_stream_wait_stream) between
+ * mg_graph_begin and mg_graph_end -- e.g. mg_plan_prepare_async + mg_emit_*_device of several plans, none of which waits for
+ * the host -- and replay it with one launch.  The batch-level counterpart of the reference's per-object loop
+ * `for obj in table: obj.get_fasta()` (genome.py:578-582).  Buffers and plan handles used inside must stay alive and unchanged
+ * in size while the graph is in use.                                                                                    */
+int mg_graph_begin(int device, void *stream);
+int mg_graph_end(int device, void *stream, void **graph_exec_out);
+int mg_graph_launch(int device, void *graph_exec, void *stream);
+int mg_graph_destroy(void *graph_exec);
+/* `waiter` waits for everything queued so far on `signaller` (event record + wait; usable inside a capture). */
+int mg_stream_wait_stream(int device, void *waiter, void *signaller);
+/* Developer / test knob: run-time choice between kernel variants that give bit-identical results ("emit": 0 = k_emit_nuc
+ * (default), 1 = bulk-copy staged, 2 = streaming; "k1": 0 = piece-parallel plan launches (default), 1 = one-launch plan kernel).  */
+int mg_tune(const char *key, int value);
 /* Number of kernels launched by this library since load (per process), for bench accounting. */
 int64_t mg_kernel_launches(void);
 

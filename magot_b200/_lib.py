@@ -73,6 +73,12 @@ SIGNATURES = {
     "mg_sixframe_emit_device": (_i32, [_vp, _vp, _vp, _vp]),
     "mg_stream_sync": (_i32, [_i32, _vp]),
     "mg_copy_d2h_async": (_i32, [_i32, _vp, _vp, _i64, _vp]),
+    "mg_tune": (_i32, [ctypes.c_char_p, _i32]),
+    "mg_graph_begin": (_i32, [_i32, _vp]),
+    "mg_graph_end": (_i32, [_i32, _vp, _pp]),
+    "mg_graph_launch": (_i32, [_i32, _vp, _vp]),
+    "mg_graph_destroy": (_i32, [_vp]),
+    "mg_stream_wait_stream": (_i32, [_i32, _vp, _vp]),
     "mg_kernel_launches": (_i64, []),
 }
 

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 #include <vector>
 #include "../../include/magot_b200.h"
@@ -30,7 +31,7 @@
 
 // ---- host-side error plumbing -----------------------------------------------------------------
 void mg_set_error(const char *fmt, ...);
-extern int64_t g_mg_launches;
+extern std::atomic<int64_t> g_mg_launches;        // kernels launched by this library (any host thread)
 #define MG_COUNT_LAUNCH() (++g_mg_launches)
 
 #define MG_CUDA(call)                                                                             \
@@ -117,6 +118,7 @@ struct mg_plan {
     int64_t n_nuc_tile = 0, n_prot_tile = 0;
     int32_t *d_blk1k = nullptr;               // first piece of every 1 KB block of the nucleotide text (+ sentinel), for k_emit_nuc_stream
     int64_t blk1k_cap = 0;                    // entries the table can take (from the host-side upper bound of the text size)
+    int64_t max_seg_per_rec = 0;             // longest record (segments): k_plan_rec walks a record with one thread
     int64_t nuc_upper = 0;                    // host-side upper bound of the nucleotide text size: sum(max(0, end-start+1)) + framing
     int64_t *d_tile_buf = nullptr;
     int64_t tile_cap = 0;

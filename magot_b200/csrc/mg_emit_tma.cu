@@ -370,13 +370,24 @@ __global__ void __launch_bounds__(T2_THREADS, T2_MINB) k_emit_nuc_tma(
 }
 
 // ---- host API -------------------------------------------------------------------------------------------------
+static int g_emit_mode = -1;
 int mg_emit_mode() {
-    static int mode = -1;
-    if (mode < 0) {
+    if (g_emit_mode < 0) {
         const char *e = getenv("MAGOT_EMIT");
-        mode = (e && !strcmp(e, "tma")) ? 1 : (e && !strcmp(e, "stream")) ? 2 : 0;
+        g_emit_mode = (e && !strcmp(e, "tma")) ? 1 : (e && !strcmp(e, "stream")) ? 2 : 0;
     }
-    return mode;
+    return g_emit_mode;
+}
+
+// Developer / test knob: select a kernel variant at run time (the variants are bit-identical in their results; tests run all of
+// them).  "emit": 0 = k_emit_nuc (default), 1 = k_emit_nuc_tma, 2 = k_emit_nuc_stream; "k1": 0 = piece-parallel launches (default), 1 = k_plan_rec.
+void mg_set_k1_mode(int v);
+extern "C" int mg_tune(const char *key, int value) {
+    MG_REQUIRE(key != nullptr, "key is NULL");
+    if (!strcmp(key, "emit")) { MG_REQUIRE(value >= 0 && value <= 2, "emit variant must be 0, 1 or 2"); g_emit_mode = value; return MG_OK; }
+    if (!strcmp(key, "k1")) { mg_set_k1_mode(value); return MG_OK; }
+    mg_set_error("mg_tune: unknown key '%s'", key);
+    return MG_EINVAL;
 }
 
 int mg_launch_nuc_tma(mg_plan *p, uint8_t *out_dev, cudaStream_t st) {

@@ -14,6 +14,8 @@
 // Replaces the per-child bookkeeping of ParentAnnotation.get_fasta (genome.py:687-705) and the slice
 // arithmetic of BaseAnnotation.get_seq (genome.py:603-608).
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include "mg_common.cuh"
 #include "mg_gather.cuh"
 #include "mg_lookback.cuh"
@@ -217,6 +219,174 @@ __global__ void __launch_bounds__(256) k_plan_records(int64_t n_rec, const int64
     }
 }
 
+
+// ---- K1 in ONE kernel: thread per record ---------------------------------------------------------------------------------
+// Round 1 ran K1 as a memset + three dependent launches (record of every 1024-piece block, thread per piece, thread per
+// record): 65-85 us of mostly launch and load latency that does not shrink with the batch (37 us for 1/8 of config 4: the
+// limiter of strong scaling, SCALE_r01 / bench line r2g).  Here a thread walks the segments of its record twice: pass 1 clamps
+// (Python slice rules, genome.py:606), sums the payload and picks up the first codon for trimX (genome.py:819-821); two block
+// scans + decoupled look-backs give the record's offsets in the nucleotide and the protein text; pass 2 writes the piece
+// table and the tile / 1 KB block tables.  No record search, no staging, one launch.  A record's pieces are contiguous, so a
+// thread writes a contiguous run of both tables.  Used when no record has more than PR_MAXSEG segments (the slowest thread
+// bounds the kernel); else the piece-parallel kernels above.
+#define PR_THREADS 256
+#ifndef PR_MAXSEG
+#define PR_MAXSEG 256
+#endif
+
+struct pr_seg { int64_t src; int64_t n; };             // piece source (plane index of its first emitted base) and clamped length
+
+__device__ __forceinline__ pr_seg pr_clamp(int64_t e, const int32_t *__restrict__ seg_contig, const int64_t *__restrict__ seg_start,
+                                           const int64_t *__restrict__ seg_end, const int8_t *__restrict__ seg_strand,
+                                           const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base,
+                                           int64_t n_contigs, int64_t two_T) {
+    const int32_t c = __ldg(seg_contig + e);
+    int64_t src = MG_FRONT_PAD, n = 0;
+    if (c >= 0 && c < n_contigs) {
+        const int64_t L = __ldg(contig_len + c);
+        // contig[start-1:end] with Python slice semantics (genome.py:606)
+        int64_t i = __ldg(seg_start + e) - 1, j = __ldg(seg_end + e);
+        if (i < 0) { i += L; if (i < 0) i = 0; } else if (i > L) i = L;
+        if (j < 0) { j += L; if (j < 0) j = 0; } else if (j > L) j = L;
+        n = j > i ? j - i : 0;
+        if (n > 0x7fffffff) n = 0x7fffffff;
+        src = __ldg(contig_base + c) + i;
+    }
+    // '-' strand: forward bases [src, src+n) are bases [2T-src-n, 2T-src) of the reverse-complement plane, in the order
+    // Sequence.reverse_compliment emits them (genome.py:784-793)
+    pr_seg r;
+    r.src = __ldg(seg_strand + e) ? two_T - src - n : src;
+    r.n = n;
+    return r;
+}
+
+__device__ __forceinline__ void pr_scatter(int64_t off, int64_t len, int64_t p, int64_t *__restrict__ tile_first, int64_t tile_cap,
+                                           int32_t *__restrict__ blk1k, int64_t blk1k_cap) {
+    if (len <= 0) return;
+    if (tile_first)
+        for (int64_t t = (off + MG_NUC_TILE - 1) / MG_NUC_TILE; t * MG_NUC_TILE < off + len && t < tile_cap; t++) tile_first[t] = p;
+    for (int64_t t = (off + 1023) >> 10; (t << 10) < off + len && t < blk1k_cap; t++) blk1k[t] = (int32_t)p;
+}
+
+#define PR_RECS 128                                   // records per block (threads 0..127 own one each)
+#ifndef PR_SEGCAP
+#define PR_SEGCAP 3072                                // clamped segments staged per block (config 4: ~1500); the rest is re-clamped from global memory
+#endif
+
+__global__ void __launch_bounds__(PR_THREADS) k_plan_rec(
+    int64_t n_rec, int64_t n_piece, const int64_t *__restrict__ rec_seg_off, const int32_t *__restrict__ seg_contig,
+    const int64_t *__restrict__ seg_start, const int64_t *__restrict__ seg_end, const int8_t *__restrict__ seg_strand,
+    const int64_t *__restrict__ rec_lit_off, const int32_t *__restrict__ rec_pre, const int32_t *__restrict__ rec_suf,
+    const int8_t *__restrict__ rec_phase, int flags, const int64_t *__restrict__ contig_len, const int64_t *__restrict__ contig_base,
+    int64_t n_contigs, int64_t two_T, const uint32_t *__restrict__ packed, unsigned long long *tmp_a, unsigned long long *tmp_b,
+    int64_t *__restrict__ piece_off, int64_t *__restrict__ piece_src, int64_t *__restrict__ prot_off, int32_t *__restrict__ rec_aa,
+    int8_t *__restrict__ rec_skip, int64_t *__restrict__ totals, int64_t *__restrict__ tf_nuc, int64_t cap_nuc,
+    int64_t *__restrict__ tf_prot, int64_t cap_prot, int32_t *__restrict__ blk1k, int64_t blk1k_cap) {
+    // Phase 1 (all threads, parallel over the block's segments, coalesced): clamp every segment once into shared memory.
+    // Phase 2 (thread per record, serial over ITS segments in shared memory): payload length, first codon, protein length.
+    // Phase 3: block scans + look-backs.  Phase 4 (thread per record): piece table, tile tables.
+    __shared__ int64_t s_src[PR_SEGCAP];
+    __shared__ int32_t s_n[PR_SEGCAP];
+    __shared__ int64_t s_warp[8];
+    __shared__ int64_t s_prefix;
+    __shared__ unsigned int s_tile;
+    const int64_t tile = mg_next_tile(tmp_a, &s_tile);
+    const int64_t r_first = tile * PR_RECS;
+    const int64_t r_last = min(r_first + PR_RECS, n_rec);
+    const int64_t e_lo = __ldg(rec_seg_off + r_first), e_hi = __ldg(rec_seg_off + r_last);
+    const int n_stage = (int)min(e_hi - e_lo, (int64_t)PR_SEGCAP);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n_stage; i += PR_THREADS) {
+        const pr_seg sg = pr_clamp(e_lo + i, seg_contig, seg_start, seg_end, seg_strand, contig_len, contig_base, n_contigs, two_T);
+        s_src[i] = sg.src;
+        s_n[i] = (int32_t)sg.n;
+    }
+    __syncthreads();
+    const int64_t r = r_first + threadIdx.x;
+    const bool mine = threadIdx.x < PR_RECS && r < n_rec;
+    int64_t s0 = 0, s1 = 0, L = 0, lit = 0;
+    int pre = 0, suf = 0;
+    int64_t naa = 0;
+    int skip = 0;
+    if (mine) {
+        s0 = __ldg(rec_seg_off + r);
+        s1 = __ldg(rec_seg_off + r + 1);
+        pre = rec_pre[r];
+        suf = rec_suf[r];
+        lit = rec_lit_off[r];
+        if ((flags & MG_PROT_USE_PHASE) && rec_phase) { skip = rec_phase[r]; if (skip < 0 || skip > 2) skip = 0; }
+        uint32_t first = 0;                              // the first five spliced bases (a codon after a phase of 0..2)
+        int got = 0;
+        for (int64_t e = s0; e < s1; e++) {
+            pr_seg sg;
+            const int64_t i = e - e_lo;
+            if (i < n_stage) { sg.src = s_src[i]; sg.n = s_n[i]; }
+            else sg = pr_clamp(e, seg_contig, seg_start, seg_end, seg_strand, contig_len, contig_base, n_contigs, two_T);
+            if (got < 5 && sg.n > 0) {
+                const int take = (int)min((int64_t)(5 - got), sg.n);
+                const uint32_t v = (uint32_t)mg_ld_nib16(packed, sg.src) & ((1u << (4 * take)) - 1u);
+                first |= v << (4 * got);
+                got += take;
+            }
+            L += sg.n;
+        }
+        const int64_t Lp = L - skip;
+        if (Lp <= 2) {
+            naa = -1;                                    // reference returns None (genome.py:810)
+        } else {
+            naa = Lp / 3;
+            if ((flags & MG_PROT_TRIMX) && (((first >> (4 * skip)) & 0xFFFu) & 0x888u)) { naa -= 1; skip += 3; }   // one leading X (genome.py:819-821)
+        }
+        if (naa > 0x7fffffff) naa = 0x7fffffff;
+        rec_aa[r] = (int32_t)naa;
+        rec_skip[r] = (int8_t)skip;
+    }
+    const int64_t nbytes = mine ? pre + L + suf : 0;
+    const int64_t pbytes = mine ? pre + (naa > 0 ? naa : 0) + suf : 0;
+    int64_t tot_n, tot_p;
+    const int64_t incl_n = mg_block_incl_scan(nbytes, s_warp, &tot_n);
+    const int64_t pre_n = mg_lookback(tmp_a, tile, tot_n, &s_prefix);
+    const int64_t incl_p = mg_block_incl_scan(pbytes, s_warp, &tot_p);
+    const int64_t pre_p = mg_lookback(tmp_b, tile, tot_p, &s_prefix);
+    if (mine) {
+        int64_t off = pre_n + incl_n - nbytes;
+        int64_t p = s0 + 2 * r;
+        piece_off[p] = off;
+        piece_src[p] = lit | (int64_t)(MG_KIND_LIT << MG_KIND_SHIFT);
+        pr_scatter(off, pre, p, tf_nuc, cap_nuc, blk1k, blk1k_cap);
+        off += pre;
+        p++;
+        for (int64_t e = s0; e < s1; e++, p++) {
+            pr_seg sg;
+            const int64_t i = e - e_lo;
+            if (i < n_stage) { sg.src = s_src[i]; sg.n = s_n[i]; }
+            else sg = pr_clamp(e, seg_contig, seg_start, seg_end, seg_strand, contig_len, contig_base, n_contigs, two_T);
+            piece_off[p] = off;
+            piece_src[p] = sg.src;
+            pr_scatter(off, sg.n, p, tf_nuc, cap_nuc, blk1k, blk1k_cap);
+            off += sg.n;
+        }
+        piece_off[p] = off;
+        piece_src[p] = (lit + pre) | (int64_t)(MG_KIND_LIT << MG_KIND_SHIFT);
+        pr_scatter(off, suf, p, tf_nuc, cap_nuc, blk1k, blk1k_cap);
+        const int64_t poff = pre_p + incl_p - pbytes;
+        prot_off[r] = poff;
+        if (tf_prot && pbytes > 0)
+            for (int64_t t = (poff + MG_PROT_TILE - 1) / MG_PROT_TILE; t * MG_PROT_TILE < poff + pbytes && t < cap_prot; t++) tf_prot[t] = r;
+    }
+    if (tile == gridDim.x - 1 && threadIdx.x == 0) {
+        const int64_t all_n = pre_n + tot_n, all_p = pre_p + tot_p;
+        piece_off[n_piece] = all_n;
+        prot_off[n_rec] = all_p;
+        totals[0] = all_n;
+        totals[1] = all_p;
+        if (tf_nuc) tf_nuc[min(cap_nuc, (all_n + MG_NUC_TILE - 1) / MG_NUC_TILE)] = n_piece > 0 ? n_piece - 1 : 0;
+        if (tf_prot) tf_prot[min(cap_prot, (all_p + MG_PROT_TILE - 1) / MG_PROT_TILE)] = n_rec > 0 ? n_rec - 1 : 0;
+        const int64_t n_blk = (all_n + 1023) >> 10;
+        if (n_blk < blk1k_cap) blk1k[n_blk] = (int32_t)(n_piece > 0 ? n_piece - 1 : 0);
+    }
+}
+
 // thread per tile: index of the piece / record that contains the tile's first byte; nucleotide tiles first, then protein
 // tiles.  The tile counts come from the totals ON THE DEVICE, so the launch needs no host round trip: the grid covers
 // cap_a + cap_b + 2 slots (capacities of the two tables), threads beyond the real counts do nothing.
@@ -245,6 +415,17 @@ __global__ void __launch_bounds__(256) k_plan_lengths(int64_t n_rec, const int64
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
+// K1 variant: env MAGOT_K1 or mg_tune("k1", v): 0 (default) = the three piece-parallel launches; 1 = k_plan_rec, one launch
+// (measured on config 4: 0.105 / 0.121 ms per plan against 0.077 / 0.085 ms -- kept as a tested variant, not the default)
+static int g_k1_mode = -1;
+static int mg_k1_mode() {
+    if (g_k1_mode < 0) {
+        const char *e = getenv("MAGOT_K1");
+        g_k1_mode = (e && !strcmp(e, "rec")) ? 1 : 0;
+    }
+    return g_k1_mode;
+}
+void mg_set_k1_mode(int v) { g_k1_mode = v ? 1 : 0; }
 
 template <typename T>
 static int upload(mg_plan *p, T **dst, const T *src, int64_t n, cudaStream_t st) {
@@ -329,7 +510,8 @@ extern "C" int mg_plan_create(mg_genome *g, int64_t n_rec, const int64_t *rec_se
     TRY(dalloc(p, &p->d_rec_aa, n_rec, st));
     TRY(dalloc(p, &p->d_rec_skip, n_rec, st));
     // look-back scratch: [ticket, status per 256-piece block] [ticket, status per 256-record block] [nuc total, prot total]
-    p->scan_tmp_cap = (p->n_piece + PLAN_TILE - 1) / PLAN_TILE + 1 + (n_rec + 255) / 256 + 1 + 2;
+    p->scan_tmp_cap = (p->n_piece + PLAN_TILE - 1) / PLAN_TILE + 1 + 2 * ((n_rec + 127) / 128 + 1) + 2;
+    for (int64_t r = 0; r < n_rec; r++) p->max_seg_per_rec = std::max(p->max_seg_per_rec, rec_seg_off[r + 1] - rec_seg_off[r]);
     TRY(dalloc(p, &p->d_scan_tmp, p->scan_tmp_cap, st));
 #undef TRY
     *out = p;
@@ -366,6 +548,18 @@ static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st, bool s
         tf_prot = p->d_prot_tile;
     }
     if (p->n_rec == 0) return MG_OK;
+    if (p->max_seg_per_rec <= PR_MAXSEG && mg_k1_mode() == 1) {     // K1 in one launch
+        const int64_t n_tile = (p->n_rec + PR_RECS - 1) / PR_RECS;
+        unsigned long long *ta = reinterpret_cast<unsigned long long *>(p->d_scan_tmp), *tb = ta + n_tile + 1;
+        p->d_totals = reinterpret_cast<int64_t *>(p->d_scan_tmp + p->scan_tmp_cap - 2);
+        k_plan_rec<<<(unsigned)n_tile, PR_THREADS, 0, st>>>(
+            p->n_rec, p->n_piece, p->d_rec_seg_off, p->d_seg_contig, p->d_seg_start, p->d_seg_end, p->d_seg_strand, p->d_rec_lit_off,
+            p->d_rec_pre, p->d_rec_suf, p->d_rec_phase, prot_flags, g->d_contig_len, g->d_contig_base, g->n_contigs, 2 * g->total_bases,
+            g->d_packed, ta, tb, p->d_piece_off, p->d_piece_src, p->d_prot_off, p->d_rec_aa, p->d_rec_skip, p->d_totals, tf_nuc,
+            p->n_nuc_tile, tf_prot, p->n_prot_tile, p->d_blk1k, p->blk1k_cap);
+        MG_LAUNCH_CHECK();
+        return MG_OK;
+    }
     k_plan_block_rec<<<(unsigned)n_rblock, 256, 0, st>>>(n_block, p->n_rec, p->d_rec_seg_off, p->d_blk_r0);
     MG_LAUNCH_CHECK();
     k_plan_pieces<<<(unsigned)n_block, 256, 0, st>>>(

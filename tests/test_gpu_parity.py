@@ -828,3 +828,90 @@ def test_setitem_on_built_genome(mg):
     assert str(gs["a"]) == "CCCC" and str(gs["c"]) == "TTTTRYAAAA" and len(gs) == 3
     assert str(mg.Sequence(gs["c"][0:6]).reverse_compliment()) == "nnAAAA"
     gs.close()
+
+
+# ---- kernel variants (mg_tune): every K1 / K2 variant gives the same bytes ------------------------------------------
+
+@pytest.fixture()
+def tune(mg):
+    from magot_b200 import _lib
+
+    def set_(key, v):
+        _lib.check(_lib.lib.mg_tune(key.encode(), v))
+    yield set_
+    set_("emit", 0)
+    set_("k1", 0)
+
+
+@pytest.mark.parametrize("emit,k1", [(0, 1), (0, 0), (1, 1), (2, 1), (2, 0), (1, 0)])
+def test_kernel_variants_bit_identical(mg, tune, emit, k1):
+    """K2 as k_emit_nuc / k_emit_nuc_tma / k_emit_nuc_stream and K1 as k_plan_rec / the piece-parallel launches, against the C
+    oracle: a synthetic twin of config 4 with FASTA framing (hundreds of 32 KB tiles, out-of-alphabet bytes), a table of tiny
+    segments (staging overflow paths) and randomised tables with negative / overrunning coordinates."""
+    from magot_b200 import engine, synth
+    tune("emit", emit)
+    tune("k1", k1)
+    layout = synth.contig_layout("human", 6_000_000, 4)
+    contigs = synth.synth_genome_host(layout, 4, n_mean=300)
+    rng = np.random.default_rng(11)
+    for a in contigs[:6]:
+        idx = rng.integers(0, a.size, size=80)
+        a[idx] = np.frombuffer(b"RYKMSWBDHVrykm*", dtype=np.uint8)[rng.integers(0, 15, size=80)]
+    ann = synth.synth_annotation(layout, 3000, 4)
+    g = engine.DeviceGenome([a.size for a in contigs], device=0)
+    for i, a in enumerate(contigs):
+        g.pack(i, a)
+    g.finalize()
+    for which in ("cds", "exon"):
+        tbl = ann.table(which, framing=False)
+        nuc, off, aa, aa_off, aa_len = _oracle_products(contigs, tbl)
+        tblf = ann.table(which, framing=True)
+        for sync in (True, False):
+            plan = engine.Plan(g, tblf)
+            if sync:
+                plan.prepare()
+            else:
+                plan.prepare_async()
+                plan.totals()
+            got_n, got_a = plan.lengths()
+            assert np.array_equal(got_n, np.diff(off)) and np.array_equal(got_a, aa_len)
+            text = plan.emit_host(protein=False).tobytes()
+            textp = plan.emit_host(protein=True).tobytes()
+            plan.close()
+            want = b"".join(b">" + n.encode() + b"\n" + nuc[off[i]:off[i + 1]].tobytes() + b"\n" for i, n in enumerate(ann.names))
+            wantp = b"".join(b">" + n.encode() + b"\n" + aa[aa_off[i]:aa_off[i + 1]].tobytes() + b"\n" for i, n in enumerate(ann.names))
+            assert text == want and textp == wantp, (which, sync)
+    # thousands of 1-8 base segments per tile, with and without framing
+    n_rec = 300
+    n_seg = rng.integers(20, 200, size=n_rec)
+    n_seg[7] = 700                                        # longer than one thread of k_plan_rec takes: the piece-parallel K1 runs
+    if emit == 2:
+        n_seg[7] = 150
+    rec_off = np.concatenate(([0], np.cumsum(n_seg)))
+    E = int(rec_off[-1])
+    cid = rng.integers(0, len(contigs), size=E).astype(np.int32)
+    Ls = np.array([a.size for a in contigs], dtype=np.int64)[cid]
+    st = rng.integers(1, Ls - 10)
+    en = st + rng.integers(0, 8, size=E)
+    sd = rng.integers(0, 2, size=E).astype(np.int8)
+    for framing in (False, True):
+        pre = (rng.integers(1, 40, size=n_rec) if framing else np.zeros(n_rec)).astype(np.int32)
+        suf = (np.ones(n_rec) if framing else np.zeros(n_rec)).astype(np.int32)
+        lit = rng.integers(33, 127, size=int(pre.sum() + suf.sum()), dtype=np.uint8)
+        lit_off = np.concatenate(([0], np.cumsum(pre.astype(np.int64) + suf)[:-1]))
+        tbl = engine.RecordTable(rec_off, cid, st, en, sd, lit_off, pre, suf, lit)
+        nuc, off = coracle.splice([a.tobytes() for a in contigs], rec_off, cid, st - 1, en, sd)
+        aa, aa_off, aa_len = coracle.splice_translate(nuc, off)
+        text, _ = engine.run_table(g, tbl)
+        textp, _ = engine.run_table(g, tbl, protein=True)
+        want, wantp = [], []
+        for r in range(n_rec):
+            p0 = int(lit_off[r])
+            head, tail = lit[p0:p0 + pre[r]].tobytes(), lit[p0 + pre[r]:p0 + pre[r] + suf[r]].tobytes()
+            want.append(head + nuc[off[r]:off[r + 1]].tobytes() + tail)
+            wantp.append(head + aa[aa_off[r]:aa_off[r + 1]].tobytes() + tail)
+        assert text == b"".join(want) and textp == b"".join(wantp), framing
+    g.close()
+    for seed in (0, 1, 2, 3):
+        test_random_tables_differential(mg, seed)
+    test_edge_records(mg)
