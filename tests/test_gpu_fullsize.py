@@ -1,6 +1,12 @@
 """Parity at BASELINE.json's FULL sizes (config 3: 500 Mbp / 60 k transcripts; configs 4 and 5: 3.1 Gbp genome, 200 k
-transcripts, whole-genome six-frame) through size-independent
-properties -- the C oracle cannot redo 800 Mbp of text in seconds, so the checks are:
+transcripts, whole-genome six-frame).
+
+WHOLE-TEXT parity against the C oracle (oracle/oracle.c) on HOST-KNOWN bytes: the synthetic genome text is copied to the host
+by torch BEFORE the library packs it, the oracle splices / translates ALL records of configs 3 and 4 from those bytes, and
+every byte of the three products (CDS nucleotides, CDS protein, exon transcripts; with and without FASTA framing) is
+compared; config 5's full ORF list of the 170 scaffolds and one chromosome is compared with the oracle's six-frame scan.
+
+Plus size-independent properties:
 
   * sampled records: K2's text of a record == its framing + the record's segments fetched one by one through the
     independent range-decode path (mg_genome_fetch, strand-aware) and, for those records, K3's protein == the C oracle's
@@ -36,16 +42,24 @@ def _build(kind, genome_bp, n_tx, seed):
     layout = synth.contig_layout(kind, genome_bp, seed)
     g = engine.DeviceGenome([l for _, l in layout], device=0)
     CH = 256 << 20
+    host = []                                            # the genome text as torch produced it, never touched by the library
     for ci, (_, L) in enumerate(layout):
+        h = np.empty(L, dtype=np.uint8)
         for off in range(0, L, CH):
             n = min(CH, L - off)
             a = synth.synth_contig_device(n, seed * 1000003 + ci * 64 + off // CH, dev)
+            h[off:off + n] = a.cpu().numpy()
             g.pack_device(ci, a.data_ptr(), n, offset=off)
             torch.cuda.synchronize()
             del a
+        host.append(h)
     g.finalize()
     torch.cuda.empty_cache()
+    _HOST[id(g)] = host
     return g, layout, synth.synth_annotation(layout, n_tx, seed)
+
+
+_HOST = {}
 
 
 @pytest.fixture(scope="module")
@@ -80,6 +94,82 @@ def _record_offsets(table, nuc_len):
     """Start of every record in the nucleotide text: prefix + spliced payload + suffix, back to back."""
     sizes = table.rec_pre_len.astype(np.int64) + nuc_len + table.rec_suf_len.astype(np.int64)
     return np.concatenate(([0], np.cumsum(sizes)))
+
+
+def _check_whole_text(fixture, which):
+    """Every byte of the products of ALL records against the C oracle run on the host copy of the genome text."""
+    g, layout, ann = fixture
+    host = _HOST[id(g)]
+    lens = np.array([l for _, l in layout], dtype=np.int64)
+    tbl = ann.table(which, framing=False)
+    lo = np.clip(tbl.seg_start - 1, 0, lens[tbl.seg_contig])
+    hi = np.clip(tbl.seg_end, 0, lens[tbl.seg_contig])
+    nuc, off = coracle.splice(host, tbl.rec_seg_off, tbl.seg_contig, lo, hi, tbl.seg_strand)
+    assert nuc.size == ann.spliced_bp(which)
+    text, nuc_len, aa_len = _emit(g, tbl)
+    assert np.array_equal(nuc_len, np.diff(off))
+    assert text.size == nuc.size and np.array_equal(text, nuc), "spliced nucleotides (%s, all records) differ from the oracle" % which
+    del text
+    aa = aa_off = None
+    if which == "cds":
+        aa, aa_off, want_aa_len = coracle.splice_translate(nuc, off)
+        prot, _, _ = _emit(g, tbl, protein=True)
+        assert np.array_equal(aa_len, want_aa_len)
+        assert prot.size == aa.size and np.array_equal(prot, aa), "protein text (all records) differs from the oracle"
+        del prot
+    # the same with FASTA framing: '>' + name + newline + payload + newline per record, compared record by record
+    tblf = ann.table(which, framing=True)
+    for protein in ((False, True) if which == "cds" else (False,)):
+        textf, _, _ = _emit(g, tblf, protein=protein)
+        pay, poff = (aa, aa_off) if protein else (nuc, off)
+        mv, pv = memoryview(textf), memoryview(pay)
+        q = 0
+        for r, name in enumerate(ann.names):
+            head = b">" + name.encode() + b"\n"
+            n = int(poff[r + 1] - poff[r])
+            assert mv[q:q + len(head)] == head, ("header", r)
+            q += len(head)
+            assert mv[q:q + n] == pv[int(poff[r]):int(poff[r]) + n], ("payload", r, protein)
+            q += n
+            assert textf[q] == 10, ("newline", r)
+            q += 1
+        assert q == textf.size
+        del textf
+
+
+def test_config3_whole_text_against_oracle(insect):
+    _check_whole_text(insect, "cds")
+    _check_whole_text(insect, "exon")
+
+
+@pytest.mark.parametrize("which", ["cds", "exon"])
+def test_config4_whole_text_against_oracle(big, which):
+    _check_whole_text(big, which)
+
+
+def test_config5_orf_list_against_oracle(big):
+    """The complete ORF list (order, frame, strand, start, length, residues) of every scaffold and of the smallest chromosome
+    of the 3.1 Gbp genome, min 100 aa, against the C oracle's Sequence.get_orfs restatement on the host copy of the text."""
+    from magot_b200 import orfs
+    g, layout, _ = big
+    host = _HOST[id(g)]
+    lens = [l for _, l in layout]
+    chrom = int(np.argmin(lens[:24]))
+    ids = [chrom] + list(range(24, len(layout)))
+    recs, aa = orfs.sixframe_list(g, ids, 100)
+    want_aa, want = [], []
+    o = 0
+    for c in ids:
+        a, rr = coracle.sixframe(host[c], 100)
+        for row in rr:
+            want.append((c, int(row[0]), int(row[1]), int(row[2]), int(row[3]), o))
+            o += int(row[3])
+        want_aa.append(a)
+    got = list(zip(recs["contig"].tolist(), recs["frame"].tolist(), recs["minus"].tolist(), recs["start"].tolist(),
+                   recs["len"].tolist(), recs["aa_off"].tolist()))
+    assert len(got) == len(want) and len(want) > 20_000
+    assert got == want
+    assert aa == b"".join(want_aa)
 
 
 def test_config3_full_size_properties(insect):
