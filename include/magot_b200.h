@@ -187,6 +187,29 @@ int mg_sixframe_count_list(mg_genome *g, int64_t n_list, const int64_t *contig_i
 int mg_sixframe_emit(mg_genome *g, uint8_t *aa_out_host, mg_orf *recs_host, void *stream);
 int mg_sixframe_emit_device(mg_genome *g, uint8_t *aa_out_dev, mg_orf *recs_dev, void *stream);
 
+/* ---- host side: native GFF3 / GTF reader + flattener (no GPU work; csrc/mg_gff.cu) ------------------------------------------
+ * mg_gff_parse replaces read_gff (genome.py:242-415: line filter, version detection, attribute parsing, ID naming, de-dup,
+ * implicit parents, child lists) on interned integer ids; `opts` is the option blob magot_b200/gffnative.py packs (format
+ * version, features_to_ignore, base_features, parents_hierarchy, features_to_replace, IDfield, parent_field, and the tables /
+ * objects an existing AnnotationSet already holds).  `text` must stay alive while the handle lives.  mg_gff_info: [0] status
+ * (0 ok; else the line the reference stops at: 1 GFF2 attribute without value, 2 parent without a line, 3 GFF3 attribute
+ * without '=', 4 bad coordinate, ...), [3] rows, [4] strings, ...  mg_gff_column / mg_gff_strings / mg_gff_find expose the SoA
+ * columns (ids, coords, strand, phase, attributes, child lists, tables in dict insertion order) and the string table.
+ * mg_gff_flatten replaces AnnotationSet.get_fasta / ParentAnnotation.get_fasta's choice of children, order and header
+ * (genome.py:578-582, :683-719) for the rows `tops` of one feature table: it emits the arrays mg_plan_create takes.           */
+typedef struct mg_gff mg_gff;
+typedef struct mg_gff_flat mg_gff_flat;
+int mg_gff_parse(const uint8_t *text, int64_t n, const uint8_t *opts, int64_t n_opts, mg_gff **out);
+int mg_gff_destroy(mg_gff *m);
+int mg_gff_info(mg_gff *m, int64_t *info16);
+int mg_gff_column(mg_gff *m, const char *name, const void **ptr, int64_t *n, int32_t *elem_size);
+int mg_gff_strings(mg_gff *m, const int32_t *ids, int64_t n, uint8_t *pool, int64_t cap, int64_t *off);
+int64_t mg_gff_find(mg_gff *m, const uint8_t *s, int64_t n);
+int mg_gff_flatten(mg_gff *m, const int64_t *tops, int64_t n_top, const int32_t *contig_of, int64_t n_contig_of, int framing,
+                   mg_gff_flat **out);
+int mg_gff_flat_destroy(mg_gff_flat *f);
+int mg_gff_flat_column(mg_gff_flat *f, const char *name, const void **ptr, int64_t *n, int32_t *elem_size);
+
 /* ---- timing / sync helpers ----------------------------------------------------------------- */
 int mg_stream_sync(int device, void *stream);
 /* Stream-ordered copy of n bytes from a device buffer (e.g. the output of an mg_emit_*_device call) to host memory (pinned

@@ -74,6 +74,15 @@ SIGNATURES = {
     "mg_stream_sync": (_i32, [_i32, _vp]),
     "mg_copy_d2h_async": (_i32, [_i32, _vp, _vp, _i64, _vp]),
     "mg_tune": (_i32, [ctypes.c_char_p, _i32]),
+    "mg_gff_parse": (_i32, [ctypes.c_char_p, _i64, ctypes.c_char_p, _i64, _pp]),
+    "mg_gff_destroy": (_i32, [_vp]),
+    "mg_gff_info": (_i32, [_vp, _vp]),
+    "mg_gff_column": (_i32, [_vp, ctypes.c_char_p, _pp, _pi64, ctypes.POINTER(ctypes.c_int32)]),
+    "mg_gff_strings": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp]),
+    "mg_gff_find": (_i64, [_vp, ctypes.c_char_p, _i64]),
+    "mg_gff_flatten": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _pp]),
+    "mg_gff_flat_destroy": (_i32, [_vp]),
+    "mg_gff_flat_column": (_i32, [_vp, ctypes.c_char_p, _pp, _pi64, ctypes.POINTER(ctypes.c_int32)]),
     "mg_graph_begin": (_i32, [_i32, _vp]),
     "mg_graph_end": (_i32, [_i32, _vp, _pp]),
     "mg_graph_launch": (_i32, [_i32, _vp, _vp]),

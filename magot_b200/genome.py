@@ -596,6 +596,13 @@ class AnnotationSet(object):
         self.UTR = {}
         self.genome = genome
 
+    def __getattribute__(self, name):
+        # A set that read_gff has just made holds the native model only (_PENDING); the tables and objects of the reference's
+        # model are built the first time an instance attribute other than `genome` (a table, __dict__) is looked up.
+        if _PENDING and (name == "__dict__" or (name not in _ASET_CLASS_NAMES and name != "genome")) and self in _PENDING:
+            _materialise(self)
+        return object.__getattribute__(self, name)
+
     def _dict_names(self):
         return sorted(k for k, v in self.__dict__.items() if type(v) == dict)
 
@@ -661,7 +668,13 @@ class AnnotationSet(object):
 
     def get_fasta(self, feature, seq_type="nucleotide", longest=False, genomic=False):
         """genome.py:578-582: '\\n'.join of every <feature> annotation's fasta, in dict order
-        (empty results stay in the list -> blank lines).  All records go through ONE device plan."""
+        (empty results stay in the list -> blank lines).  All records go through ONE device plan.  A set that still holds
+        the native model of its read_gff call is flattened there (no Python object per feature)."""
+        model = _PENDING.get(self) if _PENDING else None
+        if model is not None:
+            text = _native_get_fasta(self, model, feature, seq_type, longest, genomic)
+            if text is not None:
+                return text
         table = getattr(self, feature)
         from .flatten import Flattener
         fl = Flattener(self)
@@ -671,6 +684,61 @@ class AnnotationSet(object):
                 raise AttributeError("%s instance has no attribute 'get_fasta'" % obj.__class__.__name__)
             fl.add_top(obj, seq_type=seq_type, longest=longest, genomic=genomic, name_from='ID')
         return fl.run(seq_type)
+
+
+_ASET_CLASS_NAMES = frozenset(dir(AnnotationSet))
+
+
+def _materialise(annotation_set):
+    """Native model -> the reference's tables and objects (once; the set stops being 'pending')."""
+    model = _PENDING.pop(annotation_set, None)
+    if model is None:
+        return
+    import gc
+    was_enabled = gc.isenabled()
+    gc.disable()                                         # millions of long-lived objects: generation-2 passes walk them for nothing
+    try:
+        _apply_model(annotation_set, object.__getattribute__(annotation_set, "__dict__"), model, [], deepcopy_order=True)
+    finally:
+        if was_enabled:
+            gc.enable()
+    model.close()
+
+
+def _native_get_fasta(annotation_set, model, feature, seq_type, longest, genomic):
+    """AnnotationSet.get_fasta on the native model: tops in the set's (Python-2.7 dict, after deepcopy) order, children chosen
+    and ordered by mg_gff_flatten, one device plan.  Returns None when the call needs the object model (genomic spans,
+    longest=, an unknown table, a model the flattener refuses: the object path then prints / raises like the reference)."""
+    if genomic is True or longest is True or seq_type not in ("nucleotide", "protein") or not isinstance(feature, str):
+        return None
+    genome = object.__getattribute__(annotation_set, "__dict__").get("genome")
+    gs = getattr(genome, "genome_sequence", None) if genome is not None else None
+    if gs is None:
+        return None
+    rows = model.table_rows(feature)
+    if rows is None or rows.size == 0:
+        return None
+    ids = model.column("id")[rows]
+    keys = model.strings(ids)
+    if len(set(keys)) != len(keys):
+        return None
+    row_of = dict(zip(keys, rows.tolist()))
+    tops = np.fromiter((row_of[k] for k in _order(keys, deepcopy=True)), dtype=np.int64, count=len(keys))
+    seq_ids = np.unique(model.column("seqid"))
+    seq_ids = seq_ids[seq_ids >= 0]
+    contig_of = np.full(model.n_strings, -1, dtype=np.int32)
+    for sid, name in zip(seq_ids.tolist(), model.strings(seq_ids)):
+        if dict.__contains__(gs, name):
+            contig_of[sid] = gs.contig_index(name)
+    tbl, top_rec_off, rec_name = model.flatten(tops, contig_of, framing=True)
+    if tbl is None:
+        return None
+    protein = seq_type == "protein"
+    text, lens = gs._engine().run_table(tbl, protein=protein, want_lengths=protein)
+    if protein and lens is not None and ((lens[1] < 0) & (rec_name >= 0)).any():
+        # Sequence.translate returned None (spliced length <= 2): '>' + name + '\n' + None (genome.py:710)
+        raise TypeError("cannot concatenate 'str' and 'NoneType' objects")
+    return text[:-1].decode("latin-1")
 
 
 def write_gff(annotation_set, gff_format="simple gff3"):
@@ -694,25 +762,15 @@ _AUGUSTUS_IGNORE = ['gene', 'transcript', 'stop_codon', 'terminal', 'internal', 
 def read_gff(gff, annotation_set_to_modify=None, base_features=['CDS', 'match_part', 'similarity', 'region'],
              features_to_ignore=['exon'], gff_version="auto", parents_hierarchy=[], features_to_replace=[],
              IDfield="ID", parent_field="Parent", presets=None):
-    """genome.py:242-415, see _read_gff.  The cyclic garbage collector is paused while the object model is built: millions
-    of long-lived objects are created and every generation-2 pass walks all of them for nothing (20-25 % of the time)."""
-    import gc
-    was_enabled = gc.isenabled()
-    gc.disable()
-    try:
-        return _read_gff(gff, annotation_set_to_modify, base_features, features_to_ignore, gff_version, parents_hierarchy,
-                         features_to_replace, IDfield, parent_field, presets)
-    finally:
-        if was_enabled:
-            gc.enable()
+    """genome.py:242-415 -- GFF3 / GTF reader with the reference's ID, de-dup and implicit-parent semantics.
 
-
-def _read_gff(gff, annotation_set_to_modify=None, base_features=['CDS', 'match_part', 'similarity', 'region'],
-              features_to_ignore=['exon'], gff_version="auto", parents_hierarchy=[], features_to_replace=[],
-              IDfield="ID", parent_field="Parent", presets=None):
-    """genome.py:242-415 -- GFF3 / GTF reader with the reference's ID, de-dup and implicit-parent
-    semantics.  Returns a new AnnotationSet (dicts in the order the reference's deepcopy leaves
-    them) unless annotation_set_to_modify is given."""
+    The text is tokenised and interpreted by the native reader (csrc/mg_gff.cu through magot_b200.gffnative): lines become
+    rows of interned integer ids, IDs are named / de-duplicated and parents created on those ids.  Without
+    annotation_set_to_modify a new AnnotationSet is returned that HOLDS that model: `get_fasta(feature)` flattens it straight
+    into interval tables for the device, and the reference's Python objects (dicts in the order the reference's deepcopy
+    leaves them, genome.py:415) are built only when a table, an object or the set's __dict__ is touched.  With
+    annotation_set_to_modify the rows are added to that set's objects right away."""
+    from . import gffnative
     # presets (genome.py:261-268): the reference exec()s these assignments, which rebinds the locals under Python 2;
     # a name that is not a preset (e.g. convert_gff's input_format 'gtf') changes nothing.
     if presets == "augustus":
@@ -726,169 +784,123 @@ def _read_gff(gff, annotation_set_to_modify=None, base_features=['CDS', 'match_p
     elif presets == "CEGMA":
         # the preset text indexes a list literal with a tuple ([['First','CDS']['Internal','CDS']...]): the exec raises
         raise TypeError("list indices must be integers, not tuple")
-    parents_hierarchy = list(parents_hierarchy)
-    version = gff_version
-    gff_file = ensure_file(gff)
-    replace = [("\n", ""), ("\r", "")]
-    for feature in features_to_replace:
-        replace.append(("\t" + feature[0] + "\t", "\t" + feature[1] + "\t"))
-    extra_replace = replace[2:]
-    if annotation_set_to_modify is None:
+    text = _read_all_bytes(gff)                        # ensure_file semantics (path, file object or literal text), as bytes
+    version = 0 if gff_version == "auto" else (gff_version if gff_version in (2, 3) and not isinstance(gff_version, bool) else -1)
+    fresh = annotation_set_to_modify is None
+    table_names, nondict, existing, ext_objects = [], [], [], []
+    if fresh:
         annotation_set = AnnotationSet()
+        adict = object.__getattribute__(annotation_set, "__dict__")
     else:
         annotation_set = annotation_set_to_modify
-    generate_new_ID_dict = {}
-    adict = annotation_set.__dict__
-    # __getitem__ precedence index kept incrementally: ID -> (dict name, object); a later dict name wins
-    owner = {}
-    for name in annotation_set._dict_names():
-        for k, v in adict[name].items():
-            owner[k] = (name, v)
-
-    def register(ftype, ID, obj):
-        cur = owner.get(ID)
-        if cur is None or ftype >= cur[0]:
-            owner[ID] = (ftype, obj)
-
-    phase_ok = ('0', '1', '2')
-    for original_line in gff_file:
-        if original_line[0] != "#" and original_line.count('\t') == 8:
-            if extra_replace or '\r' in original_line or original_line.find('\n') != len(original_line) - 1:
-                line = original_line.replace("\n", "").replace("\r", "")
-                for a, b in extra_replace:
-                    line = line.replace(a, b)
-                fields = line.split('\t')
-            else:                                       # the usual line: one '\n', at the end, nothing to replace
-                fields = original_line[:-1].split('\t')
-            f8 = fields[8]
-            if version == "auto":
-                if "=" in f8:
-                    version = 3
-                else:
-                    version = 2
-                    if IDfield is not None:
-                        if (" " + IDfield + " ") not in (" " + f8.replace(';', ' ')) and parents_hierarchy == []:
-                            IDfield = None
-                            parent_field = None
-                            if "gene_id" in f8 and "transcript_id" in f8:
-                                parents_hierarchy = ['transcript_id', 'gene_id']
-                            elif "gene_id" in f8:
-                                parents_hierarchy = ['gene_id']
-            ID = None
-            parent = None
-            other_attributes = {}
-            seqid = fields[0]
-            other_attributes['source'] = fields[1]
-            feature_type = fields[2]
-            if feature_type in features_to_ignore:
-                continue
-            c0, c1 = int(fields[3]), int(fields[4])
-            coords = (c0, c1) if c0 <= c1 else (c1, c0)
-            if fields[5] != '.':                        # '.' is float()'s ValueError of the reference, without raising it
-                try:
-                    other_attributes['score'] = float(fields[5])
-                except ValueError:
-                    pass
-            strand = fields[6]
-            if fields[7] in phase_ok:
-                other_attributes['phase'] = int(fields[7])
-            defline_dict = {}
-            for defline_field in f8.split(';'):
-                if defline_field != "":
-                    if parent_field == "":
-                        defline_dict[""] = defline_field
-                    elif version == 2:
-                        if '"' in defline_field:
-                            defline_dict[defline_field.split()[0]] = defline_field.split('"')[1]
-                        else:
-                            try:
-                                sp = defline_field.split()
-                                defline_dict[sp[0]] = sp[1]
-                            except Exception:
-                                print(defline_field)
-                                return None
-                    elif version == 3:
-                        sp = defline_field.split('=')
-                        defline_dict[sp[0]] = sp[1]
-            if parent_field is not None:
-                if parent_field in defline_dict:
-                    parent = defline_dict[parent_field]
-            elif parents_hierarchy != []:
-                for parent_type in parents_hierarchy:
-                    if parent_type in defline_dict:
-                        parent = defline_dict[parent_type]
-                        break
-            if IDfield is not None:
-                if IDfield in defline_dict:
-                    ID = defline_dict[IDfield]
-                elif parent is not None:
-                    ID = parent + '-' + feature_type
-            elif parent is not None:
-                ID = parent + '-' + feature_type
-            else:
-                ID = seqid + '-' + feature_type + fields[3]
-            if ID in owner:                                     # annotation_set[ID] succeeded (genome.py:355-364)
-                if ID in generate_new_ID_dict:
-                    generate_new_ID_dict[ID] = generate_new_ID_dict[ID] + 1
-                    ID = ID + "-" + str(generate_new_ID_dict[ID])
-                else:
-                    generate_new_ID_dict[ID] = 2
-                    ID = ID + '2'
-            if parent is not None:
-                child_to_assign = ID
-                for parent_feature_index in range(len(parents_hierarchy)):
-                    parent_feature = parents_hierarchy[parent_feature_index]
-                    if parent_feature in defline_dict:
-                        parent_feature_ID = defline_dict[parent_feature]
-                        parent_feature_type = parent_feature.split('_')[0]
-                        parents_parent = None
-                        if parent_feature_index != len(parents_hierarchy) - 1:
-                            for parents_parent_feature in parents_hierarchy[parent_feature_index + 1:]:
-                                if parents_parent_feature in defline_dict:
-                                    parents_parent = defline_dict[parents_parent_feature]
-                        if parent_feature_type not in adict:
-                            adict[parent_feature_type] = {}
-                        tbl = adict[parent_feature_type]
-                        if parent_feature_ID in tbl:
-                            cl = tbl[parent_feature_ID].child_list
-                            if child_to_assign not in cl:
-                                cl.append(child_to_assign)
-                        else:
-                            pobj = ParentAnnotation(parent_feature_ID, seqid, parent_feature_type, child_list=[child_to_assign],
-                                                    parent=parents_parent, strand=strand, annotation_set=annotation_set)
-                            tbl[parent_feature_ID] = pobj
-                            register(parent_feature_type, parent_feature_ID, pobj)
-                        child_to_assign = parent_feature_ID
-                got = owner.get(parent)
-                if got is None:
-                    print("""It seems that this line has a parent attribute but that that parent doesn't have a line itself nor
+        adict = annotation_set.__dict__                 # (materialises a set that still holds a native model)
+    for name, v in adict.items():
+        if type(v) == dict:
+            table_names.append(name)
+        else:
+            nondict.append(name)
+    if not fresh:
+        for t, name in enumerate(table_names):
+            for ID, obj in adict[name].items():
+                if isinstance(ID, str):
+                    kids = getattr(obj, "child_list", None)
+                    existing.append((t, ID, isinstance(kids, list), [c for c in kids if isinstance(c, str)] if isinstance(kids, list) else []))
+                    ext_objects.append(obj)
+    # whole-line replacement of "\tX\t" by "\tY\t" (genome.py:271-272)
+    replace = [("\t" + f[0] + "\t", "\t" + f[1] + "\t") for f in features_to_replace]
+    opts = gffnative.pack_opts(version, features_to_ignore, base_features, list(parents_hierarchy), replace,
+                               IDfield, parent_field, table_names, nondict, existing)
+    model = gffnative.Model(text, opts)
+    st = model.status
+    if fresh and st == gffnative.STATUS_OK:
+        _PENDING[annotation_set] = model
+        return annotation_set
+    if not fresh or st not in (gffnative.GFF2_NO_VALUE, gffnative.MISSING_PARENT):
+        _apply_model(annotation_set, adict, model, ext_objects, deepcopy_order=False)
+    if st == gffnative.STATUS_OK:
+        return None
+    if st == gffnative.GFF2_NO_VALUE:
+        print(model.string(model.err_a))
+        return None
+    if st == gffnative.MISSING_PARENT:
+        print("""It seems that this line has a parent attribute but that that parent doesn't have a line itself nor
                     does this line have a defline attribute that specifies a parent type. I'm afraid this function can't currently
                     deal with that.""")
-                    print(ID)
-                    print(parent)
-                    return None
-                cl = got[1].child_list
-                if ID not in cl:
-                    cl.append(ID)
-            for defline_attribute in defline_dict:
-                if defline_attribute != IDfield and defline_attribute != parent_field:
-                    other_attributes[defline_attribute] = defline_dict[defline_attribute]
-            if feature_type not in adict:
-                adict[feature_type] = {}
-            if feature_type in base_features:
-                obj = BaseAnnotation(ID, seqid, coords, feature_type, parent, strand, other_attributes, annotation_set)
-            else:
-                obj = ParentAnnotation(ID, seqid, feature_type, [], parent, strand, annotation_set, other_attributes)
-            adict[feature_type][ID] = obj
-            register(feature_type, ID, obj)
-    if annotation_set_to_modify is None:
+        print(model.string(model.err_a))
+        print(model.string(model.err_b))
+        return None
+    if st == gffnative.BAD_INT:
+        raise ValueError("invalid literal for int() with base 10: %r" % model.string(model.err_a))
+    if st == gffnative.PARENT_IS_BASE:
+        raise AttributeError("'BaseAnnotation' object has no attribute 'child_list'")
+    if st == gffnative.ATTR_CLASH:
+        raise TypeError("'%s' object does not support item assignment" % type(adict.get(model.string(model.err_a))).__name__)
+    if st == gffnative.NONE_TWICE:
+        raise TypeError("unsupported operand type(s) for +: 'NoneType' and 'str'")
+    raise IndexError("list index out of range")
+
+
+# AnnotationSets that still hold the native model of the read_gff call that made them (no Python object built yet)
+_PENDING = weakref.WeakKeyDictionary()
+
+
+def _apply_model(annotation_set, adict, model, ext_objects, deepcopy_order):
+    """Build the reference's objects from a native model: one BaseAnnotation / ParentAnnotation per row through the same
+    constructors (so attribute precedence is the reference's), tables filled in dict insertion order; rows that stand
+    for objects the set already had only receive their new children."""
+    S = model.all_strings()
+    n = model.n_rows
+    col = model.column
+    ids, seqid, ftype, strand, source, parent = (col(k).tolist() for k in ("id", "seqid", "ftype", "strand", "source", "parent"))
+    start, end, score, has_score, phase = (col(k).tolist() for k in ("start", "end", "score", "has_score", "phase"))
+    is_base, implicit, ext, attr0, nattr = (col(k).tolist() for k in ("is_base", "implicit", "ext", "attr0", "nattr"))
+    child_off, child, ext0 = col("child_off").tolist(), col("child").tolist(), col("ext_children0").tolist()
+    akey, aval = col("attr_key").tolist(), col("attr_val").tolist()
+    objs = [None] * n
+    for r in range(n):
+        kids = [S[c] for c in child[child_off[r]:child_off[r + 1]]]
+        if ext[r] >= 0:
+            obj = ext_objects[ext[r]]
+            if isinstance(getattr(obj, "child_list", None), list):
+                obj.child_list.extend(kids[ext0[r]:])
+            objs[r] = obj
+            continue
+        par = S[parent[r]] if parent[r] >= 0 else None
+        if implicit[r]:
+            objs[r] = ParentAnnotation(S[ids[r]], S[seqid[r]], S[ftype[r]], child_list=kids, parent=par, strand=S[strand[r]],
+                                       annotation_set=annotation_set)
+            continue
+        other = {'source': S[source[r]]}
+        if has_score[r]:
+            other['score'] = score[r]
+        if phase[r] >= 0:
+            other['phase'] = phase[r]
+        a0 = attr0[r]
+        for k in range(a0, a0 + nattr[r]):
+            other[S[akey[k]]] = S[aval[k]]
+        if is_base[r]:
+            objs[r] = BaseAnnotation(S[ids[r]], S[seqid[r]], (start[r], end[r]), S[ftype[r]], par, S[strand[r]], other, annotation_set)
+        else:
+            obj = ParentAnnotation(S[ids[r]], S[seqid[r]], S[ftype[r]], [], par, S[strand[r]], annotation_set, other)
+            if 'child_list' not in other:
+                obj.child_list = kids
+            objs[r] = obj
+    tname, toff, trows = col("table_name").tolist(), col("table_off").tolist(), col("table_rows").tolist()
+    for t, name_id in enumerate(tname):
+        name = S[name_id]
+        if name not in adict:
+            adict[name] = {}
+        tbl = adict[name]
+        for r in trows[toff[t]:toff[t + 1]]:
+            if ext[r] < 0:
+                tbl[S[ids[r]]] = objs[r]
+    if deepcopy_order:
         # copy.deepcopy (genome.py:415) re-inserts every dict in Python-2.7 slot order
-        for name in annotation_set._dict_names():
+        for name in sorted(k for k, v in adict.items() if type(v) == dict):
             tbl = adict[name]
             if tbl:
                 adict[name] = {k: tbl[k] for k in _order(list(tbl), deepcopy=True)}
         _DEEPCOPIED_SETS.add(annotation_set)
-        return annotation_set
 
 
 def read_cegma_gff(cegma_gff, annotation_set_to_modify=None):

@@ -915,3 +915,44 @@ def test_kernel_variants_bit_identical(mg, tune, emit, k1):
     for seed in (0, 1, 2, 3):
         test_random_tables_differential(mg, seed)
     test_edge_records(mg)
+
+
+# ---- native reader + flattener (csrc/mg_gff.cu) against the object path ------------------------------------------------
+
+@pytest.mark.parametrize("gff,fasta,kw", [
+    ("O.biroi_NCBIrefseq_gff3Subset.gff", "O.biroi_refseqGenomeSubset.fasta", {}),
+    ("O.biroi_NCBIrefseq_gff3Subset.gff", "O.biroi_refseqGenomeSubset.fasta", {"base_features": ['exon', 'match_part', 'similarity', 'region'], "features_to_ignore": ['CDS']}),
+    ("StandardGTF.gtf", "C14.fasta", {}), ("transcriptlessGTF.gtf", "C14.fasta", {}), ("minimalGFF3.gff", "C14.fasta", {})])
+def test_native_flattener_equals_object_path(mg, ref_data, gff, fasta, kw):
+    """AnnotationSet.get_fasta straight from the native model (no Python object per feature) == the same call after the
+    reference's object model has been built (flatten.py walks the objects), nucleotide and protein, every table."""
+    g = mg.Genome(os.path.join(ref_data, fasta))
+    g.read_gff(os.path.join(ref_data, gff), **kw)
+    aset = g.annotations
+    assert aset in mg.genome._PENDING
+    native = {}
+    for feature in ("gene", "transcript", "mRNA"):
+        for seq_type in ("nucleotide", "protein"):
+            try:
+                native[(feature, seq_type)] = aset.get_fasta(feature, seq_type=seq_type)
+            except AttributeError:
+                native[(feature, seq_type)] = "AttributeError"
+                g.read_gff  # noqa: B018
+                if aset not in mg.genome._PENDING:      # an unknown table builds the objects: start again from the text
+                    g2 = mg.Genome(g.genome_sequence)
+                    g2.read_gff(os.path.join(ref_data, gff), **kw)
+                    g, aset = g2, g2.annotations
+    g3 = mg.Genome(g.genome_sequence)
+    g3.read_gff(os.path.join(ref_data, gff), **kw)
+    objs = g3.annotations
+    assert len(objs.gene) >= 0 and objs not in mg.genome._PENDING          # touching a table builds the objects
+    n_checked = 0
+    for (feature, seq_type), text in native.items():
+        try:
+            want = objs.get_fasta(feature, seq_type=seq_type)
+        except AttributeError:
+            want = "AttributeError"
+        assert text == want, (feature, seq_type)
+        n_checked += want not in ("", "AttributeError")
+    assert n_checked >= 2
+    g.genome_sequence.close()

@@ -402,3 +402,117 @@ def test_position_dic_fill_and_count_match_reference():
     with pytest.raises(IndexError):
         pd.fill_from_annotations(fake, "CDS")
     assert pd["c"].astype(int).tolist() == [1, 1, 1, 0, 0, 0, 0, 1, 1, 1]
+
+
+# ---- native GFF reader (csrc/mg_gff.cu) against the oracle's line-by-line restatement on adversarial text -----------------
+
+def _full_signature(tables):
+    sig = {}
+    for name, tbl in tables.items():
+        for k, o in tbl.items():
+            d = {a: v for a, v in o.__dict__.items() if a != "annotation_set"}
+            sig[(name, k)] = (type(o).__name__[:4], d)
+    return sig
+
+
+def _fuzz_gff(rng, flavour):
+    seqids = ["s1", "s2", "chr 3"]
+    parent_types = ["gene", "mRNA", "transcript", "match", "five_prime_UTR"]
+    base_types = ["exon", "CDS", "region", "match_part"]
+    ids = ["g%d" % i for i in range(6)] + ["t%d" % i for i in range(8)] + ["c%d" % i for i in range(5)]
+    lines = ["##gff-version 3", "# a comment\twith\ttabs\t1\t2\t3\t4\t5\t6"]
+    known = []                                           # IDs of features that can take children
+    n_lines = int(rng.integers(5, 160))
+    poison_at = int(rng.integers(0, n_lines)) if rng.random() < 0.3 else -1
+    for li in range(n_lines):
+        r = rng.random()
+        if r < 0.04:
+            lines.append(rng.choice(["", "#x", "a\tb\tc", "s1\tsrc\tgene\t1\t2\t.\t+\t.\tID=z\textra\tcol", "\r"]))
+            continue
+        is_parent = rng.random() < 0.45
+        ftype = str(rng.choice(parent_types if is_parent else base_types))
+        a, b = int(rng.integers(-3, 5000)), int(rng.integers(-3, 5000))
+        score = str(rng.choice([".", "1.5", "abc", "1e3", "7", " 2 ", "-0.0", "inf"]))
+        strand = str(rng.choice(["+", "-", ".", "?", "+-"]))
+        phase = str(rng.choice([".", "0", "1", "2", "3", "01"]))
+        attrs = []
+        poison = li == poison_at
+        if flavour == "gff3":
+            my_id = None
+            if rng.random() < 0.85:
+                my_id = str(rng.choice(ids))
+                attrs.append("ID=" + my_id)
+            if known and rng.random() < 0.6:
+                attrs.append("Parent=" + (str(rng.choice(known)) if not (poison and rng.random() < 0.5) else "nowhere"))
+            elif my_id is None:                              # (a line with neither ID nor Parent is filed under None, whose
+                my_id = str(rng.choice(ids))                 #  place in a Python-2 dict depends on an address: not generated)
+                attrs.append("ID=" + my_id)
+            for _k in range(int(rng.integers(0, 4))):
+                attrs.append(str(rng.choice(["Name=n1", "Name=n2", "product=a=b=c", "note=x y", "source=over", "strand=*", "Dbxref=", "k=v", ""])))
+            if poison and rng.random() < 0.5:
+                attrs.append("novalue")
+            if my_id is not None and is_parent and ftype != "five_prime_UTR":
+                known.append(my_id)
+        else:
+            t = str(rng.choice(ids[6:14]))
+            g = str(rng.choice(ids[:6]))
+            style = rng.random()
+            if style < 0.8:
+                attrs.append('transcript_id "%s"' % t)
+                attrs.append(' gene_id "%s"' % g)
+            elif style < 0.9:
+                attrs.append('gene_id "%s"' % g)
+            else:
+                attrs.append("gene_id %s" % g)
+            for _k in range(int(rng.integers(0, 3))):
+                attrs.append(str(rng.choice([' exon_number "2"', ' note "a;b"', ' gene_name "x" "y"', " tag v w", ""])))
+            if poison:
+                attrs.append(" flag")
+        if rng.random() < 0.5:
+            rng.shuffle(attrs)
+        line = "\t".join([str(rng.choice(seqids)), "src", ftype, str(a), str(b), score, strand, phase, ";".join(attrs)])
+        if rng.random() < 0.05:
+            line = line.replace("\t", "\r\t", 1) if rng.random() < 0.5 else line + "\r"
+        lines.append(line)
+    return "\n".join(lines) + ("\n" if rng.random() < 0.8 else "")
+
+
+@pytest.mark.parametrize("seed", list(range(40)))
+def test_native_reader_matches_oracle_on_adversarial_text(seed):
+    """Random GFF3 / GTF text with duplicate IDs, repeated and empty attributes, '=' and quotes inside values, CR at odd
+    places, comment / blank / short lines, reversed and negative coordinates, odd scores, phases and strands, missing parents:
+    the native reader's object model (every instance attribute, table contents and Python-2.7 order) == the oracle's, and
+    both stop (None) on the same inputs."""
+    import contextlib
+    import io
+    rng = np.random.default_rng(900 + seed)
+    flavour = "gff3" if seed % 2 == 0 else "gtf"
+    text = _fuzz_gff(rng, flavour)
+    kws = [{}, {"features_to_ignore": ["CDS"], "base_features": ["exon", "region"]},
+           {"features_to_ignore": "CDSexon", "features_to_replace": [("mRNA", "transcript"), ("five_prime_UTR", "UTR")]}]
+    if flavour == "gtf":
+        kws.append({"parents_hierarchy": ["gene_id"], "IDfield": None, "parent_field": None})
+    else:
+        kws.append({"IDfield": "Name", "parent_field": "Parent"})
+    for kw in kws:
+        out_a, out_b = io.StringIO(), io.StringIO()
+        with contextlib.redirect_stdout(out_a):
+            try:
+                a = genome.read_gff(text, **kw)
+                err_a = None
+            except Exception as e:       # noqa: BLE001
+                a, err_a = None, type(e).__name__
+        with contextlib.redirect_stdout(out_b):
+            try:
+                b = mo.read_gff(text, **kw)
+                err_b = None
+            except Exception as e:       # noqa: BLE001
+                b, err_b = None, type(e).__name__
+        assert err_a == err_b, (kw, err_a, err_b)
+        assert (a is None) == (b is None), kw
+        if a is None:
+            continue
+        ta = {name: a.__dict__[name] for name in a._dict_names()}
+        tb = {name: b.tables[name] for name in sorted(b.tables)}
+        assert {k: list(v) for k, v in ta.items()} == {k: list(v) for k, v in tb.items()}, kw
+        assert _full_signature(ta) == _full_signature(tb), kw
