@@ -296,6 +296,50 @@ def fasta_ingest_rates(device):
     return out
 
 
+def api_e2e(device):
+    """Wall time of the PUBLIC API on config 3 at full size, from text to text (rank 0, outside every timed region):
+    Genome(FASTA text) -> read_gff(GFF3 text) -> annotations.get_fasta('gene') for the CDS nucleotide product -- what
+    genome_tools.gff2fasta does before it prints (genome_tools.py:324-330).  Split: FASTA ingest (header scan on the host, K0f + K0
+    on the device), annotation parse (native reader), flatten (native, tops in Python-2.7 dict order), device + copy (K1-K2 and
+    the text into a bytes object), decode (bytes -> the str the API returns)."""
+    import numpy as np
+    import torch
+    from magot_b200 import engine, synth, genome as mg
+    dev = torch.device("cuda", device)
+    layout = synth.contig_layout("insect", 500_000_000, 3)
+    parts = []
+    for ci, (name, L) in enumerate(layout):              # the genome as 60-column FASTA text, produced on the device
+        a = synth.synth_contig_device(L, 3 * 1000003 + ci * 64, dev).cpu().numpy()
+        full = L // 60
+        rows = np.empty((full, 61), dtype=np.uint8)
+        rows[:, :60] = a[:full * 60].reshape(full, 60)
+        rows[:, 60] = 10
+        parts.append(b">" + name.encode() + b"\n" + rows.tobytes() + a[full * 60:].tobytes() + b"\n")
+    fasta = b"".join(parts)
+    del parts
+    ann = synth.synth_annotation(layout, 60_000, 3)
+    gff = ann.to_gff3([n for n, _ in layout])
+    out = {"workload": "config 3 at full size through the public API: %.0f MB of FASTA text (500 Mbp, 2 000 scaffolds), %d lines of GFF3 text (30k genes / 60k mRNAs)" % (len(fasta) / 1e6, gff.count("\n"))}
+    mg.TIMINGS = {}
+    t0 = time.perf_counter()
+    G = mg.Genome(fasta)
+    t1 = time.perf_counter()
+    G.read_gff(gff)
+    t2 = time.perf_counter()
+    text = G.annotations.get_fasta('gene')
+    t3 = time.perf_counter()
+    out.update({"fasta_ingest_s": round(t1 - t0, 3), "read_gff_s": round(t2 - t1, 3), "get_fasta_s": round(t3 - t2, 3),
+                "total_s": round(t3 - t0, 3), "gff_lines_per_s": round(gff.count("\n") / (t2 - t1)),
+                "fasta_GBps": round(len(fasta) / (t1 - t0) / 1e9, 2)})
+    out.update({k: (round(v, 4) if isinstance(v, float) else v) for k, v in mg.TIMINGS.items()})
+    out["spliced_Gbp_per_s_text_to_text"] = round(ann.spliced_bp("cds") / (t3 - t0) / 1e9, 4)
+    out["spliced_Gbp_per_s_get_fasta_only"] = round(ann.spliced_bp("cds") / (t3 - t2) / 1e9, 4)
+    assert text.count(">") == 60_000
+    mg.TIMINGS = None
+    G.genome_sequence.close()
+    return out
+
+
 def cpu_port_rate():
     """Single-threaded C restatement (oracle/oracle.c) on a larger sample: tight-loop CPU figure."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -862,6 +906,10 @@ def gpu_arm(args):
                     cpu["host_annotation_parse"] = host_phases()
                 except Exception as e:
                     cpu["host_annotation_parse"] = {"error": str(e)[:200]}
+                try:
+                    cpu["api_e2e"] = api_e2e(local)
+                except Exception as e:
+                    cpu["api_e2e"] = {"error": str(e)[:300]}
                 try:
                     cpu["fasta_ingest"] = fasta_ingest_rates(local)
                 except Exception as e:

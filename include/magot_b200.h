@@ -60,6 +60,10 @@ int mg_genome_pack_device(mg_genome *g, int64_t contig, int64_t offset, const ui
  * never touches the sequence bytes.  The number of kept bytes must equal the contig length given to
  * mg_genome_create (count the line ends on the host), else MG_EINVAL.                          */
 int mg_genome_pack_fasta(mg_genome *g, int64_t contig, const uint8_t *raw, int64_t n_raw, void *stream);
+/* Host helper of the FASTA header scan: out[r] = number of CR / LF bytes in data[lo[r], hi[r]) for every record body, so that
+ * the contig lengths (body bytes minus line ends, genome.py:875) are known before mg_genome_create without a Python pass over
+ * the sequence bytes.  Threaded; no GPU work.                                                                             */
+int mg_count_line_ends(const uint8_t *data, int64_t n, int64_t n_ranges, const int64_t *lo, const int64_t *hi, int64_t *out);
 /* Sort the exception list and make the genome usable by every call below.                   */
 int mg_genome_finalize(mg_genome *g, int64_t *n_exceptions_out);
 int mg_genome_destroy(mg_genome *g);

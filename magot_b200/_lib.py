@@ -47,6 +47,7 @@ SIGNATURES = {
     "mg_genome_pack": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp]),
     "mg_genome_pack_device": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp]),
     "mg_genome_pack_fasta": (_i32, [_vp, _i64, _vp, _i64, _vp]),
+    "mg_count_line_ends": (_i32, [ctypes.c_char_p, _i64, _i64, _vp, _vp, _vp]),
     "mg_genome_finalize": (_i32, [_vp, _pi64]),
     "mg_genome_destroy": (_i32, [_vp]),
     "mg_genome_bytes": (_i64, [_vp]),

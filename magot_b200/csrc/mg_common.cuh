@@ -153,6 +153,7 @@ int mg_scan_i32(const int32_t *d_in, int64_t *d_out, int64_t n, int64_t *d_tmp, 
 int64_t mg_scan_tmp_elems(int64_t n);
 int mg_ensure_stage(mg_genome *g, int64_t bytes);
 int mg_ensure_pin(mg_genome *g, int64_t bytes);
+void mg_parallel_copy(const uint8_t *src, uint8_t *dst, int64_t n);   // memcpy on up to 8 host threads (pageable <-> page-locked staging)
 int mg_emit_mode();                                   // K2 variant, env MAGOT_EMIT: 0 = ldg (mg_emit.cu, default: the fastest), 1 = tma (mg_emit_tma.cu), 2 = stream (mg_emit_stream.cu)
 int mg_launch_nuc_tma(mg_plan *p, uint8_t *out_dev, cudaStream_t st);
 int mg_launch_nuc_stream(mg_plan *p, uint8_t *out_dev, cudaStream_t st);

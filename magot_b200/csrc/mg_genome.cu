@@ -5,6 +5,7 @@
 #include <numeric>
 #include <stdarg.h>
 #include <string.h>
+#include <thread>
 #include "mg_common.cuh"
 #include "mg_lookback.cuh"
 
@@ -374,6 +375,58 @@ __global__ void __launch_bounds__(STRIP_THREADS) k_fasta_strip(const uint8_t *__
     if (tile == gridDim.x - 1 && threadIdx.x == 0) *kept_total = prefix + total;
 }
 
+// Host side of K0f: the caller's FASTA bytes are pageable; a pageable cudaMemcpy runs at ~10 GB/s (the round-1 ingest rate).
+// Worker threads copy the NEXT trip into one of two page-locked buffers while the device takes the previous trip from the
+// other buffer at the PCIe rate and strips it; the number of bases the strip kept comes back in a page-locked word that the
+// host reads after its own copy, i.e. without ever waiting for it.
+void mg_parallel_copy(const uint8_t *src, uint8_t *dst, int64_t n) {
+    int T = (int)std::thread::hardware_concurrency();
+    T = std::max(1, std::min(T, 8));
+    if (n < (4 << 20)) T = 1;
+    std::vector<std::thread> th;
+    const int64_t per = ((n + T - 1) / T + 4095) / 4096 * 4096;
+    for (int t = 1; t < T; t++) {
+        const int64_t a = std::min(n, t * per), b = std::min(n, a + per);
+        if (b > a) th.emplace_back([=]() { memcpy(dst + a, src + a, (size_t)(b - a)); });
+    }
+    memcpy(dst, src, (size_t)std::min(n, per));
+    for (auto &x : th) x.join();
+}
+
+// Line-end bytes (CR, LF) inside each of n_ranges byte ranges [lo, hi) of a FASTA text: body length of a record = its bytes
+// minus these (genome.py:875 drops exactly '\n' and '\r').  Host only; the ranges are shared out over up to 8 threads by bytes.
+extern "C" int mg_count_line_ends(const uint8_t *data, int64_t n, int64_t n_ranges, const int64_t *lo, const int64_t *hi, int64_t *out) {
+    MG_REQUIRE((data || n == 0) && n_ranges >= 0 && (n_ranges == 0 || (lo && hi && out)), "bad arguments");
+    for (int64_t r = 0; r < n_ranges; r++) MG_REQUIRE(lo[r] >= 0 && hi[r] >= lo[r] && hi[r] <= n, "range outside the text");
+    int T = (int)std::thread::hardware_concurrency();
+    T = std::max(1, std::min(T, 8));
+    if (n < (8 << 20)) T = 1;
+    auto work = [&](int64_t r0, int64_t r1) {
+        for (int64_t r = r0; r < r1; r++) {
+            const uint8_t *p = data + lo[r];
+            const int64_t m = hi[r] - lo[r];
+            int64_t c = 0;
+            for (int64_t i = 0; i < m; i += 1 << 16) {    // blocks small enough for a byte-wide vectorised count
+                const int64_t e = std::min<int64_t>(m, i + (1 << 16));
+                uint32_t cc = 0;
+                for (int64_t j = i; j < e; j++) cc += (uint32_t)((p[j] == '\n') | (p[j] == '\r'));
+                c += cc;
+            }
+            out[r] = c;
+        }
+    };
+    std::vector<std::thread> th;
+    int64_t r0 = 0, acc = 0;
+    const int64_t per = n / T + 1;
+    for (int64_t r = 0; r < n_ranges; r++) {
+        acc += hi[r] - lo[r];
+        if (acc >= per && (int)th.size() < T - 1) { th.emplace_back(work, r0, r + 1); r0 = r + 1; acc = 0; }
+    }
+    work(r0, n_ranges);
+    for (auto &x : th) x.join();
+    return MG_OK;
+}
+
 extern "C" int mg_genome_pack_fasta(mg_genome *g, int64_t contig, const uint8_t *raw, int64_t n_raw, void *stream) {
     MG_REQUIRE(g != nullptr, "genome handle is NULL");
     MG_REQUIRE(contig >= 0 && contig < g->n_contigs, "contig index out of range");
@@ -383,7 +436,12 @@ extern "C" int mg_genome_pack_fasta(mg_genome *g, int64_t contig, const uint8_t 
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t RAW = 64ll << 20;                   // raw bytes per trip (multiple of the tile)
     const int64_t clen = g->h_contig_len[contig];
-    const int64_t chunk_cap = std::min<int64_t>(RAW, (n_raw + STRIP_TILE - 1) / STRIP_TILE * STRIP_TILE);
+    // one size for the life of the handle (a FASTA with thousands of scaffolds must not re-allocate page-locked memory per
+    // scaffold): what the longest contig needs with 60-column lines, at most one trip
+    int64_t longest = 0;
+    for (int64_t L : g->h_contig_len) longest = std::max(longest, L);
+    const int64_t want_cap = std::min<int64_t>(RAW, ((longest + longest / 16 + 4096) + STRIP_TILE - 1) / STRIP_TILE * STRIP_TILE);
+    const int64_t chunk_cap = std::max(want_cap, std::min<int64_t>(RAW, (n_raw + STRIP_TILE - 1) / STRIP_TILE * STRIP_TILE));
     if (g->raw_cap < chunk_cap) {
         if (g->d_raw) MG_CUDA(cudaFree(g->d_raw));
         if (g->d_strip_tmp) MG_CUDA(cudaFree(g->d_strip_tmp));
@@ -394,25 +452,37 @@ extern "C" int mg_genome_pack_fasta(mg_genome *g, int64_t contig, const uint8_t 
     }
     int rc = mg_ensure_stage(g, chunk_cap + 256);     // ASCII staging: up to 31 carried bytes + one stripped chunk
     if (rc) return rc;
+    rc = mg_ensure_pin(g, 2 * g->raw_cap + 64);       // two page-locked trip buffers + the kept-bytes word
+    if (rc) return rc;
+    uint8_t *pin[2] = {g->h_pin, g->h_pin + g->raw_cap};
+    volatile int64_t *h_kept = reinterpret_cast<volatile int64_t *>(g->h_pin + 2 * g->raw_cap);
     int64_t *d_kept = reinterpret_cast<int64_t *>(g->d_strip_tmp + (g->raw_cap / STRIP_TILE + 2));
     int64_t carry = 0, done_bases = 0;
-    for (int64_t done = 0; done < n_raw || (n_raw == 0 && done == 0);) {
-        const int64_t m = std::min<int64_t>(g->raw_cap, n_raw - done);
-        int64_t kept = 0;
+    int64_t m_next = std::min<int64_t>(g->raw_cap, n_raw);
+    if (m_next > 0) mg_parallel_copy(raw, pin[0], m_next);
+    int k = 0;
+    for (int64_t done = 0; done < n_raw || (n_raw == 0 && done == 0); k++) {
+        const int64_t m = m_next;
         if (m > 0) {
             const int64_t nt = (m + STRIP_TILE - 1) / STRIP_TILE;
-            MG_CUDA(cudaMemcpyAsync(g->d_raw, raw + done, m, cudaMemcpyHostToDevice, st));
+            MG_CUDA(cudaMemcpyAsync(g->d_raw, pin[k & 1], m, cudaMemcpyHostToDevice, st));
             MG_CUDA(cudaMemsetAsync(g->d_strip_tmp, 0, (nt + 1) * sizeof(unsigned long long), st));
             k_fasta_strip<<<(unsigned)nt, STRIP_THREADS, 0, st>>>(g->d_raw, m, g->d_strip_tmp, g->d_stage + carry, d_kept);
             MG_LAUNCH_CHECK();
-            MG_CUDA(cudaMemcpyAsync(&kept, d_kept, sizeof(kept), cudaMemcpyDeviceToHost, st));
-            MG_CUDA(cudaStreamSynchronize(st));
+            MG_CUDA(cudaMemcpyAsync((void *)h_kept, d_kept, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         }
         done += m;
         const bool last = done >= n_raw;
+        // the next trip is copied by the host while the device copies / strips this one; its buffer was last read by the trip
+        // before this one, whose pack has been waited for
+        m_next = last ? 0 : std::min<int64_t>(g->raw_cap, n_raw - done);
+        if (m_next > 0) mg_parallel_copy(raw + done, pin[(k + 1) & 1], m_next);
+        int64_t kept = 0;
+        if (m > 0) { MG_CUDA(cudaStreamSynchronize(st)); kept = *h_kept; }
         const int64_t avail = carry + kept;
         const int64_t npack = last ? avail : avail / 32 * 32;
         if (done_bases + npack > clen || (last && done_bases + npack != clen)) {
+            cudaStreamSynchronize(st);
             mg_set_error("FASTA body of contig %lld holds %s%lld bases, the genome was created with %lld", (long long)contig,
                          last ? "" : "more than ", (long long)(done_bases + npack), (long long)clen);
             return MG_EINVAL;

@@ -39,6 +39,28 @@ def pinned_empty(nbytes):
     return np.empty(nbytes, dtype=np.uint8)
 
 
+_PyBytes_New = ctypes.pythonapi.PyBytes_FromStringAndSize
+_PyBytes_New.restype = ctypes.py_object
+_PyBytes_New.argtypes = [ctypes.c_char_p, ctypes.c_ssize_t]
+_PyBytes_Buf = ctypes.pythonapi.PyBytes_AsString
+_PyBytes_Buf.restype = ctypes.c_void_p
+_PyBytes_Buf.argtypes = [ctypes.py_object]
+
+
+def new_bytes(n):
+    """(bytes object of n uninitialised bytes, address of its buffer): the library writes the text straight into the object
+    the API returns (CPython's own way of building a bytes result), no bytearray / numpy detour."""
+    obj = _PyBytes_New(None, int(n))
+    return obj, _PyBytes_Buf(obj)
+
+
+def decode_text(text, strip_last=0):
+    """latin-1 str of a bytes text without its last `strip_last` bytes (no intermediate bytes copy)."""
+    if strip_last:
+        return str(memoryview(text)[:len(text) - strip_last], "latin-1")
+    return text.decode("latin-1")
+
+
 class DeviceGenome(object):
     """A genome replica on one CUDA device: nibble-packed contigs + exception side list."""
 
@@ -174,6 +196,18 @@ class Plan(object):
             check(lib.mg_stream_sync(self.genome.device, self.stream))
         return out[:total]
 
+    def emit_bytes(self, protein=False):
+        """The text as a bytes object, filled by the library (mg_emit_*_host: device text -> two page-locked staging buffers
+        -> this object, pipelined)."""
+        total = self.prot_total if protein else self.nuc_total
+        if not total:
+            return b""
+        obj, addr = new_bytes(total)
+        fn = lib.mg_emit_prot_host if protein else lib.mg_emit_nuc_host
+        check(fn(self.handle, ctypes.c_void_p(addr), self.stream))
+        check(lib.mg_stream_sync(self.genome.device, self.stream))
+        return obj
+
     def emit_device(self, dev_ptr, protein=False):
         fn = lib.mg_emit_prot_device if protein else lib.mg_emit_nuc_device
         check(fn(self.handle, ctypes.c_void_p(dev_ptr), self.stream))
@@ -196,7 +230,7 @@ def run_table(genome, table, protein=False, trimx=True, use_phase=False, want_le
     try:
         plan.prepare(trimx=trimx, use_phase=use_phase)
         lens = plan.lengths() if want_lengths else None
-        text = plan.emit_host(protein=protein).tobytes()
+        text = plan.emit_bytes(protein=protein)
     finally:
         plan.close()
     return text, lens

@@ -22,11 +22,16 @@ class _Top(object):
         self.genomic = genomic
 
 
+def _short_circuits(obj):
+    """ParentAnnotation.get_fasta returns "" before it looks at `longest` (genome.py:683, :730-731): no children, no set, no genome."""
+    return not (len(obj.child_list) > 0 and obj.annotation_set is not None) or obj.annotation_set.genome is None
+
+
 class Flattener(object):
     def __init__(self, annotation_set):
         self.aset = annotation_set
         self.gs = annotation_set.genome.genome_sequence
-        self.index = annotation_set.build_index()
+        self.index = annotation_set.build_index()       # cached on the set between calls (see AnnotationSet.build_index)
         self.tops = []
         # leaf records
         self.names = []                 # header text without '>' (str)
@@ -123,7 +128,8 @@ class Flattener(object):
             rid = self._leaf(obj.ID, [(self._contig(obj.seqid), c[0], c[1], 0)])
             self.tops.append(_Top([[rid]], False, True))
             return
-        self.tops.append(_Top(self._collect(obj, name_from), longest is True, False))
+        # a top that short-circuits never reaches the `longest` selection (its max() over no sequences would raise ValueError)
+        self.tops.append(_Top(self._collect(obj, name_from), longest is True and not _short_circuits(obj), False))
 
     # -- execution -------------------------------------------------------------------------------
     def _table(self, rec_ids, pre, suf):
@@ -146,19 +152,14 @@ class Flattener(object):
         se = np.asarray(self.seg_end, dtype=np.int64)
         st = np.asarray(self.seg_strand, dtype=np.int8)
         ph = np.asarray(self.rec_phase, dtype=np.int8)
-        lit_parts = []
-        lit_off = np.zeros(ids.size, dtype=np.int64)
-        pre_len = np.zeros(ids.size, dtype=np.int32)
-        suf_len = np.zeros(ids.size, dtype=np.int32)
-        o = 0
-        for k in range(ids.size):
-            lit_off[k] = o
-            pre_len[k] = len(pre[k])
-            suf_len[k] = len(suf[k])
-            lit_parts.append(pre[k])
-            lit_parts.append(suf[k])
-            o += len(pre[k]) + len(suf[k])
-        lit = np.frombuffer(b"".join(lit_parts), dtype=np.uint8) if o else np.zeros(0, dtype=np.uint8)
+        # literals: prefix bytes immediately followed by suffix bytes, record after record (no Python statement per record)
+        n = ids.size
+        pre_len = np.fromiter(map(len, pre), dtype=np.int32, count=n)
+        suf_len = np.fromiter(map(len, suf), dtype=np.int32, count=n)
+        both = pre_len.astype(np.int64) + suf_len
+        lit_off = np.concatenate(([0], np.cumsum(both)[:-1])) if n else np.zeros(0, dtype=np.int64)
+        blob = b"".join(x for pair in zip(pre, suf) for x in pair)
+        lit = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(0, dtype=np.uint8)
         return engine.RecordTable(rec_seg_off, sc[src] if total else sc[:0], ss[src] if total else ss[:0],
                                   se[src] if total else se[:0], st[src] if total else st[:0], lit_off, pre_len,
                                   suf_len, lit, np.where(valid, ph[safe] if ph.size else 0, 0).astype(np.int8))
@@ -212,4 +213,4 @@ class Flattener(object):
         if protein and l2 is not None and (l2[1] < 0)[np.asarray(rec_ids) >= 0].any():
             # Sequence.translate returned None (spliced length <= 2): '>' + name + '\n' + None (genome.py:710)
             raise TypeError("cannot concatenate 'str' and 'NoneType' objects")
-        return text[:-1].decode("latin-1")
+        return engine.decode_text(text, strip_last=1)

@@ -31,6 +31,7 @@ import weakref
 verbose = True                      # genome.py:22
 RECORD_ORDER = "py2"                # "py2" (reference-identical) | "insertion"
 DEFAULT_DEVICES = None              # None -> [0]; or a list of CUDA device indices to shard over
+TIMINGS = None                      # a dict here receives the split of the last native get_fasta call (bench.py: api_e2e)
 
 
 def _order(keys, deepcopy=False):
@@ -412,30 +413,20 @@ class _RawBody(object):
 
 
 def _scan_fasta(data, truncate_names):
-    """genome.py:856-877 without touching the sequence bytes: header discovery (bytes.find) and, per record, the span
-    of its body and its length = body bytes minus CR/LF (bytes.count).  Empty
-    records are dropped, text before the first header belongs to seqid '', a repeated header replaces the earlier
-    record but keeps its place."""
+    """genome.py:856-877 without touching the sequence bytes in Python: header discovery (bytes.find) and, per record, the
+    span of its body and its length = body bytes minus CR/LF (counted for all records in one threaded native call,
+    mg_count_line_ends).  Empty records are dropped, text before the first header belongs to seqid '', a repeated header
+    replaces the earlier record but keeps its place."""
+    import ctypes
     n = len(data)
-    names = []
-    spans = {}
-
-    def put(name, lo, hi):
-        if hi <= lo:
-            return
-        size = (hi - lo) - data.count(b"\n", lo, hi) - data.count(b"\r", lo, hi)
-        if size <= 0:
-            return
-        if name not in spans:
-            names.append(name)
-        spans[name] = (lo, hi, size)
+    recs = []                                            # (seqid, body lo, body hi) in file order
 
     pos = 0 if data[:1] == b">" else data.find(b"\n>")
     if pos < 0:
-        put("", 0, n)
-        return names, spans
-    if pos > 0 or data[:1] != b">":
-        put("", 0, pos + 1)
+        recs.append(("", 0, n))
+        pos = n
+    elif pos > 0 or data[:1] != b">":
+        recs.append(("", 0, pos + 1))
         pos += 1
     while pos < n:
         eol = data.find(b"\n", pos)
@@ -445,8 +436,23 @@ def _scan_fasta(data, truncate_names):
         seqid = raw.split()[0] if truncate_names is True else raw
         nxt = data.find(b"\n>", eol)
         body_hi = n if nxt < 0 else nxt + 1
-        put(seqid, min(eol + 1, n), body_hi)
+        recs.append((seqid, min(eol + 1, n), body_hi))
         pos = n if nxt < 0 else nxt + 1
+    lo = np.array([r[1] for r in recs], dtype=np.int64)
+    hi = np.array([max(r[2], r[1]) for r in recs], dtype=np.int64)
+    eols = np.zeros(len(recs), dtype=np.int64)
+    if len(recs):
+        _lib.check(_lib.lib.mg_count_line_ends(data, n, len(recs), lo.ctypes.data_as(ctypes.c_void_p), hi.ctypes.data_as(ctypes.c_void_p),
+                                               eols.ctypes.data_as(ctypes.c_void_p)))
+    names = []
+    spans = {}
+    for (name, a, b), e in zip(recs, eols.tolist()):
+        size = (b - a) - e
+        if b <= a or size <= 0:
+            continue
+        if name not in spans:
+            names.append(name)
+        spans[name] = (a, b, size)
     return names, spans
 
 
@@ -623,10 +629,20 @@ class AnnotationSet(object):
         return hit
 
     def build_index(self):
-        """ID -> object for every feature with __getitem__'s precedence (one pass, used by the flattener)."""
+        """ID -> object for every feature with __getitem__'s precedence (one pass, used by the flattener).  Kept between calls
+        (module-level weak map, so the set's __dict__ stays the reference's) and rebuilt when a table has been added, removed,
+        replaced or has changed size -- the loop `for t in aset.transcript.values(): t.get_fasta()` costs one pass, not one
+        per call.  Bulk extraction should still go through AnnotationSet.get_fasta (one device plan for all records)."""
+        d = self.__dict__
+        names = self._dict_names()
+        stamp = tuple((name, id(d[name]), len(d[name])) for name in names)
+        hit = _INDEX_CACHE.get(self)
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
         idx = {}
-        for name in self._dict_names():
-            idx.update(self.__dict__[name])
+        for name in names:
+            idx.update(d[name])
+        _INDEX_CACHE[self] = (stamp, idx)
         return idx
 
     def get_seqid(self, seqid):
@@ -715,6 +731,8 @@ def _native_get_fasta(annotation_set, model, feature, seq_type, longest, genomic
     gs = getattr(genome, "genome_sequence", None) if genome is not None else None
     if gs is None:
         return None
+    import time as _time
+    t0 = _time.perf_counter()
     rows = model.table_rows(feature)
     if rows is None or rows.size == 0:
         return None
@@ -734,11 +752,17 @@ def _native_get_fasta(annotation_set, model, feature, seq_type, longest, genomic
     if tbl is None:
         return None
     protein = seq_type == "protein"
+    t1 = _time.perf_counter()
     text, lens = gs._engine().run_table(tbl, protein=protein, want_lengths=protein)
+    t2 = _time.perf_counter()
     if protein and lens is not None and ((lens[1] < 0) & (rec_name >= 0)).any():
         # Sequence.translate returned None (spliced length <= 2): '>' + name + '\n' + None (genome.py:710)
         raise TypeError("cannot concatenate 'str' and 'NoneType' objects")
-    return text[:-1].decode("latin-1")
+    out = engine.decode_text(text, strip_last=1)
+    if TIMINGS is not None:
+        TIMINGS.update({"flatten_s": t1 - t0, "device_and_copy_s": t2 - t1, "decode_s": _time.perf_counter() - t2,
+                        "records": int(tbl.n_rec), "segments": int(tbl.n_seg), "text_bytes": len(text)})
+    return out
 
 
 def write_gff(annotation_set, gff_format="simple gff3"):
@@ -842,6 +866,7 @@ def read_gff(gff, annotation_set_to_modify=None, base_features=['CDS', 'match_pa
 
 # AnnotationSets that still hold the native model of the read_gff call that made them (no Python object built yet)
 _PENDING = weakref.WeakKeyDictionary()
+_INDEX_CACHE = weakref.WeakKeyDictionary()              # AnnotationSet -> (stamp of its tables, ID -> object)
 
 
 def _apply_model(annotation_set, adict, model, ext_objects, deepcopy_order):

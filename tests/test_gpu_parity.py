@@ -956,3 +956,37 @@ def test_native_flattener_equals_object_path(mg, ref_data, gff, fasta, kw):
         n_checked += want not in ("", "AttributeError")
     assert n_checked >= 2
     g.genome_sequence.close()
+
+
+def test_longest_with_childless_gene(mg, ref_data):
+    """gff2fasta longest=True over a set that holds a gene without children: the reference's ParentAnnotation.get_fasta returns
+    "" for it before the `longest` block (genome.py:683, :730-731), i.e. a blank line, not ValueError."""
+    fa = os.path.join(ref_data, "O.biroi_refseqGenomeSubset.fasta")
+    with open(os.path.join(ref_data, "O.biroi_NCBIrefseq_gff3Subset.gff"), encoding="latin-1") as fh:
+        lines = [ln for ln in fh.read().split("\n") if ln and not ln.startswith("#") and ln.count("\t") == 8]
+
+    def attr(ln, key):
+        for x in ln.split("\t")[8].split(";"):
+            if x.startswith(key + "="):
+                return x[len(key) + 1:]
+        return None
+    picked = None
+    for gene in (ln for ln in lines if ln.split("\t")[2] == "gene"):
+        rna = [ln for ln in lines if attr(ln, "Parent") == attr(gene, "ID") and ln.split("\t")[2] == "mRNA"]
+        cds = [ln for ln in lines if ln.split("\t")[2] == "CDS" and attr(ln, "Parent") in {attr(r, "ID") for r in rna}]
+        if len(rna) >= 2 and cds:
+            picked = [gene] + rna + cds
+            break
+    assert picked is not None
+    lonely = picked[0].replace("ID=" + attr(picked[0], "ID"), "ID=lonely_gene")
+    text = "\n".join([lonely] + picked) + "\n"
+    g = mg.Genome(fa)
+    g.read_gff(text)
+    out = g.annotations.get_fasta('gene', longest=True)
+    assert out.count(">") == 1 and (out.startswith("\n") or out.endswith("\n"))
+    want = mo.read_gff(text)
+    seqs, _ = mo.read_fasta(fa)
+    want.genome = seqs
+    ref = "\n".join(mo.parent_get_fasta(want.table('gene')[k], longest=True) for k in want.table('gene'))
+    assert out == ref
+    g.genome_sequence.close()
