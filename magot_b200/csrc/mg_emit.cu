@@ -38,6 +38,9 @@
 #ifndef FRAME_LANES4
 #define FRAME_LANES4 1
 #endif
+#ifndef NUC_RC_COST
+#define NUC_RC_COST 0
+#endif
 #ifndef NUC_FASTDEC
 #define NUC_FASTDEC 1                                    // ACGT/acgt-only chunks take a two-look-up decode (mg_decode32)
 #endif
@@ -245,6 +248,16 @@ __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_nuc(
             nuc_chunk_slow(packed, s_base, s_rel, s_kind, s_unit, ncache, p, end, T, lit, exc_pos, exc_byte, n_exc, out + P0 + p);
             continue;
         }
+#if NUC_RC_COST
+        // A/B knob (profiles/README.md, "reverse-complement plane"): the ALU work a register reverse complement of this chunk
+        // would cost, applied twice (identity) to EVERY chunk, i.e. about twice what a 50 % '-' strand mix would pay without
+        // the second plane -- the memory side (a descending window instead of an ascending one) is the same traffic
+        {
+            const uint64_t a = mg_rc_nib16(mg_rc_nib16(((uint64_t)n[1] << 32) | n[0]));
+            const uint64_t b = mg_rc_nib16(mg_rc_nib16(((uint64_t)n[3] << 32) | n[2]));
+            n[0] = (uint32_t)a; n[1] = (uint32_t)(a >> 32); n[2] = (uint32_t)b; n[3] = (uint32_t)(b >> 32);
+        }
+#endif
         uint32_t w[8];
 #if NUC_FASTDEC
         mg_decode32(n, w);

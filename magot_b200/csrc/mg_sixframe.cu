@@ -16,6 +16,8 @@
 // 16-residue-per-thread gather like K3 (k_six_aa).  Only when the kept ORFs do not fit the hit list
 // (tiny min_aa: an ORF every few bases) a second genome pass writes them (k_six_orfs<true>).
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include "mg_common.cuh"
 
 #ifndef SIX_THREADS
@@ -74,8 +76,10 @@ struct mg_sixframe_state {
     int64_t aa_cap = 0;
     std::vector<void *> owned;
     bool counted = false;
+    bool force_single = false;
     cudaStream_t stream = 0;
 };
+static thread_local bool g_six_force_single = false;
 
 // ---- per-stream geometry ------------------------------------------------------------------------------
 // stream index sidx = 2*frame + (plus ? 1 : 0): reference order is sidx ascending.
@@ -718,6 +722,157 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
     }
 }
 
+
+// ---- two-level scan (min_aa >= SIX_WIN_MIN_AA) --------------------------------------------------------------------------------
+// k_six_scan spends ~18 instructions per base on exact stop positions, their prefix-max across threads / warps / tiles and
+// the ORF tests, although a kept ORF of >= 100 residues needs >= 100 stop-free codons in a row: in random DNA one window of 32
+// codons in five is stop-free, two in a row 4.7 %.  So:
+//   pass A (k_six_bits)  one thread per WINDOW of 96 bases (32 codons of each of the six streams): "does stream s hold a stop in
+//                        this window" -- six_masks + a residue mask, one ballot per stream; one bit per (stream, window) and the
+//                        last window with a stop per (tile, stream).  The genome is read once, nothing else is remembered.
+//   pass B (k_six_cand)  one thread per (tile, stream) walks the tile's 768 bits; a window with a stop that follows z stop-free
+//                        windows can only close an ORF of < 32 (z + 2) codons, so exact stop positions are recomputed (six_masks
+//                        on the two windows involved) for the few candidates only, tested with the same arithmetic as
+//                        enumerate_stream and appended to the same hit list.  "Previous stop" needs no look-back chain: the
+//                        bitmap is complete, the thread reads backwards over the per-tile summaries.
+// Everything after the scan (counts -> prefix sums -> k_six_place -> k_six_aa) is shared with the single-pass scan, which
+// stays for small min_aa.
+#define SIX_WIN 96
+#define SIX_WPT (SIX_TILE / SIX_WIN)                 // 768 windows per tile
+#define SIX_WORDS (SIX_WPT / 32)                     // 24 bitmap words per (tile, stream)
+#define SIX_WIN_MIN_AA 96                            // below this a candidate is every window: the single-pass scan is used
+static_assert(SIX_TILE % (SIX_WIN * 32) == 0, "a tile must hold a whole number of bitmap words");
+
+// stops of stream s inside window w of the contig (two 48-base halves), one bit per position
+__device__ __forceinline__ void window_stream_stops(const uint32_t *__restrict__ packed, const TileInfo &ti, int64_t w, int s, uint64_t x[2]) {
+    const uint64_t rm = 0x0000249249249249ull << stream_res(s, ti.Lm3);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int64_t xh = w * SIX_WIN + SIX_HALF * h;
+        x[h] = 0;
+        if (xh < ti.L) {
+            SixMasks sm;
+            six_masks(packed, ti.gb, ti.L, xh, ti.cs, sm);
+            x[h] = pos48((s & 1) ? sm.pm : sm.mm) & rm;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_six_bits(const uint32_t *__restrict__ packed, const int64_t *__restrict__ tile_base,
+                                                  const int32_t *__restrict__ cid, const int64_t *__restrict__ contig_len,
+                                                  const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
+                                                  const int64_t *__restrict__ m, const int32_t *__restrict__ tile_contig,
+                                                  uint32_t *__restrict__ bits, int32_t *__restrict__ last_set) {
+    __shared__ TileInfo ti;
+    const int64_t tile = blockIdx.x / 3;
+    const int part = blockIdx.x % 3;
+    if (threadIdx.x == 0) tile_info_at(tile, tile_contig[tile], tile_base, cid, contig_len, contig_base, cs, m, ti);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int wl = part * 256 + (int)threadIdx.x;          // window inside the tile
+    const int64_t x0 = (ti.k * SIX_WPT + wl) * (int64_t)SIX_WIN;
+    uint64_t P[2] = {0, 0}, M[2] = {0, 0};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int64_t xh = x0 + SIX_HALF * h;
+        if (xh < ti.L) {
+            SixMasks sm;
+            six_masks(packed, ti.gb, ti.L, xh, ti.cs, sm);
+            P[h] = pos48(sm.pm);
+            M[h] = pos48(sm.mm);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        const uint64_t rm = 0x0000249249249249ull << stream_res(s, ti.Lm3);
+        const bool has = ti.m[s] > 0 && ((((s & 1) ? P[0] : M[0]) | ((s & 1) ? P[1] : M[1])) & rm) != 0;
+        const unsigned int b = __ballot_sync(0xffffffffu, has);
+        if (lane == 0) {
+            bits[(tile * 6 + s) * SIX_WORDS + part * 8 + wid] = b;
+            if (b) atomicMax(last_set + tile * 6 + s, part * 256 + wid * 32 + 31 - __clz(b));
+        }
+    }
+}
+
+// 3 * residues of the candidate ORF between a lower stop xl and a higher stop xh (the arithmetic of enumerate_stream::visit)
+__device__ __forceinline__ int64_t six_span3(const TileInfo &ti, int s, int64_t xl, bool xl_real, int64_t xh, bool xh_real) {
+    const int plus = s & 1;
+    const int32_t L32 = (int32_t)ti.L, cs32 = ti.cs[s], m32 = (int32_t)ti.m[s];
+    const int32_t ql = plus ? (int32_t)xl - cs32 : L32 - 3 - cs32 - (int32_t)xl;
+    const int32_t qh = plus ? (int32_t)xh - cs32 : L32 - 3 - cs32 - (int32_t)xh;
+    if (plus) return (int64_t)(xh_real ? qh : 3 * m32) - (xl_real ? ql : -3) - 3;
+    return (int64_t)(xl_real ? ql : 3 * m32) - (xh_real ? qh : -3) - 3;
+}
+
+__global__ void __launch_bounds__(128) k_six_cand(const uint32_t *__restrict__ packed, const int64_t *__restrict__ tile_base,
+                                                  const int32_t *__restrict__ cid, const int64_t *__restrict__ contig_len,
+                                                  const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
+                                                  const int64_t *__restrict__ m, const int32_t *__restrict__ tile_contig, int64_t n_tiles,
+                                                  const uint32_t *__restrict__ bits, const int32_t *__restrict__ last_set, int64_t min_aa,
+                                                  int32_t *__restrict__ cnt, SixHit *__restrict__ hits, int64_t hit_cap,
+                                                  unsigned long long *hit_count) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_tiles * 6) return;
+    const int64_t tile = i / 6;
+    const int s = (int)(i % 6);
+    TileInfo ti;
+    tile_info_at(tile, tile_contig[tile], tile_base, cid, contig_len, contig_base, cs, m, ti);
+    const int64_t li = layout_index(ti, tile_base, s);
+    if (ti.m[s] <= 0) { cnt[li] = 0; return; }           // `if translated_seq:` (genome.py:832)
+    const int64_t need3 = 3 * min_aa;
+    // last window with a stop before this tile (same contig, same stream): backwards over the per-tile summaries
+    int64_t prev_w = -1;
+    for (int64_t tt = tile - 1; tt >= tile - ti.k; tt--) {
+        const int32_t ls = last_set[tt * 6 + s];
+        if (ls >= 0) { prev_w = (tt - (tile - ti.k)) * SIX_WPT + ls; break; }
+    }
+    int k = 0;
+    auto keep = [&](int64_t xl, bool xl_real, int64_t xh, bool xh_real) {
+        if (six_span3(ti, s, xl, xl_real, xh, xh_real) < need3) return;
+        const unsigned long long slot = atomicAdd(hit_count, 1ull);
+        if ((int64_t)slot < hit_cap) {
+            SixHit h;
+            h.tile = (int32_t)tile; h.rank = k; h.xl = (int32_t)xl; h.xh = (int32_t)xh;
+            h.s = (uint8_t)s; h.xl_real = xl_real; h.xh_real = xh_real; h.pad = 0;
+            hits[slot] = h;
+        }
+        k++;
+    };
+    auto last_stop_in = [&](int64_t w) -> int64_t {        // exact position of the last stop of the stream in window w (it has one)
+        uint64_t x[2];
+        window_stream_stops(packed, ti, w, s, x);
+        return w * SIX_WIN + (x[1] ? SIX_HALF + 63 - __clzll((long long)x[1]) : 63 - __clzll((long long)x[0]));
+    };
+    const uint32_t *row = bits + (tile * 6 + s) * SIX_WORDS;
+    const int64_t w0 = ti.k * SIX_WPT;
+#pragma unroll 1
+    for (int j = 0; j < SIX_WORDS; j++) {
+        uint32_t b = __ldg(row + j);
+        while (b) {
+            const int64_t w = w0 + j * 32 + __ffs(b) - 1;
+            b &= b - 1;
+            const int64_t z = w - prev_w - 1;              // stop-free windows in front of this one
+            if (32 * (z + 2) > min_aa) {                   // else the ORF this window closes has < 32 (z + 2) - 1 residues
+                uint64_t x[2];
+                window_stream_stops(packed, ti, w, s, x);
+                const int64_t xh = w * SIX_WIN + (x[0] ? __ffsll((long long)x[0]) - 1 : SIX_HALF + __ffsll((long long)x[1]) - 1);
+                const int64_t xl = prev_w >= 0 ? last_stop_in(prev_w) : -1;
+                keep(xl, prev_w >= 0, xh, true);
+            }
+            prev_w = w;
+        }
+    }
+    if (ti.k == ti.Tc - 1) {                               // the virtual stop at the contig's high end belongs to the last tile
+        const int64_t Lw = (ti.L + SIX_WIN - 1) / SIX_WIN;
+        const int64_t z = Lw - prev_w - 1;
+        if (32 * (z + 2) > min_aa) {
+            const int64_t xl = prev_w >= 0 ? last_stop_in(prev_w) : -1;
+            keep(xl, prev_w >= 0, 0, false);
+        }
+    }
+    cnt[li] = k;
+}
+
 // thread per hit: reference-order slot of the ORF and its record
 __global__ void __launch_bounds__(256) k_six_place(const SixHit *__restrict__ hits, int64_t n_hit, const int64_t *__restrict__ tile_base,
                                                    int64_t nc, const int32_t *__restrict__ cid, const int64_t *__restrict__ contig_len,
@@ -909,6 +1064,7 @@ extern "C" int mg_sixframe_count_list(mg_genome *g, int64_t n_list, const int64_
     g->six = s;
     s->stream = st;
     s->min_aa = min_aa;
+    s->force_single = g_six_force_single;
     const int64_t nc = n_list;
     std::vector<int32_t> &h_cid = s->h_cid;
     h_cid.resize(nc);
@@ -948,15 +1104,43 @@ extern "C" int mg_sixframe_count_list(mg_genome *g, int64_t n_list, const int64_
     TRY(six_alloc(s, &s->d_tile_contig, s->n_tiles));
     k_six_tile_contig<<<(unsigned)((s->n_tiles + 255) / 256), 256, 0, st>>>(s->d_tile_base, nc, s->n_tiles, s->d_tile_contig);
     MG_LAUNCH_CHECK();
-    k_six_scan<<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, s->d_cid, g->d_contig_len, g->d_contig_base,
-                                                              s->d_cs, s->d_m, s->d_tile_contig, s->n_tiles, s->d_look, s->d_carry, min_aa, 2 * g->total_bases,
-                                                              s->d_cnt, s->d_hits, s->hit_cap, s->d_hit_count);
-    MG_LAUNCH_CHECK();
+    static int two_level = -1;                        // env MAGOT_SIX=two selects the two-level scan (A/B; the single pass is faster so far)
+    if (two_level < 0) { const char *e = getenv("MAGOT_SIX"); two_level = (e && !strcmp(e, "two")) ? 1 : 0; }
+    const bool use_two_level = two_level && min_aa >= SIX_WIN_MIN_AA && !s->force_single;
+    if (use_two_level) {
+        uint32_t *d_bits = nullptr;
+        int32_t *d_last = nullptr;
+        TRY(six_alloc(s, &d_bits, s->n_tiles * 6 * SIX_WORDS));
+        TRY(six_alloc(s, &d_last, s->n_tiles * 6));
+        MG_CUDA(cudaMemsetAsync(d_last, 0xFF, s->n_tiles * 6 * sizeof(int32_t), st));
+        k_six_bits<<<(unsigned)(s->n_tiles * 3), 256, 0, st>>>(g->d_packed, s->d_tile_base, s->d_cid, g->d_contig_len, g->d_contig_base, s->d_cs,
+                                                              s->d_m, s->d_tile_contig, d_bits, d_last);
+        MG_LAUNCH_CHECK();
+        k_six_cand<<<(unsigned)((s->n_tiles * 6 + 127) / 128), 128, 0, st>>>(g->d_packed, s->d_tile_base, s->d_cid, g->d_contig_len,
+                                                                             g->d_contig_base, s->d_cs, s->d_m, s->d_tile_contig, s->n_tiles, d_bits,
+                                                                             d_last, min_aa, s->d_cnt, s->d_hits, s->hit_cap, s->d_hit_count);
+        MG_LAUNCH_CHECK();
+    } else {
+        k_six_scan<<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, s->d_cid, g->d_contig_len, g->d_contig_base,
+                                                                  s->d_cs, s->d_m, s->d_tile_contig, s->n_tiles, s->d_look, s->d_carry, min_aa, 2 * g->total_bases,
+                                                                  s->d_cnt, s->d_hits, s->hit_cap, s->d_hit_count);
+        MG_LAUNCH_CHECK();
+    }
     s->scan_tmp_cap = mg_scan_tmp_elems(s->n_tiles * 6) + 2;
     TRY(six_alloc(s, &s->d_scan_tmp, s->scan_tmp_cap));
     TRY(mg_scan_i32(s->d_cnt, s->d_cnt_off, s->n_tiles * 6, s->d_scan_tmp, s->scan_tmp_cap, st));
     MG_CUDA(cudaMemcpyAsync(&s->n_orf, s->d_cnt_off + s->n_tiles * 6, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     MG_CUDA(cudaStreamSynchronize(st));
+    if (use_two_level && s->n_orf > s->hit_cap) {     // more kept ORFs than the hit list holds: the single-pass scan + dense emit
+#undef TRY
+        std::vector<int64_t> ids(contig_ids, contig_ids + n_list);
+        mg_sixframe_free(g);
+        g_six_force_single = true;
+        const int rc2 = mg_sixframe_count_list(g, n_list, ids.data(), min_aa, n_orf, n_bytes, stream);
+        g_six_force_single = false;
+        return rc2;
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+    }
     if (s->n_orf > 0) {
         TRY(six_alloc(s, &s->d_recs, s->n_orf));
         TRY(six_alloc(s, &s->d_len, s->n_orf));

@@ -504,7 +504,7 @@ def test_sixframe_matches_reference_get_orfs(mg, kat):
         assert got == r, (len(s), s[:40])
 
 
-@pytest.mark.parametrize("min_aa", [0, 1, 15, 16, 30, 31, 32, 33, 47, 48, 49, 100])
+@pytest.mark.parametrize("min_aa", [0, 1, 15, 16, 30, 31, 32, 33, 47, 48, 49, 95, 96, 97, 100, 127, 128, 129, 300, 4000])
 def test_sixframe_random_contigs(mg, min_aa):
     rng = np.random.default_rng(100 + min_aa)
     alpha = np.frombuffer(b"ACGTacgtNnR", dtype=np.uint8)
@@ -517,6 +517,12 @@ def test_sixframe_random_contigs(mg, min_aa):
     c = bytearray(alpha[rng.integers(0, 4, size=50000)].tobytes())
     c[20000:33000] = b"N" * 13000
     contigs.append(bytes(c))
+    # a stop-free stretch longer than several tiles inside a long contig (the two-level scan reads back over tile summaries),
+    # and contigs that end / begin inside stop-free windows
+    c = bytearray(alpha[rng.integers(0, 4, size=400000)].tobytes())
+    c[60000:300000] = np.frombuffer(b"ACG", dtype=np.uint8)[rng.integers(0, 3, size=240000)].tobytes()
+    contigs.append(bytes(c))
+    contigs.append(np.frombuffer(b"ACG", dtype=np.uint8)[rng.integers(0, 3, size=73728 * 2 + 5)].tobytes())
     _sixframe_case(mg, contigs, min_aa)
 
 
