@@ -140,6 +140,22 @@ int mg_emit_nuc_device(mg_plan *p, uint8_t *out_dev, void *stream);
 /* ---- K3: protein -- replaces Sequence.translate(frame=0,strand='+') (genome.py:795-822) on the
  * spliced sequence (genome.py:707).  Same buffer rules with prot_total.                     */
 int mg_emit_prot_device(mg_plan *p, uint8_t *out_dev, void *stream);
+/* ---- K23: fused splice + translate -- the reference translates the very string it has just joined (genome.py:704-707:
+ * seq = "".join(...get_seq()); Sequence(seq).translate()).  One launch writes the nucleotide text of the plan to nuc_out_dev and
+ * its protein text to prot_out_dev (buffer rules of the two single calls): the CTA that assembles 32 KB of nucleotide text keeps
+ * the bases in shared memory and translates the codons that start there, so the genome is read once.  Bit-identical to
+ * mg_emit_nuc_device + mg_emit_prot_device.  The _host variant copies both texts to host buffers (stream-ordered).          */
+int mg_emit_nuc_prot_device(mg_plan *p, uint8_t *nuc_out_dev, uint8_t *prot_out_dev, void *stream);
+int mg_emit_nuc_prot_host(mg_plan *p, uint8_t *nuc_out_host, uint8_t *prot_out_host, void *stream);
+/* ---- K2 + K2 + K3 of one batch in ONE launch -- what `gff2fasta` run three times (seq_type nucleotide on the exon-based
+ * transcripts, nucleotide and protein on the CDS; genome_tools.py:324-330, genome.py:687-710) reads from the genome: the same
+ * bases.  Nucleotide text of plan `pa` -> out_a, nucleotide text of plan `pb` -> out_b_nuc, protein text of `pb` -> out_b_prot
+ * (buffer rules as above; any output may be NULL and is then skipped).  The tiles of the products are interleaved so that every
+ * product advances through the record list at the same pace, `pb` slightly behind `pa`: when both plans list the same
+ * transcripts in the same order (exon table / CDS table) the later products find their genome bytes in L2 instead of DRAM.
+ * The texts are bit-identical to the single-product calls.                                                                */
+int mg_emit_products_device(mg_plan *pa, uint8_t *out_a, mg_plan *pb, uint8_t *out_b_nuc, uint8_t *out_b_prot, void *stream);
+int mg_emit_products_host(mg_plan *pa, uint8_t *out_a_host, mg_plan *pb, uint8_t *out_b_nuc_host, uint8_t *out_b_prot_host, void *stream);
 /* Host-buffer variants: run the kernel into a library-owned device buffer and copy the exact
  * text (nuc_total / prot_total bytes) to `out_host` (pinned for full PCIe speed).  The copy is
  * stream-ordered; call mg_stream_sync before reading.                                        */
@@ -232,7 +248,9 @@ int mg_graph_destroy(void *graph_exec);
 /* `waiter` waits for everything queued so far on `signaller` (event record + wait; usable inside a capture). */
 int mg_stream_wait_stream(int device, void *waiter, void *signaller);
 /* Developer / test knob: run-time choice between kernel variants that give bit-identical results ("emit": 0 = k_emit_nuc
- * (default), 1 = bulk-copy staged, 2 = streaming; "k1": 0 = piece-parallel plan launches (default), 1 = one-launch plan kernel).  */
+ * (default), 1 = bulk-copy staged, 2 = streaming; "k1": 0 = piece-parallel plan launches (default), 1 = one-launch plan kernel;
+ * "fuse": 1 = mg_emit_nuc_prot_* as one fused launch (default), 0 = as K2 + K3;
+ * "multi_lag": distance between the products of mg_emit_products_device in millionths of a text).  */
 int mg_tune(const char *key, int value);
 /* Number of kernels launched by this library since load (per process), for bench accounting. */
 int64_t mg_kernel_launches(void);

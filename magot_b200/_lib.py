@@ -63,6 +63,10 @@ SIGNATURES = {
     "mg_plan_lengths": (_i32, [_vp, _vp, _vp, _vp]),
     "mg_emit_nuc_device": (_i32, [_vp, _vp, _vp]),
     "mg_emit_prot_device": (_i32, [_vp, _vp, _vp]),
+    "mg_emit_nuc_prot_device": (_i32, [_vp, _vp, _vp, _vp]),
+    "mg_emit_nuc_prot_host": (_i32, [_vp, _vp, _vp, _vp]),
+    "mg_emit_products_device": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "mg_emit_products_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "mg_emit_nuc_host": (_i32, [_vp, _vp, _vp]),
     "mg_emit_prot_host": (_i32, [_vp, _vp, _vp]),
     "mg_revcomp": (_i32, [_i32, _vp, _i64, _vp, _vp]),

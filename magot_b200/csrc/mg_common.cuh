@@ -130,6 +130,8 @@ struct mg_plan {
     bool totals_known = false;                    // false between mg_plan_prepare_async and mg_plan_totals
     int prot_flags = 0;
     bool prepared = false;
+    uint32_t *d_order = nullptr;              // rank -> (job, tile) of mg_emit_products_device launches led by this plan
+    int64_t order_cap = 0;
     uint8_t *d_out = nullptr;                 // library-owned output buffer for *_host emits
     int64_t out_cap = 0;
     std::vector<void *> owned;                // everything to free
@@ -157,6 +159,8 @@ void mg_parallel_copy(const uint8_t *src, uint8_t *dst, int64_t n);   // memcpy 
 int mg_emit_mode();                                   // K2 variant, env MAGOT_EMIT: 0 = ldg (mg_emit.cu, default: the fastest), 1 = tma (mg_emit_tma.cu), 2 = stream (mg_emit_stream.cu)
 int mg_launch_nuc_tma(mg_plan *p, uint8_t *out_dev, cudaStream_t st);
 int mg_launch_nuc_stream(mg_plan *p, uint8_t *out_dev, cudaStream_t st);
+void mg_set_fuse(int v);                              // mg_tune("fuse", 0/1): K23 as one fused launch (1, default) or K2 + K3
+void mg_set_multi_lag(int ppm);                       // lag between the jobs of mg_emit_products_device (mg_tune("multi_lag", ppm))
 
 #ifdef __CUDACC__
 // ---- device primitives -----------------------------------------------------------------------------

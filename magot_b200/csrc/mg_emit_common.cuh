@@ -84,6 +84,14 @@ __device__ __forceinline__ void st32(uint8_t *p, const uint32_t w[8]) {         
                  "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 
+// The same 32 bytes as two 128-bit stores, for the out-of-line slow paths: ptxas 12.9 turns the v8 store into a single 32-bit
+// STG when it clones such a helper for an entry that takes its arguments as a __grid_constant__ struct (seen in the SASS of
+// nuc_chunk_slow / nuc_chunk_generic under k_emit_nuc: only the first word of a chunk with out-of-alphabet bytes was written).
+__device__ __forceinline__ void st32_2x16(uint8_t *p, const uint32_t w[8]) {
+    asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+    asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p + 16), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
 // 32 nibbles -> 32 ASCII bytes.  Chunks without N / IUPAC / '-' codes (bit 3 clear in every nibble: A C G T a c g t) need two
 // table look-ups per word; the general decode needs four plus the two select masks (and, at 32 registers, re-materialises
 // its four table constants: 70 instructions per chunk in the round-1 SASS against ~20 here).
@@ -143,7 +151,7 @@ static __device__ __noinline__ void nuc_chunk_generic(const uint32_t *__restrict
         }
         t = hi;
     }
-    st32(out + P, w);
+    st32_2x16(out + P, w);
 }
 
 #define PIECE_G 0

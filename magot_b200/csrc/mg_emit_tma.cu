@@ -386,6 +386,8 @@ extern "C" int mg_tune(const char *key, int value) {
     MG_REQUIRE(key != nullptr, "key is NULL");
     if (!strcmp(key, "emit")) { MG_REQUIRE(value >= 0 && value <= 2, "emit variant must be 0, 1 or 2"); g_emit_mode = value; return MG_OK; }
     if (!strcmp(key, "k1")) { mg_set_k1_mode(value); return MG_OK; }
+    if (!strcmp(key, "fuse")) { mg_set_fuse(value != 0); return MG_OK; }
+    if (!strcmp(key, "multi_lag")) { MG_REQUIRE(value >= 0 && value <= 1000000, "multi_lag is in millionths of a text"); mg_set_multi_lag(value); return MG_OK; }
     mg_set_error("mg_tune: unknown key '%s'", key);
     return MG_EINVAL;
 }

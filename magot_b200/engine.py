@@ -208,6 +208,16 @@ class Plan(object):
         check(lib.mg_stream_sync(self.genome.device, self.stream))
         return obj
 
+    def emit_both_host(self):
+        """K23 (mg_emit_nuc_prot_host): the nucleotide text and its translation from ONE pass over the genome, as the
+        reference produces them (genome.py:704-707).  Returns (nuc, prot) uint8 arrays."""
+        nuc = np.empty(self.nuc_total, dtype=np.uint8)
+        prot = np.empty(self.prot_total, dtype=np.uint8)
+        if self.nuc_total or self.prot_total:
+            check(lib.mg_emit_nuc_prot_host(self.handle, _ptr(nuc), _ptr(prot), self.stream))
+            check(lib.mg_stream_sync(self.genome.device, self.stream))
+        return nuc, prot
+
     def emit_device(self, dev_ptr, protein=False):
         fn = lib.mg_emit_prot_device if protein else lib.mg_emit_nuc_device
         check(fn(self.handle, ctypes.c_void_p(dev_ptr), self.stream))
@@ -234,6 +244,39 @@ def run_table(genome, table, protein=False, trimx=True, use_phase=False, want_le
     finally:
         plan.close()
     return text, lens
+
+
+def run_table_both(genome, table, trimx=True, use_phase=False, async_prepare=False):
+    """Nucleotide AND protein text of one batch from one fused pass (K23). Returns (nuc bytes, prot bytes)."""
+    plan = Plan(genome, table)
+    try:
+        if async_prepare:
+            plan.prepare_async(trimx=trimx, use_phase=use_phase)
+            plan.totals()
+        else:
+            plan.prepare(trimx=trimx, use_phase=use_phase)
+        nuc, prot = plan.emit_both_host()
+    finally:
+        plan.close()
+    return nuc.tobytes(), prot.tobytes()
+
+
+def run_products(genome, table_a, table_b, protein_b=True, trimx=True, use_phase=False):
+    """mg_emit_products_host: nucleotide text of table_a, nucleotide (+ protein) text of table_b from one launch.
+    Returns (text_a, nuc_b, prot_b) as bytes (prot_b is b"" without protein_b)."""
+    pa, pb = Plan(genome, table_a), Plan(genome, table_b)
+    try:
+        pa.prepare(trimx=trimx, use_phase=use_phase)
+        pb.prepare(trimx=trimx, use_phase=use_phase)
+        oa = np.empty(pa.nuc_total, dtype=np.uint8)
+        obn = np.empty(pb.nuc_total, dtype=np.uint8)
+        obp = np.empty(pb.prot_total if protein_b else 0, dtype=np.uint8)
+        check(lib.mg_emit_products_host(pa.handle, _ptr(oa), pb.handle, _ptr(obn), _ptr(obp) if protein_b else None, None))
+        check(lib.mg_stream_sync(genome.device, None))
+    finally:
+        pa.close()
+        pb.close()
+    return oa.tobytes(), obn.tobytes(), obp.tobytes()
 
 
 def shard_bounds(weights, n_shards):

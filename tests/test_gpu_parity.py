@@ -279,6 +279,22 @@ def test_pack_fasta_strips_line_ends_on_device(mg):
 
 # ---- synthetic twins of configs 3/4 against the C oracle --------------------------------------------------------
 
+def _check_fused(g, tbl, text, textp, other=None):
+    """K23 (mg_emit_nuc_prot_*: nucleotide + protein text from one pass, genome.py:704-707) and the one-launch form of all
+    products (mg_emit_products_*) must give the very bytes of the single-product kernels (which the caller has compared with
+    the oracle), after mg_plan_prepare and after mg_plan_prepare_async."""
+    from magot_b200 import engine
+    for async_prepare in (False, True):
+        n, p = engine.run_table_both(g, tbl, async_prepare=async_prepare)
+        assert n == text, ("K23 nucleotide text", async_prepare)
+        assert p == textp, ("K23 protein text", async_prepare)
+    a, bn, bp = engine.run_products(g, other if other is not None else tbl, tbl)
+    assert bn == text and bp == textp
+    if other is None:
+        assert a == text
+    return a
+
+
 def _oracle_products(contigs, tbl):
     lens = np.array([a.size for a in contigs])
     # Python slice semantics for in-range/overrunning coordinates (all synthetic starts are >= 1)
@@ -323,6 +339,13 @@ def test_synthetic_twin_against_c_oracle(mg, kind, total, ntx, seed):
         textp, _ = engine.run_table(g, tblf, protein=True)
         wantp = b"".join(b">" + n.encode() + b"\n" + aa[aa_off[i]:aa_off[i + 1]].tobytes() + b"\n" for i, n in enumerate(ann.names))
         assert textp == wantp
+        _check_fused(g, tbl, nuc.tobytes(), aa.tobytes())
+        if which == "cds":                                # the step of config 4: exon text + CDS text + protein in one launch
+            exon_f = ann.table("exon", framing=True)
+            got_exon = _check_fused(g, tblf, want, wantp, other=exon_f)
+            assert got_exon == engine.run_table(g, exon_f)[0]
+        else:
+            _check_fused(g, tblf, want, wantp)
     g.close()
 
 
@@ -370,6 +393,7 @@ def test_dense_tiny_segments_overflow_the_tile_staging(mg, framing):
         want, wantp = nuc.tobytes(), aa.tobytes()
     assert text == want
     assert textp == wantp
+    _check_fused(g, tbl, want, wantp)
     g.close()
 
 
@@ -424,6 +448,7 @@ def test_random_tables_differential(mg, seed):
         wantp.append(head + aa[aa_off[r]:aa_off[r + 1]].tobytes() + tail)
     assert text == b"".join(want)
     assert textp == b"".join(wantp)
+    _check_fused(g, tbl, text, textp)
     g.close()
 
 
@@ -460,6 +485,7 @@ def test_edge_records(mg):
     assert plan.emit_host(False).tobytes().decode() == "".join(want_n)
     assert plan.emit_host(True).tobytes().decode() == "".join(want_p)
     plan.close()
+    _check_fused(g, tbl, "".join(want_n).encode(), "".join(want_p).encode())
     empty = engine.RecordTable([0], [], [], [], [], [], [], [], np.zeros(0, np.uint8))
     assert engine.run_table(g, empty)[0] == b""
     g.close()
