@@ -457,6 +457,22 @@ class Workload(object):
         share the GPU (measured: 0.458 ms against 0.480 ms with the emit kernels put in series, scratch/overlap.py)."""
         import torch
         lib, chk, P = self.lib, self._lib.check, self.P
+        mode = STEP_MODE
+        if mode == "fused":
+            # CDS plan: K1 -> K23 (nucleotide + protein text from one pass) on `stream`; exon plan: K1 -> K2 on `stream_b`
+            self.prepare_on("cds", self.stream)
+            chk(lib.mg_emit_nuc_prot_device(self.plans["cds"], P(self.out["cds_n"]), P(self.out["cds_p"]), self.sp(self.stream)))
+            self.prepare_on("exon", self.stream_b)
+            chk(lib.mg_emit_nuc_device(self.plans["exon"], P(self.out["exon_n"]), self.sp(self.stream_b)))
+            return
+        if mode == "multi":
+            # both K1 side by side on two streams, then ONE launch for the three products (tiles interleaved for L2 reuse)
+            self.prepare_on("exon", self.stream_b)
+            self.prepare_on("cds", self.stream)
+            self.stream.wait_stream(self.stream_b)
+            chk(lib.mg_emit_products_device(self.plans["exon"], P(self.out["exon_n"]), self.plans["cds"], P(self.out["cds_n"]),
+                                            P(self.out["cds_p"]), self.sp(self.stream)))
+            return
         self.prepare_on("cds", self.stream)
         e1 = torch.cuda.Event()
         e1.record(self.stream)
@@ -531,6 +547,9 @@ class Workload(object):
     def close(self):
         for h in self.plans.values():
             self.lib.mg_plan_destroy(h)
+
+
+STEP_MODE = os.environ.get("MAGOT_STEP", "streams3")     # streams3 | fused | multi  (see Workload.step)
 
 
 def profile_traffic():

@@ -141,21 +141,23 @@ struct NucArgs {
 };
 // pieces of the tile: piece i covers text [s_rel[i], s_rel[i+1]) relative to the tile; the nibble index (literal: byte
 // index) of tile position q is s_base[i] + q; s_ng[i] = first non-empty GENOME piece at or after i
-struct NucSmem {
-    int64_t s_base[NUC_CAP + 2];
-    int32_t s_rel[NUC_CAP + 3];
-    uint16_t s_ng[NUC_CAP + 2];
-    uint8_t s_kind[NUC_CAP + 2];
+template <int CAP>
+struct NucSmemT {
+    int64_t s_base[CAP + 2];
+    int32_t s_rel[CAP + 3];
+    uint16_t s_ng[CAP + 2];
+    uint8_t s_kind[CAP + 2];
     uint16_t s_unit[NUC_UNITS];                       // piece holding byte 32*u of the tile, i.e. the first byte of chunk u
     uint16_t s_lits[NUC_LITCAP];                      // the tile's non-empty literal pieces (any order)
     int s_nlit;
 };
+typedef NucSmemT<NUC_CAP> NucSmem;
 
 // one CTA, one 32 KB tile of the nucleotide text (the caller has checked tile * MG_NUC_TILE < total).  STAGE: the merged
 // nibbles of every chunk are also left in shared memory (s_nib[8 + 4 * chunk ..], the K23 protein phase reads its codons there);
 // *s_over is set when a chunk of the tile went through the generic path (its nibbles are then not staged).
-template <bool STAGE>
-__device__ __forceinline__ void nuc_tile(const NucArgs &a, NucSmem &sm, const int64_t tile, const int64_t total, uint32_t *s_nib = nullptr,
+template <bool STAGE, int CAP>
+__device__ __forceinline__ void nuc_tile(const NucArgs &a, NucSmemT<CAP> &sm, const int64_t tile, const int64_t total, uint32_t *s_nib = nullptr,
                                          int *s_over = nullptr) {
     const uint32_t *__restrict__ packed = a.packed;
     const int64_t *__restrict__ piece_off = a.piece_off, *__restrict__ piece_src = a.piece_src;
@@ -174,7 +176,7 @@ __device__ __forceinline__ void nuc_tile(const NucArgs &a, NucSmem &sm, const in
     const int64_t p_lo = tile_first[tile];
     int64_t p_hi = tile_first[tile + 1] + 1;          // one past the last piece this tile can touch
     if (p_hi > n_piece) p_hi = n_piece;
-    const int ncache = (int)min((int64_t)NUC_CAP, p_hi - p_lo);
+    const int ncache = (int)min((int64_t)CAP, p_hi - p_lo);
     const int tile_len = (int)min((int64_t)MG_NUC_TILE, total - P0);
     if (threadIdx.x == 0) s_nlit = 0;
     for (int i = threadIdx.x; i < ncache + 2; i += NUC_THREADS) {
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_nuc(const __grid
     const int64_t total = min(__ldg(a.total_dev), a.cap);
     if ((int64_t)blockIdx.x * MG_NUC_TILE >= total) return;
     __shared__ NucSmem sm;
-    nuc_tile<false>(a, sm, blockIdx.x, total);
+    nuc_tile<false, NUC_CAP>(a, sm, blockIdx.x, total);
 }
 
 
@@ -567,6 +569,10 @@ __global__ void __launch_bounds__(PROT_THREADS, PROT_MINB) k_emit_prot(const __g
 #ifndef K23_MINB
 #define K23_MINB 6
 #endif
+#ifndef K23_CAP
+#define K23_CAP NUC_CAP                              // pieces staged per tile in the fused kernel
+#endif
+#define K23_PMAX (MG_NUC_TILE / 3 + 64 * K23_RCAP + 64)   // the protein range of a tile that stays on the fast path (else per-residue path)
 #define K23_NIBW (MG_NUC_TILE / 8 + 16)               // staged nibble words: the tile + 8 words of slack at both ends
 
 struct FusedArgs {
@@ -575,7 +581,7 @@ struct FusedArgs {
 };
 struct FusedSmem {
     union {
-        NucSmem n;                                   // phase 1
+        NucSmemT<K23_CAP> n;                         // phase 1
         struct {                                     // phase 2
             __align__(16) uint8_t s_aa[4096];
             int32_t r_s[K23_RCAP + 2], r_e[K23_RCAP + 2], r_q0[K23_RCAP + 2];   // owned residues [r_s, r_e) relative to Abase; codon of position x at r_q0 + 3x
@@ -647,13 +653,13 @@ __global__ void __launch_bounds__(NUC_THREADS, K23_MINB) k_emit_nuc_prot(const _
         sm.s_bound[1][0] = a.n_rec - 1;
         sm.s_bound[1][1] = total_p;
     }
-    nuc_tile<true>(f.n, sm.u.n, tile, total, sm.s_nib, &sm.s_over);
+    nuc_tile<true, K23_CAP>(f.n, sm.u.n, tile, total, sm.s_nib, &sm.s_over);
     __syncthreads();                                  // the nucleotide framing has read its tables: phase 2 may overwrite them
     const int64_t R0 = sm.s_bound[0][0], R1 = sm.s_bound[1][0];
     const int64_t A = min(sm.s_bound[0][1], total_p), B = min(sm.s_bound[1][1], total_p);
     const int64_t Abase = A & ~(int64_t)15;
     const int nrec = (int)min(R1 - R0 + 1, (int64_t)K23_RCAP + 1);
-    const bool slow = sm.s_over != 0 || R1 - R0 + 1 > K23_RCAP || B - Abase > (int64_t)BIG / 4;
+    const bool slow = sm.s_over != 0 || R1 - R0 + 1 > K23_RCAP || B - Abase > (int64_t)K23_PMAX;
     uint8_t *__restrict__ out = a.out;
     if (slow) {                                       // per residue from global memory; framing below
         for (int64_t r = R0; r <= R1; r++) {
@@ -738,8 +744,11 @@ __global__ void __launch_bounds__(NUC_THREADS, K23_MINB) k_emit_nuc_prot(const _
                 }
                 const uint32_t m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
                 own |= m;
+                if (m == 0xFFFFu) { bw[0] = w[0]; bw[1] = w[1]; bw[2] = w[2]; bw[3] = w[3]; }
+                else {
 #pragma unroll
-                for (int k = 0; k < 4; k++) { const uint32_t mk = expand4(m >> (4 * k)); bw[k] = (bw[k] & ~mk) | (w[k] & mk); }
+                    for (int k = 0; k < 4; k++) { const uint32_t mk = expand4(m >> (4 * k)); bw[k] = (bw[k] & ~mk) | (w[k] & mk); }
+                }
             }
             const int64_t pos = Abase + p;
             if (pos >= A && pos + 16 <= B) {
@@ -924,8 +933,8 @@ __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_multi(const __gr
     const uint32_t o = __ldg(m.order + blockIdx.x);
     const int64_t tile = o & 0x0FFFFFFFu;
     const uint32_t job = o >> 28;
-    if (job == 0) nuc_tile<false>(m.a, sm.n, tile, min(__ldg(m.a.total_dev), m.a.cap));
-    else if (job == 1) nuc_tile<false>(m.b, sm.n, tile, min(__ldg(m.b.total_dev), m.b.cap));
+    if (job == 0) nuc_tile<false, NUC_CAP>(m.a, sm.n, tile, min(__ldg(m.a.total_dev), m.a.cap));
+    else if (job == 1) nuc_tile<false, NUC_CAP>(m.b, sm.n, tile, min(__ldg(m.b.total_dev), m.b.cap));
     else prot_tile(m.c, sm.p, tile, min(__ldg(m.c.total_dev), m.c.cap));
 }
 
