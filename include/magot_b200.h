@@ -249,7 +249,8 @@ int mg_graph_destroy(void *graph_exec);
 int mg_stream_wait_stream(int device, void *waiter, void *signaller);
 /* Developer / test knob: run-time choice between kernel variants that give bit-identical results ("emit": 0 = k_emit_nuc
  * (default), 1 = bulk-copy staged, 2 = streaming; "k1": 0 = piece-parallel plan launches (default), 1 = one-launch plan kernel;
- * "fuse": 1 = mg_emit_nuc_prot_* as one fused launch (default), 0 = as K2 + K3;
+ * "six": K4 scan for min_aa >= 96: 2 = two-level scan over the stop-codon index (default), 1 = two-level scan on the packed
+ * bases, 0 = single-pass scan; "fuse": 1 = mg_emit_nuc_prot_* as one fused launch (default), 0 = as K2 + K3;
  * "multi_lag": distance between the products of mg_emit_products_device in millionths of a text).  */
 int mg_tune(const char *key, int value);
 /* Number of kernels launched by this library since load (per process), for bench accounting. */

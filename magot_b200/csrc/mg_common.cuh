@@ -89,6 +89,9 @@ struct mg_genome {
     int64_t pin_cap = 0;
     uint8_t *d_aa4096 = nullptr;              // 4096-entry nibble-triplet -> amino acid table
     uint8_t *d_aa4096h = nullptr;             // the same, entry of codon c stored at mg_aa_slot(c) (shared-memory friendly)
+    uint32_t *d_stops = nullptr;              // stop-codon index (K4): one bit per base and strand, [0, stop_words) plus, [stop_words, 2 stop_words) minus
+    int64_t stop_words = 0;
+    bool stops_valid = false;                 // false after pack / mask: rebuilt by the next ORF scan
     mg_sixframe_state *six = nullptr;
     int64_t device_bytes = 0;
 };

@@ -382,10 +382,12 @@ int mg_emit_mode() {
 // Developer / test knob: select a kernel variant at run time (the variants are bit-identical in their results; tests run all of
 // them).  "emit": 0 = k_emit_nuc (default), 1 = k_emit_nuc_tma, 2 = k_emit_nuc_stream; "k1": 0 = piece-parallel launches (default), 1 = k_plan_rec.
 void mg_set_k1_mode(int v);
+void mg_set_six_mode(int v);
 extern "C" int mg_tune(const char *key, int value) {
     MG_REQUIRE(key != nullptr, "key is NULL");
     if (!strcmp(key, "emit")) { MG_REQUIRE(value >= 0 && value <= 2, "emit variant must be 0, 1 or 2"); g_emit_mode = value; return MG_OK; }
     if (!strcmp(key, "k1")) { mg_set_k1_mode(value); return MG_OK; }
+    if (!strcmp(key, "six")) { MG_REQUIRE(value >= 0 && value <= 2, "six-frame scan variant must be 0, 1 or 2"); mg_set_six_mode(value); return MG_OK; }
     if (!strcmp(key, "fuse")) { mg_set_fuse(value != 0); return MG_OK; }
     if (!strcmp(key, "multi_lag")) { MG_REQUIRE(value >= 0 && value <= 1000000, "multi_lag is in millionths of a text"); mg_set_multi_lag(value); return MG_OK; }
     mg_set_error("mg_tune: unknown key '%s'", key);

@@ -80,6 +80,8 @@ struct mg_sixframe_state {
     cudaStream_t stream = 0;
 };
 static thread_local bool g_six_force_single = false;
+static int g_six_mode = -1;                          // K4 scan variant (env MAGOT_SIX / mg_tune("six", v)): 0 single pass, 1 two-level on the packed bases, 2 two-level on the stop index (default)
+void mg_set_six_mode(int v) { g_six_mode = v; }
 
 // ---- per-stream geometry ------------------------------------------------------------------------------
 // stream index sidx = 2*frame + (plus ? 1 : 0): reference order is sidx ascending.
@@ -117,8 +119,10 @@ struct SixMasks {
 };
 
 // x0 = contig offset of the thread's first position (multiple of 48); gb = contig's global base index
-__device__ __forceinline__ void six_masks(const uint32_t *__restrict__ packed, int64_t gb, int64_t L, int64_t x0,
-                                          const int32_t *cs6, SixMasks &s) {
+// WHICH: 0 = both strands, 1 = plus only (s.mm undefined), 2 = minus only (s.pm undefined)
+template <int WHICH>
+__device__ __forceinline__ void six_masks_t(const uint32_t *__restrict__ packed, int64_t gb, int64_t L, int64_t x0,
+                                            const int32_t *cs6, SixMasks &s) {
     uint64_t v[4];
     const uint2 *p = reinterpret_cast<const uint2 *>(packed + ((gb + x0) >> 3));
 #pragma unroll
@@ -142,8 +146,8 @@ __device__ __forceinline__ void six_masks(const uint32_t *__restrict__ packed, i
         const uint64_t G1 = (G[g] >> 4) | (G[g + 1] << 60), G2 = (G[g] >> 8) | (G[g + 1] << 56);
         const uint64_t T1 = (T[g] >> 4) | (T[g + 1] << 60);
         const uint64_t C1 = (C[g] >> 4) | (C[g + 1] << 60);
-        s.pm[g] = T[g] & ((A1 & (A2 | G2)) | (G1 & A2));              // TAA TAG TGA
-        s.mm[g] = A2 & ((T1 & (T[g] | C[g])) | (C1 & T[g]));          // TTA CTA TCA = rc of the above
+        if (WHICH != 2) s.pm[g] = T[g] & ((A1 & (A2 | G2)) | (G1 & A2));              // TAA TAG TGA
+        if (WHICH != 1) s.mm[g] = A2 & ((T1 & (T[g] | C[g])) | (C1 & T[g]));          // TTA CTA TCA = rc of the above
     }
     // ---- validity at the contig ends
     const int64_t lim = L - 2 - x0;                  // positions t >= lim have no full codon
@@ -152,20 +156,25 @@ __device__ __forceinline__ void six_masks(const uint32_t *__restrict__ packed, i
         for (int g = 0; g < 3; g++) {
             const int64_t k = lim - 16 * g;
             const uint64_t keep = k <= 0 ? 0ull : (k >= 16 ? ~0ull : ((1ull << (4 * k)) - 1ull));
-            s.pm[g] &= keep;
-            s.mm[g] &= keep;
+            if (WHICH != 2) s.pm[g] &= keep;
+            if (WHICH != 1) s.mm[g] &= keep;
         }
     }
-    if (x0 == 0) {
+    if (WHICH != 2 && x0 == 0) {
         if (cs6[1] == 3) s.pm[0] &= ~1ull;           // frame 0 '+': trimmed first codon
         s.pm[0] &= ~(1ull << 4);                     // frame 2 '+' starts at offset 4: codon at 1 is not read
     }
     // minus strand: oriented start q0 = L-3-x; frame 0 trimmed drops q0 = 0, frame 2 never reads q0 = 1
-    {
+    if (WHICH != 1) {
         const int64_t t0 = L - 3 - x0, t1 = L - 4 - x0;
         if (cs6[0] == 3 && t0 >= 0 && t0 < 48) s.mm[t0 >> 4] &= ~(1ull << (4 * (t0 & 15)));
         if (t1 >= 0 && t1 < 48) s.mm[t1 >> 4] &= ~(1ull << (4 * (t1 & 15)));
     }
+}
+
+__device__ __forceinline__ void six_masks(const uint32_t *__restrict__ packed, int64_t gb, int64_t L, int64_t x0,
+                                          const int32_t *cs6, SixMasks &s) {
+    six_masks_t<0>(packed, gb, L, x0, cs6, s);
 }
 
 // residue (t % 3) selected by stream sidx: plus frame f -> rho_f, minus -> (L%3 - rho_f) % 3
@@ -730,7 +739,7 @@ __global__ void __launch_bounds__(SIX_THREADS, SIX_SCAN_MINB) k_six_scan(
 //   pass A (k_six_bits)  one thread per WINDOW of 96 bases (32 codons of each of the six streams): "does stream s hold a stop in
 //                        this window" -- six_masks + a residue mask, one ballot per stream; one bit per (stream, window) and the
 //                        last window with a stop per (tile, stream).  The genome is read once, nothing else is remembered.
-//   pass B (k_six_cand)  one thread per (tile, stream) walks the tile's 768 bits; a window with a stop that follows z stop-free
+//   pass B (k_six_cand)  one warp per (tile, stream) walks the tile's 768 bits; a window with a stop that follows z stop-free
 //                        windows can only close an ORF of < 32 (z + 2) codons, so exact stop positions are recomputed (six_masks
 //                        on the two windows involved) for the few candidates only, tested with the same arithmetic as
 //                        enumerate_stream and appended to the same hit list.  "Previous stop" needs no look-back chain: the
@@ -752,8 +761,13 @@ __device__ __forceinline__ void window_stream_stops(const uint32_t *__restrict__
         x[h] = 0;
         if (xh < ti.L) {
             SixMasks sm;
-            six_masks(packed, ti.gb, ti.L, xh, ti.cs, sm);
-            x[h] = pos48((s & 1) ? sm.pm : sm.mm) & rm;
+            if (s & 1) {                                   // one strand only: half the mask logic (s is uniform across the warp)
+                six_masks_t<1>(packed, ti.gb, ti.L, xh, ti.cs, sm);
+                x[h] = pos48(sm.pm) & rm;
+            } else {
+                six_masks_t<2>(packed, ti.gb, ti.L, xh, ti.cs, sm);
+                x[h] = pos48(sm.mm) & rm;
+            }
         }
     }
 }
@@ -771,21 +785,28 @@ __global__ void __launch_bounds__(256) k_six_bits(const uint32_t *__restrict__ p
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int wl = part * 256 + (int)threadIdx.x;          // window inside the tile
     const int64_t x0 = (ti.k * SIX_WPT + wl) * (int64_t)SIX_WIN;
-    uint64_t P[2] = {0, 0}, M[2] = {0, 0};
+    // "does residue class r of the plus / minus strand hold a stop in this window": tested on the nibble-spaced flags themselves
+    // (position 16 g + k of a half has residue (g + k) % 3: three masked ORs per class) -- compressing them to one bit per
+    // position first (pos48) was a quarter of this kernel's instructions
+    uint64_t hp[3] = {0, 0, 0}, hm[3] = {0, 0, 0};
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int64_t xh = x0 + SIX_HALF * h;
         if (xh < ti.L) {
             SixMasks sm;
             six_masks(packed, ti.gb, ti.L, xh, ti.cs, sm);
-            P[h] = pos48(sm.pm);
-            M[h] = pos48(sm.mm);
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                hp[r] |= (sm.pm[0] & res_mask(r)) | (sm.pm[1] & res_mask((r + 2) % 3)) | (sm.pm[2] & res_mask((r + 1) % 3));
+                hm[r] |= (sm.mm[0] & res_mask(r)) | (sm.mm[1] & res_mask((r + 2) % 3)) | (sm.mm[2] & res_mask((r + 1) % 3));
+            }
         }
     }
 #pragma unroll
     for (int s = 0; s < 6; s++) {
-        const uint64_t rm = 0x0000249249249249ull << stream_res(s, ti.Lm3);
-        const bool has = ti.m[s] > 0 && ((((s & 1) ? P[0] : M[0]) | ((s & 1) ? P[1] : M[1])) & rm) != 0;
+        const int r = stream_res(s, ti.Lm3);
+        const uint64_t v = (s & 1) ? (r == 0 ? hp[0] : (r == 1 ? hp[1] : hp[2])) : (r == 0 ? hm[0] : (r == 1 ? hm[1] : hm[2]));
+        const bool has = ti.m[s] > 0 && v != 0;
         const unsigned int b = __ballot_sync(0xffffffffu, has);
         if (lane == 0) {
             bits[(tile * 6 + s) * SIX_WORDS + part * 8 + wid] = b;
@@ -804,73 +825,260 @@ __device__ __forceinline__ int64_t six_span3(const TileInfo &ti, int s, int64_t 
     return (int64_t)(xl_real ? ql : 3 * m32) - (xh_real ? qh : -3) - 3;
 }
 
-__global__ void __launch_bounds__(128) k_six_cand(const uint32_t *__restrict__ packed, const int64_t *__restrict__ tile_base,
+// ---- stop-codon index ---------------------------------------------------------------------------------------------------
+// The stop flags of a base depend on the genome alone (codon at t on the plus strand: TAA TAG TGA; on the minus strand: the
+// reverse complements; the first-codon trims of the reference's frame quirk are per-contig constants), so they are computed ONCE
+// per packed genome -- like the reverse-complement plane -- into two dense bit planes, 2 bits per base (0.25 B/base next to the
+// 1 B/base of the two nibble planes).  The two-level scan then reads 0.25 B/base instead of 0.5 and spends ~1 instruction per 3
+// bases instead of ~8 per base on the codon logic (k_six_bits: 790 M warp instructions, 1.08 ms on config 5).  Built lazily by
+// the first ORF scan after mg_genome_finalize / mg_genome_mask (k_stop_index, one thread per 96-base window, six_masks as in the
+// scan kernels, so the validity rules at contig ends are the same code).
+__global__ void __launch_bounds__(256) k_stop_index(const uint32_t *__restrict__ packed, const int64_t *__restrict__ contig_len,
+                                                    const int64_t *__restrict__ contig_base, const int64_t *__restrict__ win_base, int64_t nc,
+                                                    const int32_t *__restrict__ cs, uint32_t *__restrict__ sp, uint32_t *__restrict__ sm_) {
+    const int64_t flat = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (flat >= win_base[nc]) return;
+    int64_t lo = 0, hi = nc;                          // largest c with win_base[c] <= flat
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (win_base[mid] <= flat) lo = mid; else hi = mid;
+    }
+    const int64_t w = flat - win_base[lo], L = contig_len[lo], gb = contig_base[lo];
+    int32_t cs6[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) cs6[k] = cs[lo * 6 + k];
+    uint64_t P[2] = {0, 0}, M[2] = {0, 0};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int64_t xh = w * SIX_WIN + SIX_HALF * h;
+        if (xh < L) {
+            SixMasks s;
+            six_masks(packed, gb, L, xh, cs6, s);
+            P[h] = pos48(s.pm);
+            M[h] = pos48(s.mm);
+        }
+    }
+    const int64_t base = (gb >> 5) + 3 * w;
+    const uint32_t pw[3] = {(uint32_t)P[0], (uint32_t)(P[0] >> 32) | (uint32_t)(P[1] << 16), (uint32_t)(P[1] >> 16)};
+    const uint32_t mw[3] = {(uint32_t)M[0], (uint32_t)(M[0] >> 32) | (uint32_t)(M[1] << 16), (uint32_t)(M[1] >> 16)};
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+        if (w * SIX_WIN + 32 * j < L) { sp[base + j] = pw[j]; sm_[base + j] = mw[j]; }   // the words beyond belong to the next contig
+}
+
+// stops of stream s in window w of the contig from the index: three words, bit k of word j = position 96 w + 32 j + k
+__device__ __forceinline__ void window_stops_ix(const uint32_t *__restrict__ stops, int64_t stop_words, const TileInfo &ti, int64_t w, int s,
+                                                uint32_t x[3]) {
+    const uint32_t *pl = stops + ((s & 1) ? 0 : stop_words) + (ti.gb >> 5) + 3 * w;
+    const int r = stream_res(s, ti.Lm3);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {                     // position 32 j + k of the window has residue (2 j + k) % 3
+        const uint32_t rm = 0x49249249u << ((r + j) % 3);
+        x[j] = w * SIX_WIN + 32 * j < ti.L ? __ldg(pl + j) & rm : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_six_bits_ix(const uint32_t *__restrict__ stops, int64_t stop_words, const int64_t *__restrict__ tile_base,
+                                                     const int32_t *__restrict__ cid, const int64_t *__restrict__ contig_len,
+                                                     const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
+                                                     const int64_t *__restrict__ m, const int32_t *__restrict__ tile_contig,
+                                                     uint32_t *__restrict__ bits, int32_t *__restrict__ last_set) {
+    // one block per tile, three windows per thread (their loads are independent): the per-block prologue (tile -> contig ->
+    // geometry, three dependent loads) is paid once per 768 windows
+    __shared__ TileInfo ti;
+    __shared__ int s_last[6];
+    const int64_t tile = blockIdx.x;
+    if (threadIdx.x == 0) tile_info_at(tile, tile_contig[tile], tile_base, cid, contig_len, contig_base, cs, m, ti);
+    if (threadIdx.x < 6) s_last[threadIdx.x] = -1;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t p[3][3], q[3][3];
+#pragma unroll
+    for (int part = 0; part < 3; part++) {
+        const int64_t w = ti.k * SIX_WPT + part * 256 + (int)threadIdx.x;      // window of the contig
+        const int64_t base = (ti.gb >> 5) + 3 * w;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const bool in = w * SIX_WIN + 32 * j < ti.L;
+            p[part][j] = in ? __ldg(stops + base + j) : 0u;
+            q[part][j] = in ? __ldg(stops + stop_words + base + j) : 0u;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        const int r = stream_res(s, ti.Lm3);
+        const uint32_t r0 = 0x49249249u << r, r1 = 0x49249249u << ((r + 1) % 3), r2 = 0x49249249u << ((r + 2) % 3);
+        int last = -1;
+#pragma unroll
+        for (int part = 0; part < 3; part++) {
+            const uint32_t v = (s & 1) ? ((p[part][0] & r0) | (p[part][1] & r1) | (p[part][2] & r2))
+                                       : ((q[part][0] & r0) | (q[part][1] & r1) | (q[part][2] & r2));
+            const unsigned int b = __ballot_sync(0xffffffffu, ti.m[s] > 0 && v != 0);
+            if (lane == 0) bits[(tile * 6 + s) * SIX_WORDS + part * 8 + wid] = b;
+            if (b) last = part * 256 + wid * 32 + 31 - __clz(b);
+        }
+        if (lane == 0 && last >= 0) atomicMax(&s_last[s], last);
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) last_set[tile * 6 + threadIdx.x] = s_last[threadIdx.x];
+}
+
+// One WARP per (tile, stream).  Lane j holds word j of the row's bitmap (SIX_WORDS = 24 of the 32 lanes).  A window is a
+// candidate only if the two windows in front of it are stop-free (one AND of shifted words; min_aa >= SIX_WIN_MIN_AA = 96 needs
+// at least two) and 32 (z + 2) > min_aa for its z stop-free predecessors: ~4 % of the windows at min_aa = 100, ~28 per row, but
+// 0 to 5 per word.  So the lanes first LIST the row's candidates in shared memory (window, previous window with a stop), in
+// ascending order through a warp scan of their counts, and then take them 32 at a time: the exact stop positions (the
+// expensive part: the genome bases of two windows) are computed by all lanes at once whatever word a candidate came from.  The
+// list order is the window order, so the rank of a kept ORF inside the row is a running count + a ballot prefix.
+#define CAND_WARPS 8
+#define CAND_LIST (SIX_WPT / 3 + 2)                  // a candidate needs two stop-free windows in front of it
+template <bool IX>                                   // IX: exact stop positions from the stop-codon index instead of the packed bases
+__global__ void __launch_bounds__(32 * CAND_WARPS) k_six_cand(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ stops,
+                                                  int64_t stop_words, const int64_t *__restrict__ tile_base,
                                                   const int32_t *__restrict__ cid, const int64_t *__restrict__ contig_len,
                                                   const int64_t *__restrict__ contig_base, const int32_t *__restrict__ cs,
                                                   const int64_t *__restrict__ m, const int32_t *__restrict__ tile_contig, int64_t n_tiles,
                                                   const uint32_t *__restrict__ bits, const int32_t *__restrict__ last_set, int64_t min_aa,
                                                   int32_t *__restrict__ cnt, SixHit *__restrict__ hits, int64_t hit_cap,
                                                   unsigned long long *hit_count) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n_tiles * 6) return;
-    const int64_t tile = i / 6;
+    // per warp: the row's candidates (window, previous window with a stop), overwritten in place by the bounding stops (xl, xh)
+    __shared__ int32_t s_w[CAND_WARPS][CAND_LIST], s_pw[CAND_WARPS][CAND_LIST];
+    __shared__ uint8_t s_f[CAND_WARPS][CAND_LIST];          // bit 0 xl_real, bit 1 xh_real, bit 2 kept
+    __shared__ int s_tot[CAND_WARPS];
+    __shared__ unsigned long long s_slot;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t i = blockIdx.x * (int64_t)CAND_WARPS + wid;
+    const bool row = i < n_tiles * 6;                      // whole warp
+    const int64_t tile = row ? i / 6 : 0;
     const int s = (int)(i % 6);
     TileInfo ti;
     tile_info_at(tile, tile_contig[tile], tile_base, cid, contig_len, contig_base, cs, m, ti);
     const int64_t li = layout_index(ti, tile_base, s);
-    if (ti.m[s] <= 0) { cnt[li] = 0; return; }           // `if translated_seq:` (genome.py:832)
+    const bool live = row && ti.m[s] > 0;                  // `if translated_seq:` (genome.py:832)
     const int64_t need3 = 3 * min_aa;
-    // last window with a stop before this tile (same contig, same stream): backwards over the per-tile summaries
-    int64_t prev_w = -1;
-    for (int64_t tt = tile - 1; tt >= tile - ti.k; tt--) {
-        const int32_t ls = last_set[tt * 6 + s];
-        if (ls >= 0) { prev_w = (tt - (tile - ti.k)) * SIX_WPT + ls; break; }
-    }
-    int k = 0;
-    auto keep = [&](int64_t xl, bool xl_real, int64_t xh, bool xh_real) {
-        if (six_span3(ti, s, xl, xl_real, xh, xh_real) < need3) return;
-        const unsigned long long slot = atomicAdd(hit_count, 1ull);
-        if ((int64_t)slot < hit_cap) {
-            SixHit h;
-            h.tile = (int32_t)tile; h.rank = k; h.xl = (int32_t)xl; h.xh = (int32_t)xh;
-            h.s = (uint8_t)s; h.xl_real = xl_real; h.xh_real = xh_real; h.pad = 0;
-            hits[slot] = h;
-        }
-        k++;
-    };
-    auto last_stop_in = [&](int64_t w) -> int64_t {        // exact position of the last stop of the stream in window w (it has one)
-        uint64_t x[2];
-        window_stream_stops(packed, ti, w, s, x);
-        return w * SIX_WIN + (x[1] ? SIX_HALF + 63 - __clzll((long long)x[1]) : 63 - __clzll((long long)x[0]));
-    };
-    const uint32_t *row = bits + (tile * 6 + s) * SIX_WORDS;
-    const int64_t w0 = ti.k * SIX_WPT;
-#pragma unroll 1
-    for (int j = 0; j < SIX_WORDS; j++) {
-        uint32_t b = __ldg(row + j);
-        while (b) {
-            const int64_t w = w0 + j * 32 + __ffs(b) - 1;
-            b &= b - 1;
-            const int64_t z = w - prev_w - 1;              // stop-free windows in front of this one
-            if (32 * (z + 2) > min_aa) {                   // else the ORF this window closes has < 32 (z + 2) - 1 residues
-                uint64_t x[2];
-                window_stream_stops(packed, ti, w, s, x);
-                const int64_t xh = w * SIX_WIN + (x[0] ? __ffsll((long long)x[0]) - 1 : SIX_HALF + __ffsll((long long)x[1]) - 1);
-                const int64_t xl = prev_w >= 0 ? last_stop_in(prev_w) : -1;
-                keep(xl, prev_w >= 0, xh, true);
+    int C = 0, total = 0;
+    if (live) {
+        // last window with a stop before this tile (same contig, same stream): 32 tile summaries per step, backwards
+        int64_t prev_tile_w = -1;
+        for (int64_t t0 = tile - 1; t0 >= tile - ti.k; t0 -= 32) {
+            const int64_t tt = t0 - lane;
+            const int32_t ls = tt >= tile - ti.k ? last_set[tt * 6 + s] : -1;
+            const unsigned int has = __ballot_sync(0xffffffffu, ls >= 0);
+            if (has) {
+                const int src = __ffs(has) - 1;
+                const int32_t lsv = __shfl_sync(0xffffffffu, ls, src);
+                prev_tile_w = (t0 - src - (tile - ti.k)) * SIX_WPT + lsv;
+                break;
             }
-            prev_w = w;
+        }
+        const int64_t w0 = ti.k * SIX_WPT + lane * 32;      // contig-level index of the first window of this lane's word
+        const uint32_t b = lane < SIX_WORDS ? __ldg(bits + (tile * 6 + s) * SIX_WORDS + lane) : 0u;
+        // last window with a stop before this lane's word: exclusive prefix max over the lanes, then the earlier tiles
+        int64_t incl = b ? w0 + 31 - __clz(b) : -1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d && t > incl) incl = t;
+        }
+        int64_t prev_before = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0 || prev_before < prev_tile_w) prev_before = prev_tile_w;
+        // windows with a stop whose two predecessors are stop-free (the window in front of the contig counts as a stop, like prev = -1)
+        uint32_t pword = __shfl_up_sync(0xffffffffu, b, 1);
+        if (lane == 0) pword = prev_before == w0 - 1 ? 0x80000000u : (prev_before == w0 - 2 ? 0x40000000u : 0u);
+        const uint64_t ext = ((uint64_t)b << 32) | pword;
+        const uint32_t cand = b & ~(uint32_t)((ext << 1) >> 32) & ~(uint32_t)((ext << 2) >> 32);
+        // exact test on z, then the list
+        uint32_t keepm = 0;
+        for (uint32_t c = cand; c; c &= c - 1) {
+            const int k = __ffs(c) - 1;
+            const uint32_t below = b & ((1u << k) - 1u);
+            const int64_t pw = below ? w0 + 31 - __clz(below) : prev_before;
+            if (32 * (w0 + k - pw - 1 + 2) > min_aa) keepm |= 1u << k;    // else the ORF this window closes has < 32 (z + 2) - 1 residues
+        }
+        const bool tail = lane == 31 && ti.k == ti.Tc - 1 &&      // the virtual stop at the contig's high end belongs to the last tile
+                          32 * ((ti.L + SIX_WIN - 1) / SIX_WIN - prev_before - 1 + 2) > min_aa;
+        int off = __popc(keepm) + (tail ? 1 : 0);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, off, d);
+            if (lane >= d) off += t;
+        }
+        C = __shfl_sync(0xffffffffu, off, 31);
+        off -= __popc(keepm) + (tail ? 1 : 0);
+        for (uint32_t c = keepm; c; c &= c - 1) {
+            const int k = __ffs(c) - 1;
+            const uint32_t below = b & ((1u << k) - 1u);
+            s_w[wid][off] = (int32_t)(w0 + k);
+            s_pw[wid][off] = (int32_t)(below ? w0 + 31 - __clz(below) : prev_before);
+            off++;
+        }
+        if (tail) { s_w[wid][off] = -1; s_pw[wid][off] = (int32_t)prev_before; }
+        __syncwarp();
+        for (int r0 = 0; r0 < C; r0 += 32) {
+            const int idx = r0 + lane;
+            bool pass = false;
+            if (idx < C) {
+                const int64_t w = s_w[wid][idx], pw = s_pw[wid][idx];
+                const bool xl_real = pw >= 0, xh_real = w >= 0;
+                int64_t xl = -1, xh = 0;
+                if (IX) {
+                    uint32_t y[3];
+                    if (xh_real) {
+                        window_stops_ix(stops, stop_words, ti, w, s, y);
+                        xh = w * SIX_WIN + (y[0] ? __ffs(y[0]) - 1 : (y[1] ? 32 + __ffs(y[1]) - 1 : 64 + __ffs(y[2]) - 1));
+                    }
+                    if (xl_real) {                         // exact position of the last stop of the stream in window pw (it has one)
+                        window_stops_ix(stops, stop_words, ti, pw, s, y);
+                        xl = pw * SIX_WIN + (y[2] ? 64 + 31 - __clz(y[2]) : (y[1] ? 32 + 31 - __clz(y[1]) : 31 - __clz(y[0])));
+                    }
+                } else {
+                    uint64_t x[2];
+                    if (xh_real) {
+                        window_stream_stops(packed, ti, w, s, x);
+                        xh = w * SIX_WIN + (x[0] ? __ffsll((long long)x[0]) - 1 : SIX_HALF + __ffsll((long long)x[1]) - 1);
+                    }
+                    if (xl_real) {
+                        window_stream_stops(packed, ti, pw, s, x);
+                        xl = pw * SIX_WIN + (x[1] ? SIX_HALF + 63 - __clzll((long long)x[1]) : 63 - __clzll((long long)x[0]));
+                    }
+                }
+                pass = six_span3(ti, s, xl, xl_real, xh, xh_real) >= need3;
+                s_w[wid][idx] = (int32_t)xl;
+                s_pw[wid][idx] = (int32_t)xh;
+                s_f[wid][idx] = (uint8_t)((xl_real ? 1 : 0) | (xh_real ? 2 : 0) | (pass ? 4 : 0));
+            }
+            total += __popc(__ballot_sync(0xffffffffu, pass));
         }
     }
-    if (ti.k == ti.Tc - 1) {                               // the virtual stop at the contig's high end belongs to the last tile
-        const int64_t Lw = (ti.L + SIX_WIN - 1) / SIX_WIN;
-        const int64_t z = Lw - prev_w - 1;
-        if (32 * (z + 2) > min_aa) {
-            const int64_t xl = prev_w >= 0 ? last_stop_in(prev_w) : -1;
-            keep(xl, prev_w >= 0, 0, false);
-        }
+    // one slot allocation per block (a quarter of a million same-address atomics, one per row, were as long as the rest of the kernel)
+    if (lane == 0) s_tot[wid] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < CAND_WARPS; k++) sum += s_tot[k];
+        s_slot = sum ? atomicAdd(hit_count, (unsigned long long)sum) : 0ull;
     }
-    cnt[li] = k;
+    __syncthreads();
+    if (!row) return;
+    if (!live) { if (lane == 0) cnt[li] = 0; return; }
+    unsigned long long slot = s_slot;
+    for (int k = 0; k < wid; k++) slot += s_tot[k];
+    int rank = 0;
+    for (int r0 = 0; r0 < C; r0 += 32) {
+        const int idx = r0 + lane;
+        const uint32_t f = idx < C ? s_f[wid][idx] : 0u;
+        const unsigned int bal = __ballot_sync(0xffffffffu, (f & 4u) != 0);
+        const int my = rank + __popc(bal & ((1u << lane) - 1u));
+        if ((f & 4u) && (int64_t)(slot + my) < hit_cap) {
+            SixHit h;
+            h.tile = (int32_t)tile; h.rank = my; h.xl = s_w[wid][idx]; h.xh = s_pw[wid][idx];
+            h.s = (uint8_t)s; h.xl_real = f & 1u; h.xh_real = (f >> 1) & 1u; h.pad = 0;
+            hits[slot + my] = h;
+        }
+        rank += __popc(bal);
+    }
+    if (lane == 0) cnt[li] = total;
 }
 
 // thread per hit: reference-order slot of the ORF and its record
@@ -1050,6 +1258,40 @@ static int six_alloc(mg_sixframe_state *s, T **p, int64_t n) {
 }
 
 // contigs given as a LIST (any order, e.g. the LPT share of one GPU): ORFs come out contig by contig in list order
+// stop-codon index of the whole genome (see k_stop_index); st-ordered, no host wait
+static int six_build_stops(mg_genome *g, cudaStream_t st) {
+    if (g->stops_valid) return MG_OK;
+    const int64_t W = g->total_bases / 32 + 8, nc = g->n_contigs;
+    if (!g->d_stops || g->stop_words != W) {
+        if (g->d_stops) { MG_CUDA(cudaFree(g->d_stops)); g->device_bytes -= 2 * g->stop_words * 4; }
+        g->d_stops = nullptr;
+        MG_CUDA(cudaMalloc((void **)&g->d_stops, 2 * W * sizeof(uint32_t)));
+        g->stop_words = W;
+        g->device_bytes += 2 * W * 4;
+    }
+    MG_CUDA(cudaMemsetAsync(g->d_stops, 0, 2 * W * sizeof(uint32_t), st));
+    std::vector<int64_t> wb(nc + 1, 0);
+    std::vector<int32_t> ident(nc);
+    for (int64_t c = 0; c < nc; c++) { wb[c + 1] = wb[c] + (g->h_contig_len[c] + SIX_WIN - 1) / SIX_WIN; ident[c] = (int32_t)c; }
+    if (wb[nc] == 0) { g->stops_valid = true; return MG_OK; }
+    char *tmp = nullptr;                                     // win_base | cs | m | ident
+    const size_t o_cs = (nc + 1) * 8, o_m = o_cs + nc * 6 * 4 + 8, o_id = o_m + nc * 6 * 8, bytes = o_id + nc * 4;
+    MG_CUDA(cudaMallocAsync((void **)&tmp, bytes, st));
+    int64_t *d_wb = (int64_t *)tmp, *d_m = (int64_t *)(tmp + (o_m & ~(size_t)7));
+    int32_t *d_cs = (int32_t *)(tmp + o_cs), *d_id = (int32_t *)(tmp + o_id);
+    MG_CUDA(cudaMemcpyAsync(d_wb, wb.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, st));
+    MG_CUDA(cudaMemcpyAsync(d_id, ident.data(), nc * 4, cudaMemcpyHostToDevice, st));
+    k_six_streams<<<(unsigned)((nc * 6 + 127) / 128), 128, 0, st>>>(g->d_packed, g->d_contig_len, g->d_contig_base, d_id, nc, d_cs, d_m);
+    MG_LAUNCH_CHECK();
+    k_stop_index<<<(unsigned)((wb[nc] + 255) / 256), 256, 0, st>>>(g->d_packed, g->d_contig_len, g->d_contig_base, d_wb, nc, d_cs, g->d_stops,
+                                                                   g->d_stops + W);
+    MG_LAUNCH_CHECK();
+    MG_CUDA(cudaStreamSynchronize(st));                      // wb / ident are host vectors of this frame
+    MG_CUDA(cudaFreeAsync(tmp, st));
+    g->stops_valid = true;
+    return MG_OK;
+}
+
 extern "C" int mg_sixframe_count_list(mg_genome *g, int64_t n_list, const int64_t *contig_ids, int64_t min_aa, int64_t *n_orf,
                                       int64_t *n_bytes, void *stream) {
     MG_REQUIRE(g != nullptr, "genome handle is NULL");
@@ -1104,8 +1346,10 @@ extern "C" int mg_sixframe_count_list(mg_genome *g, int64_t n_list, const int64_
     TRY(six_alloc(s, &s->d_tile_contig, s->n_tiles));
     k_six_tile_contig<<<(unsigned)((s->n_tiles + 255) / 256), 256, 0, st>>>(s->d_tile_base, nc, s->n_tiles, s->d_tile_contig);
     MG_LAUNCH_CHECK();
-    static int two_level = -1;                        // env MAGOT_SIX=two selects the two-level scan (A/B; the single pass is faster so far)
-    if (two_level < 0) { const char *e = getenv("MAGOT_SIX"); two_level = (e && !strcmp(e, "two")) ? 1 : 0; }
+    // min_aa >= 96: two-level scan over the stop-codon index (MAGOT_SIX=single forces the single pass over the packed bases,
+    // MAGOT_SIX=bases the two-level scan with the codon logic on the packed bases; A/B knobs)
+    if (g_six_mode < 0) { const char *e = getenv("MAGOT_SIX"); g_six_mode = (e && !strcmp(e, "single")) ? 0 : ((e && !strcmp(e, "bases")) ? 1 : 2); }
+    const int two_level = g_six_mode;
     const bool use_two_level = two_level && min_aa >= SIX_WIN_MIN_AA && !s->force_single;
     if (use_two_level) {
         uint32_t *d_bits = nullptr;
@@ -1113,13 +1357,25 @@ extern "C" int mg_sixframe_count_list(mg_genome *g, int64_t n_list, const int64_
         TRY(six_alloc(s, &d_bits, s->n_tiles * 6 * SIX_WORDS));
         TRY(six_alloc(s, &d_last, s->n_tiles * 6));
         MG_CUDA(cudaMemsetAsync(d_last, 0xFF, s->n_tiles * 6 * sizeof(int32_t), st));
-        k_six_bits<<<(unsigned)(s->n_tiles * 3), 256, 0, st>>>(g->d_packed, s->d_tile_base, s->d_cid, g->d_contig_len, g->d_contig_base, s->d_cs,
-                                                              s->d_m, s->d_tile_contig, d_bits, d_last);
-        MG_LAUNCH_CHECK();
-        k_six_cand<<<(unsigned)((s->n_tiles * 6 + 127) / 128), 128, 0, st>>>(g->d_packed, s->d_tile_base, s->d_cid, g->d_contig_len,
-                                                                             g->d_contig_base, s->d_cs, s->d_m, s->d_tile_contig, s->n_tiles, d_bits,
-                                                                             d_last, min_aa, s->d_cnt, s->d_hits, s->hit_cap, s->d_hit_count);
-        MG_LAUNCH_CHECK();
+        const unsigned cand_grid = (unsigned)((s->n_tiles * 6 + CAND_WARPS - 1) / CAND_WARPS);
+        if (two_level == 2) {
+            TRY(six_build_stops(g, st));
+            k_six_bits_ix<<<(unsigned)s->n_tiles, 256, 0, st>>>(g->d_stops, g->stop_words, s->d_tile_base, s->d_cid, g->d_contig_len,
+                                                                     g->d_contig_base, s->d_cs, s->d_m, s->d_tile_contig, d_bits, d_last);
+            MG_LAUNCH_CHECK();
+            k_six_cand<true><<<cand_grid, 32 * CAND_WARPS, 0, st>>>(g->d_packed, g->d_stops, g->stop_words, s->d_tile_base, s->d_cid, g->d_contig_len,
+                                                                     g->d_contig_base, s->d_cs, s->d_m, s->d_tile_contig, s->n_tiles, d_bits,
+                                                                     d_last, min_aa, s->d_cnt, s->d_hits, s->hit_cap, s->d_hit_count);
+            MG_LAUNCH_CHECK();
+        } else {
+            k_six_bits<<<(unsigned)(s->n_tiles * 3), 256, 0, st>>>(g->d_packed, s->d_tile_base, s->d_cid, g->d_contig_len, g->d_contig_base, s->d_cs,
+                                                                  s->d_m, s->d_tile_contig, d_bits, d_last);
+            MG_LAUNCH_CHECK();
+            k_six_cand<false><<<cand_grid, 32 * CAND_WARPS, 0, st>>>(g->d_packed, nullptr, 0, s->d_tile_base, s->d_cid, g->d_contig_len,
+                                                                      g->d_contig_base, s->d_cs, s->d_m, s->d_tile_contig, s->n_tiles, d_bits,
+                                                                      d_last, min_aa, s->d_cnt, s->d_hits, s->hit_cap, s->d_hit_count);
+            MG_LAUNCH_CHECK();
+        }
     } else {
         k_six_scan<<<(unsigned)s->n_tiles, SIX_THREADS, 0, st>>>(g->d_packed, s->d_tile_base, nc, s->d_cid, g->d_contig_len, g->d_contig_base,
                                                                   s->d_cs, s->d_m, s->d_tile_contig, s->n_tiles, s->d_look, s->d_carry, min_aa, 2 * g->total_bases,

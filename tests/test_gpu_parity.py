@@ -494,12 +494,20 @@ def test_edge_records(mg):
 # ---- K4: six-frame translation + ORF scan -------------------------------------------------------------------------
 
 def _sixframe_case(mg, contigs, min_aa):
-    from magot_b200 import engine, orfs
+    from magot_b200 import engine, orfs, _lib
     g = engine.DeviceGenome([len(c) for c in contigs], device=0)
     for i, c in enumerate(contigs):
         g.pack(i, np.frombuffer(c, dtype=np.uint8))
     g.finalize()
     recs, aa = orfs.sixframe(g, 0, len(contigs), min_aa)
+    if min_aa >= 96:                                     # the three scan variants (stop index / packed bases / single pass) agree
+        for mode in (1, 0):
+            _lib.check(_lib.lib.mg_tune(b"six", mode))
+            try:
+                recs2, aa2 = orfs.sixframe(g, 0, len(contigs), min_aa)
+            finally:
+                _lib.check(_lib.lib.mg_tune(b"six", 2))
+            assert aa2 == aa and np.array_equal(recs2, recs), mode
     g.close()
     want_aa, want_rec = [], []
     off = 0
