@@ -7,6 +7,9 @@
 #ifndef NUC_LD64
 #define NUC_LD64 1
 #endif
+#ifndef NUC_LD128
+#define NUC_LD128 1                 // measured on config 4: CDS launch 0.1053 -> 0.1037 ms, exon launch 0.1514 -> 0.1505 ms against three 8-byte loads
+#endif
 #ifndef FRAME_LANES4
 #define FRAME_LANES4 1
 #endif
@@ -56,9 +59,24 @@ __device__ __forceinline__ uint32_t ld_pk(const uint32_t *p) {
 // five consecutive packed words starting at the (4-byte aligned) word p, fetched as three 8-byte loads from the enclosing
 // 8-byte aligned window and selected by the odd/even word address: 3 instead of 5 load instructions and 48 instead of 80 L1
 // sectors per warp (the lanes of a warp read 16-byte strided windows, so every load instruction touches all 16 sectors
-// of the 512-byte span whatever its width).  Reads at most 4 bytes past p + 20: inside the tail slack of the buffer.
+// of the 512-byte span whatever its width).  Reads at most 12 bytes before p and 12 bytes past p + 20: inside the front
+// padding and the tail slack of the buffer.
 __device__ __forceinline__ void ld_pk5(const uint32_t *p, uint32_t r[5]) {
-#if NUC_LD64
+#if NUC_LD128
+    // two 16-byte loads from the enclosing 16-byte aligned window + a two-level select on the word offset: 2 instead of 3 load
+    // instructions per window (each one touches every 128-byte line the warp's windows lie in, whatever its width)
+    const uint64_t a = (uint64_t)p;
+    const uint64_t a16 = a & ~15ull;
+    uint32_t v[8];
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(a16));
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(a16 + 16));
+    const bool two = (a & 8ull) != 0, one = (a & 4ull) != 0;
+    uint32_t t[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) t[k] = two ? v[k + 2] : v[k];
+#pragma unroll
+    for (int k = 0; k < 5; k++) r[k] = one ? t[k + 1] : t[k];
+#elif NUC_LD64
     const uint64_t a = (uint64_t)p;
     const uint64_t a8 = a & ~7ull;
     uint32_t v[6];

@@ -1155,6 +1155,35 @@ __global__ void __launch_bounds__(AA_THREADS) k_six_aa(const uint32_t *__restric
                 if (s_off[mid] <= P) lo = mid; else hi = mid;
             }
             uint32_t bw[4] = {0, 0, 0, 0};
+            const int64_t left = s_off[lo + 1] - P;   // residues of ORF lo from P on
+            if (left >= 16 || s_off[lo + 2] >= P + 16) {
+                // One or two ORFs in the chunk (always, for min_aa >= 16): their nibbles are merged BEFORE the look-ups, as K2 merges
+                // two pieces -- the second ORF's window is fetched at an index chosen so that its first base lands on window nibble
+                // 3c -- so no lane takes a second trip (the per-ORF loop below ran at 15 of 32 lanes: 72 % of the warps hold a
+                // chunk with an ORF boundary) and the 16 look-ups are done once.
+                const int c = left >= 16 ? 16 : (int)left;
+                const int64_t g0 = s_src[lo] + 3 * (P - s_off[lo]);
+                const int64_t g1 = (c < 16 ? s_src[lo + 1] : g0 + 48) - 3 * c;
+                const uint32_t *pa = packed + (g0 >> 3), *pb = packed + (g1 >> 3);
+                const uint32_t sha = ((uint32_t)g0 & 7u) << 2, shb = ((uint32_t)g1 & 7u) << 2;
+                uint32_t va[7], vb[7], n[6];
+#pragma unroll
+                for (int k = 0; k < 7; k++) { va[k] = __ldg(pa + k); vb[k] = __ldg(pb + k); }
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    const int t = 3 * c - 8 * k;                                   // window nibbles < 3c come from the first ORF
+                    const uint32_t m = __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)(4 * max(t, 0)));
+                    n[k] = (__funnelshift_r(va[k], va[k + 1], sha) & m) | (__funnelshift_r(vb[k], vb[k + 1], shb) & ~m);
+                }
+#pragma unroll
+                for (int k = 0; k < 16; k++) {            // codon k = nibbles 3k..3k+2 = bits 12k.. of n[5]:..:n[0]
+                    const int bit = 12 * k, ww = bit >> 5, sh = bit & 31;
+                    uint32_t idx = n[ww] >> sh;
+                    if (sh > 20) idx |= n[ww + 1] << (32 - sh);
+                    bw[k >> 2] |= (uint32_t)s_aa[idx & 0xFFFu] << ((k & 3) * 8);
+                }
+                filled = 16;
+            }
             while (filled < 16 && pos < total) {
                 while (s_off[lo + 1] <= pos) lo++;
                 const int64_t a = pos - s_off[lo];
