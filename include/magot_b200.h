@@ -115,6 +115,9 @@ int mg_plan_destroy(mg_plan *p);
 /* flags for mg_plan_prepare / emit */
 #define MG_PROT_TRIMX      1      /* Sequence.translate(trimX=True): drop ONE leading 'X' (genome.py:819-821) */
 #define MG_PROT_USE_PHASE  2      /* non-reference extension: start at the GFF phase of the first segment     */
+#define MG_PROT_DEFER      4      /* mg_plan_prepare_async only: leave out the record pass (amino-acid counts, protein offsets);
+                                     mg_plan_prepare_prot_async runs it later -- on another stream next to K2, or never when only
+                                     the nucleotide text is wanted (e.g. the exon-based transcripts of gff2fasta)          */
 
 /* Clamp, measure and scan (warp/block prefix sums on the device).  Outputs (host, may be NULL):
  * total bytes of the nucleotide text and of the protein text (literals included).
@@ -126,6 +129,7 @@ int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, int64_t *pro
  * graph): the tile counts are derived on the device and surplus CTAs exit.  mg_plan_totals waits for the stream and
  * returns the real sizes; it fails if they exceeded the capacities (the texts are then truncated).             */
 int mg_plan_prepare_async(mg_plan *p, int prot_flags, int64_t nuc_capacity, int64_t prot_capacity, void *stream);
+int mg_plan_prepare_prot_async(mg_plan *p, void *stream);   /* the record pass left out by MG_PROT_DEFER; after the piece pass in stream order */
 int mg_plan_totals(mg_plan *p, int64_t *nuc_total, int64_t *prot_total, void *stream);
 /* Per-record payload lengths to the host (for `longest=True`, genome.py:720-724).
  * nuc_len[r] = spliced bases; aa_len[r] = amino acids, or -1 where the reference's translate

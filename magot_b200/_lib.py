@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("MAGOT_B200_LIB") or os.path.join(_HERE, "libmagot_b20
 
 MG_PROT_TRIMX = 1
 MG_PROT_USE_PHASE = 2
+MG_PROT_DEFER = 4
 
 
 class MagotError(RuntimeError):
@@ -59,6 +60,7 @@ SIGNATURES = {
     "mg_genome_mask": (_i32, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp]),
     "mg_plan_prepare": (_i32, [_vp, _i32, _pi64, _pi64, _vp]),
     "mg_plan_prepare_async": (_i32, [_vp, _i32, _i64, _i64, _vp]),
+    "mg_plan_prepare_prot_async": (_i32, [_vp, _vp]),
     "mg_plan_totals": (_i32, [_vp, _pi64, _pi64, _vp]),
     "mg_plan_lengths": (_i32, [_vp, _vp, _vp, _vp]),
     "mg_emit_nuc_device": (_i32, [_vp, _vp, _vp]),

@@ -836,6 +836,7 @@ extern "C" int mg_emit_nuc_device(mg_plan *p, uint8_t *out_dev, void *stream) {
 extern "C" int mg_emit_prot_device(mg_plan *p, uint8_t *out_dev, void *stream) {
     MG_REQUIRE(p != nullptr, "plan handle is NULL");
     if (!p->prepared) { mg_set_error("mg_plan_prepare has not been called"); return MG_ESTATE; }
+    if (!p->prot_ready) { mg_set_error("the record pass was deferred (MG_PROT_DEFER): call mg_plan_prepare_prot_async first"); return MG_ESTATE; }
     if (p->prot_total == 0) return MG_OK;
     MG_REQUIRE(out_dev != nullptr && ((uintptr_t)out_dev & 15) == 0, "out_dev must be a 16-byte aligned device pointer");
     MG_CUDA(cudaSetDevice(p->device));
@@ -853,6 +854,7 @@ void mg_set_fuse(int v) { g_fuse = v; }
 extern "C" int mg_emit_nuc_prot_device(mg_plan *p, uint8_t *nuc_out_dev, uint8_t *prot_out_dev, void *stream) {
     MG_REQUIRE(p != nullptr, "plan handle is NULL");
     if (!p->prepared) { mg_set_error("mg_plan_prepare has not been called"); return MG_ESTATE; }
+    if (!p->prot_ready) { mg_set_error("the record pass was deferred (MG_PROT_DEFER): call mg_plan_prepare_prot_async first"); return MG_ESTATE; }
     if (p->nuc_total == 0) return mg_emit_prot_device(p, prot_out_dev, stream);       // no nucleotide tile: framing-only protein text
     if (p->prot_total == 0) return mg_emit_nuc_device(p, nuc_out_dev, stream);
     if (!g_fuse || mg_emit_mode() != 0) {
@@ -943,6 +945,7 @@ __global__ void __launch_bounds__(NUC_THREADS, NUC_MINB) k_emit_multi(const __gr
 // prepared (mg_plan_prepare or mg_plan_prepare_async, the latter on this stream or joined with it) and belong to one genome.
 extern "C" int mg_emit_products_device(mg_plan *pa, uint8_t *out_a, mg_plan *pb, uint8_t *out_b_nuc, uint8_t *out_b_prot, void *stream) {
     const bool ja = pa && out_a && pa->nuc_total > 0, jb = pb && out_b_nuc && pb->nuc_total > 0, jc = pb && out_b_prot && pb->prot_total > 0;
+    if (jc && !pb->prot_ready) { mg_set_error("the record pass was deferred (MG_PROT_DEFER): call mg_plan_prepare_prot_async first"); return MG_ESTATE; }
     MG_REQUIRE(!out_a || pa, "out_a given without a plan");
     MG_REQUIRE((!out_b_nuc && !out_b_prot) || pb, "out_b given without a plan");
     if (pa && out_a && !pa->prepared) { mg_set_error("mg_plan_prepare has not been called"); return MG_ESTATE; }

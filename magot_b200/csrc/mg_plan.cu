@@ -531,11 +531,13 @@ extern "C" int mg_plan_destroy(mg_plan *p) {
 static int plan_alloc_tiles(mg_plan *p, int64_t cap_nuc, int64_t cap_prot, cudaStream_t st);
 
 // scatter_tiles: the tile tables are sized for the caller's capacities and filled by the plan kernels themselves
+static int plan_launch_records(mg_plan *p, cudaStream_t st);
 static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st, bool scatter_tiles = false, int64_t cap_nuc = 0,
                              int64_t cap_prot = 0) {
     mg_genome *g = p->g;
     p->prot_flags = prot_flags;
     p->last_stream = st;
+    p->prot_ready = false;
     const int64_t n_block = (p->n_piece + PLAN_TILE - 1) / PLAN_TILE, n_rblock = (p->n_rec + 255) / 256;
     unsigned long long *tmp_a = reinterpret_cast<unsigned long long *>(p->d_scan_tmp), *tmp_b = tmp_a + n_block + 1;
     p->d_totals = reinterpret_cast<int64_t *>(tmp_b + n_rblock + 1);
@@ -547,7 +549,7 @@ static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st, bool s
         tf_nuc = p->d_nuc_tile;
         tf_prot = p->d_prot_tile;
     }
-    if (p->n_rec == 0) return MG_OK;
+    if (p->n_rec == 0) { p->prot_ready = true; return MG_OK; }
     if (p->max_seg_per_rec <= PR_MAXSEG && mg_k1_mode() == 1) {     // K1 in one launch
         const int64_t n_tile = (p->n_rec + PR_RECS - 1) / PR_RECS;
         unsigned long long *ta = reinterpret_cast<unsigned long long *>(p->d_scan_tmp), *tb = ta + n_tile + 1;
@@ -558,6 +560,7 @@ static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st, bool s
             g->d_packed, ta, tb, p->d_piece_off, p->d_piece_src, p->d_prot_off, p->d_rec_aa, p->d_rec_skip, p->d_totals, tf_nuc,
             p->n_nuc_tile, tf_prot, p->n_prot_tile, p->d_blk1k, p->blk1k_cap);
         MG_LAUNCH_CHECK();
+        p->prot_ready = true;
         return MG_OK;
     }
     k_plan_block_rec<<<(unsigned)n_rblock, 256, 0, st>>>(n_block, p->n_rec, p->d_rec_seg_off, p->d_blk_r0);
@@ -567,11 +570,31 @@ static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st, bool s
         p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, g->d_contig_len, g->d_contig_base, g->n_contigs, 2 * g->total_bases,
         tmp_a, p->d_piece_off, p->d_piece_src, p->d_totals, tf_nuc, p->n_nuc_tile, p->d_blk1k, p->blk1k_cap);
     MG_LAUNCH_CHECK();
+    p->rec_tmp = tmp_b;
+    p->rec_tile = tf_prot;
+    if (prot_flags & MG_PROT_DEFER) return MG_OK;     // the record pass comes later (mg_plan_prepare_prot_async), maybe on another stream
+    return plan_launch_records(p, st);
+}
+
+// K1, record half: amino-acid counts, first-codon trims and the offsets in the protein text (needed by the protein kernels only)
+static int plan_launch_records(mg_plan *p, cudaStream_t st) {
+    mg_genome *g = p->g;
+    const int64_t n_rblock = (p->n_rec + 255) / 256;
     k_plan_records<<<(unsigned)n_rblock, 256, 0, st>>>(
-        p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_piece_src, g->d_packed, p->d_rec_phase, prot_flags,
-        p->d_rec_aa, p->d_rec_skip, tmp_b, p->d_prot_off, p->d_totals + 1, tf_prot, p->n_prot_tile);
+        p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_piece_src, g->d_packed, p->d_rec_phase, p->prot_flags,
+        p->d_rec_aa, p->d_rec_skip, p->rec_tmp, p->d_prot_off, p->d_totals + 1, p->rec_tile, p->n_prot_tile);
     MG_LAUNCH_CHECK();
+    p->prot_ready = true;
     return MG_OK;
+}
+
+extern "C" int mg_plan_prepare_prot_async(mg_plan *p, void *stream) {
+    MG_REQUIRE(p != nullptr, "plan handle is NULL");
+    if (!p->prepared) { mg_set_error("mg_plan_prepare_async has not been called"); return MG_ESTATE; }
+    if (p->prot_ready || p->n_rec == 0) return MG_OK;
+    MG_CUDA(cudaSetDevice(p->device));
+    p->last_stream = (cudaStream_t)stream;
+    return plan_launch_records(p, (cudaStream_t)stream);
 }
 
 // K1, second half: tile -> first piece / first record, for texts of up to cap_nuc / cap_prot bytes (the real tile counts are
@@ -618,7 +641,7 @@ extern "C" int mg_plan_prepare(mg_plan *p, int prot_flags, int64_t *nuc_total, i
     MG_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     p->prepared = false;
-    int rc = plan_launch_scans(p, prot_flags, st);
+    int rc = plan_launch_scans(p, prot_flags & ~MG_PROT_DEFER, st);
     if (rc) return rc;
     int64_t totals[2];
     rc = plan_read_totals(p, st, totals);            // the one host round trip: the caller sizes its buffers from these
@@ -676,6 +699,7 @@ extern "C" int mg_plan_lengths(mg_plan *p, int64_t *nuc_len, int64_t *aa_len, vo
     MG_REQUIRE(p != nullptr, "plan handle is NULL");
     MG_REQUIRE(p->prepared, "mg_plan_prepare has not been called");
     if (p->n_rec == 0 || (!nuc_len && !aa_len)) return MG_OK;
+    if (aa_len && !p->prot_ready) { mg_set_error("the record pass was deferred (MG_PROT_DEFER): call mg_plan_prepare_prot_async first"); return MG_ESTATE; }
     MG_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     int64_t *d = nullptr;

@@ -162,16 +162,21 @@ class Plan(object):
         lit = int(t.rec_pre_len.astype(np.int64).sum() + t.rec_suf_len.astype(np.int64).sum())
         return int(pay.sum()) + lit, int((pay // 3).sum()) + lit
 
-    def prepare_async(self, nuc_capacity=None, prot_capacity=None, trimx=True, use_phase=False):
-        """K1 without the host round trip; sizes come later from totals()."""
+    def prepare_async(self, nuc_capacity=None, prot_capacity=None, trimx=True, use_phase=False, defer_records=False):
+        """K1 without the host round trip; sizes come later from totals().  defer_records: only the piece pass (what the
+        nucleotide text needs); prepare_prot() runs the record pass before anything protein-related."""
         if nuc_capacity is None or prot_capacity is None:
             a, b = self.capacities()
             nuc_capacity = a if nuc_capacity is None else nuc_capacity
             prot_capacity = b if prot_capacity is None else prot_capacity
-        flags = (_lib.MG_PROT_TRIMX if trimx else 0) | (_lib.MG_PROT_USE_PHASE if use_phase else 0)
+        flags = (_lib.MG_PROT_TRIMX if trimx else 0) | (_lib.MG_PROT_USE_PHASE if use_phase else 0) | (_lib.MG_PROT_DEFER if defer_records else 0)
         check(lib.mg_plan_prepare_async(self.handle, flags, int(nuc_capacity), int(prot_capacity), self.stream))
         self.nuc_total = self.prot_total = None
         return int(nuc_capacity), int(prot_capacity)
+
+    def prepare_prot(self, stream=None):
+        """The record pass a prepare_async(defer_records=True) left out (mg_plan_prepare_prot_async)."""
+        check(lib.mg_plan_prepare_prot_async(self.handle, stream if stream is not None else self.stream))
 
     def totals(self):
         a, b = ctypes.c_int64(0), ctypes.c_int64(0)

@@ -601,6 +601,25 @@ def test_prepare_async_equals_prepare(mg):
             # host variants after an async prepare resolve the sizes themselves
             assert plan.emit_host(protein=True).tobytes() == want_p
             plan.close()
+        # MG_PROT_DEFER: the piece pass alone serves the nucleotide text; protein calls are refused until the record pass has run
+        plan = engine.Plan(g, tbl)
+        cap_n, cap_p = plan.capacities()
+        plan.prepare_async(cap_n, cap_p, defer_records=True)
+        out_n = torch.zeros((cap_n + 31) // 32 * 32 + 32, dtype=torch.uint8, device="cuda")
+        out_p = torch.zeros((cap_p + 31) // 32 * 32 + 32, dtype=torch.uint8, device="cuda")
+        plan.emit_device(out_n.data_ptr(), protein=False)
+        with pytest.raises(_lib.MagotError):
+            plan.emit_device(out_p.data_ptr(), protein=True)
+        assert plan.totals() == (nuc, 0)
+        assert out_n[:nuc].cpu().numpy().tobytes() == want_n
+        plan.close()
+        plan = engine.Plan(g, tbl)
+        plan.prepare_async(cap_n, cap_p, defer_records=True)
+        plan.prepare_prot()
+        plan.emit_device(out_p.data_ptr(), protein=True)
+        assert plan.totals() == (nuc, prot)
+        assert out_p[:prot].cpu().numpy().tobytes() == want_p
+        plan.close()
         plan = engine.Plan(g, tbl)
         plan.prepare_async(max(nuc - 40_000, 0), prot)
         out_n = torch.zeros((nuc + 31) // 32 * 32 + 32, dtype=torch.uint8, device="cuda")
