@@ -135,6 +135,7 @@ struct mg_plan {
     bool prepared = false;
     bool prot_ready = false;                      // false between mg_plan_prepare_async(MG_PROT_DEFER) and mg_plan_prepare_prot_async
     unsigned long long *rec_tmp = nullptr;        // look-back words / tile table of the deferred record pass
+    int64_t rec_tmp_words = 0;
     int64_t *rec_tile = nullptr;
     uint32_t *d_order = nullptr;              // rank -> (job, tile) of mg_emit_products_device launches led by this plan
     int64_t order_cap = 0;

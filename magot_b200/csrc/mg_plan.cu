@@ -541,7 +541,13 @@ static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st, bool s
     const int64_t n_block = (p->n_piece + PLAN_TILE - 1) / PLAN_TILE, n_rblock = (p->n_rec + 255) / 256;
     unsigned long long *tmp_a = reinterpret_cast<unsigned long long *>(p->d_scan_tmp), *tmp_b = tmp_a + n_block + 1;
     p->d_totals = reinterpret_cast<int64_t *>(tmp_b + n_rblock + 1);
-    MG_CUDA(cudaMemsetAsync(p->d_scan_tmp, 0, p->scan_tmp_cap * sizeof(int64_t), st));
+    // Each pass zeroes ITS OWN look-back words, in its own stream, right before its kernel: the record pass of a deferred
+    // prepare may still be running on another stream when the next piece pass of the same plan starts (a bench step that
+    // re-prepares a plan does exactly that), and wiping its ticket counter / status words would leave its tiles waiting for
+    // predecessors for ever.  The two text sizes are written unconditionally by the last tile of each pass.
+    const bool one_launch = p->n_rec > 0 && p->max_seg_per_rec <= PR_MAXSEG && mg_k1_mode() == 1;
+    if (p->n_rec == 0 || one_launch) MG_CUDA(cudaMemsetAsync(p->d_scan_tmp, 0, p->scan_tmp_cap * sizeof(int64_t), st));
+    else MG_CUDA(cudaMemsetAsync(tmp_a, 0, (n_block + 1) * sizeof(unsigned long long), st));
     int64_t *tf_nuc = nullptr, *tf_prot = nullptr;
     if (scatter_tiles) {
         int rc = plan_alloc_tiles(p, cap_nuc, cap_prot, st);
@@ -571,6 +577,7 @@ static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st, bool s
         tmp_a, p->d_piece_off, p->d_piece_src, p->d_totals, tf_nuc, p->n_nuc_tile, p->d_blk1k, p->blk1k_cap);
     MG_LAUNCH_CHECK();
     p->rec_tmp = tmp_b;
+    p->rec_tmp_words = n_rblock + 1;
     p->rec_tile = tf_prot;
     if (prot_flags & MG_PROT_DEFER) return MG_OK;     // the record pass comes later (mg_plan_prepare_prot_async), maybe on another stream
     return plan_launch_records(p, st);
@@ -580,6 +587,7 @@ static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st, bool s
 static int plan_launch_records(mg_plan *p, cudaStream_t st) {
     mg_genome *g = p->g;
     const int64_t n_rblock = (p->n_rec + 255) / 256;
+    MG_CUDA(cudaMemsetAsync(p->rec_tmp, 0, p->rec_tmp_words * sizeof(unsigned long long), st));
     k_plan_records<<<(unsigned)n_rblock, 256, 0, st>>>(
         p->n_rec, p->d_rec_seg_off, p->d_piece_off, p->d_piece_src, g->d_packed, p->d_rec_phase, p->prot_flags,
         p->d_rec_aa, p->d_rec_skip, p->rec_tmp, p->d_prot_off, p->d_totals + 1, p->rec_tile, p->n_prot_tile);
@@ -679,6 +687,7 @@ extern "C" int mg_plan_totals(mg_plan *p, int64_t *nuc_total, int64_t *prot_tota
         int64_t totals[2];
         int rc = plan_read_totals(p, (cudaStream_t)stream, totals);
         if (rc) return rc;
+        if (!p->prot_ready) totals[1] = 0;               // deferred record pass not run: no protein text (the device word is stale)
         if (totals[0] > p->nuc_total || totals[1] > p->prot_total) {
             mg_set_error("text sizes (%lld nucleotide, %lld protein bytes) exceed the capacities given to mg_plan_prepare_async "
                          "(%lld, %lld): the emitted texts are truncated", (long long)totals[0], (long long)totals[1],
