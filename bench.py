@@ -1004,7 +1004,7 @@ def gpu_arm(args):
                        "genome_bp": GENOME_BP, "transcripts": N_TX, "transcripts_this_rank": int(ann.n_tx), "cds_segments_this_rank": int(T["cds"].n_seg),
                        "exons_this_rank": int(T["exon"].n_seg), "spliced_cds_bp_this_rank": wl.S_cds, "spliced_exon_bp_this_rank": wl.S_exon,
                        "bp_per_step_all_ranks": int(bp_all),
-                       "parallelism": "transcript shards per GPU, genome replicated, no collective on the data path (NCCL only for barriers and the max/sum of timing scalars); per GPU the CDS plan, its protein kernel and the exon plan run on three CUDA streams",
+                       "parallelism": "transcript shards per GPU, genome replicated, no collective on the data path (NCCL only for barriers and the max/sum of timing scalars); per GPU three CUDA streams: CDS piece pass -> K2 | CDS record pass -> K3 | exon piece pass -> K2 (K1's record pass is deferred off the critical path, MG_PROT_DEFER)",
                        "l2": "no flush: each step streams ~%.2f GB of distinct output + genome lines per GPU, far above the 126 MB L2" % ((wl.d2h_bytes + 0.5 * wl.bp_step) / 1e9),
                        "genome_device_bytes": int(g.device_bytes()), "pack_s": round(t_pack, 3), "setup_s": round(setup_s, 1),
                        "cpu_affinity": affinity},

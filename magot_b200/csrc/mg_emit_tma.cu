@@ -1,7 +1,7 @@
 // mg_emit_tma.cu -- K2 with the tile's packed genome bytes staged in shared memory by per-piece bulk copies
-// (cp.async.bulk + mbarrier: the copy engine, not the warps, waits for DRAM), and K23, the fused splice + translate
-// kernel that emits the nucleotide text AND the residues of the codons the tile already holds in one pass
-// (mg_splice_translate of SURVEY 8b; the reference translates the very string it has just joined, genome.py:704-707).
+// (cp.async.bulk + mbarrier: the copy engine, not the warps, waits for DRAM).  An A/B variant (MAGOT_EMIT=tma / mg_tune("emit", 1)):
+// measured slower than the per-lane loads of mg_emit.cu (CDS 0.118-0.122 vs 0.107 ms, exon 0.169-0.173 vs 0.155 ms on config 4;
+// profiles/r2a_bulk_copy_ab.jsonl), kept as a tested variant.  (The fused splice + translate kernel K23 lives in mg_emit.cu.)
 //
 // Why: the round-1 K2 (mg_emit.cu) fetched every 32-nibble window with per-lane global loads (3 x 8 B for the first piece
 // of a chunk, 3 x 8 B for the second): ~31 of its ~60 L1 data-pipe wavefronts per KB of text, L1 data pipe 72 % busy,
