@@ -229,6 +229,11 @@ int mg_gff_info(mg_gff *m, int64_t *info16);
 int mg_gff_column(mg_gff *m, const char *name, const void **ptr, int64_t *n, int32_t *elem_size);
 int mg_gff_strings(mg_gff *m, const int32_t *ids, int64_t n, uint8_t *pool, int64_t cap, int64_t *off);
 int64_t mg_gff_find(mg_gff *m, const uint8_t *s, int64_t n);
+/* Iteration order of a CPython-2.7 dict holding the n keys pool[off[i], off[i+1]) inserted in that order (the reference prints
+ * records by iterating plain dicts, genome.py:580, genome_tools.py:385; rounds = 2: after read_gff's copy.deepcopy, genome.py:415).
+ * perm[k] = input index of the k-th key yielded.  mg_gff_py2_order: the same on string ids of a model.  Host only.            */
+int mg_py2_order(const uint8_t *pool, const int64_t *off, int64_t n, int rounds, int64_t *perm);
+int mg_gff_py2_order(mg_gff *m, const int32_t *ids, int64_t n, int rounds, int64_t *perm);
 int mg_gff_flatten(mg_gff *m, const int64_t *tops, int64_t n_top, const int32_t *contig_of, int64_t n_contig_of, int framing,
                    mg_gff_flat **out);
 int mg_gff_flat_destroy(mg_gff_flat *f);

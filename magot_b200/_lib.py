@@ -87,6 +87,8 @@ SIGNATURES = {
     "mg_gff_column": (_i32, [_vp, ctypes.c_char_p, _pp, _pi64, ctypes.POINTER(ctypes.c_int32)]),
     "mg_gff_strings": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "mg_gff_find": (_i64, [_vp, ctypes.c_char_p, _i64]),
+    "mg_py2_order": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "mg_gff_py2_order": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "mg_gff_flatten": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _pp]),
     "mg_gff_flat_destroy": (_i32, [_vp]),
     "mg_gff_flat_column": (_i32, [_vp, ctypes.c_char_p, _pp, _pi64, ctypes.POINTER(ctypes.c_int32)]),

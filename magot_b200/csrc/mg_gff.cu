@@ -703,6 +703,82 @@ extern "C" int64_t mg_gff_find(mg_gff *m, const uint8_t *s, int64_t n) {
     return m->in.find((const char *)s, (size_t)n, fnv1a((const char *)s, (size_t)n));
 }
 
+// ---- iteration order of a CPython-2.7 dict (the reference prints records by iterating plain dicts: genome.py:580) -----------
+// Replays Objects/dictobject.c of CPython 2.7 on the keys' 2.7 string hashes (hash randomisation off): 8 initial slots, probe
+// i = 5 i + perturb + 1 with perturb >>= 5, grow when fill * 3 >= 2 * size to the first power of two > 4 * used (2 * used above
+// 50 000 entries).  rounds = 2 re-inserts the keys in the first table's slot order, which is what read_gff's copy.deepcopy does
+// (genome.py:415).  perm[k] = index (into the input) of the k-th key the dict yields.  Host only.
+static inline uint64_t py27_string_hash(const unsigned char *p, size_t len) {
+    if (len == 0) return 0;
+    uint64_t x = (uint64_t)p[0] << 7;
+    for (size_t i = 0; i < len; i++) x = (1000003ull * x) ^ p[i];
+    x ^= (uint64_t)len;
+    if (x == ~0ull) x = ~0ull - 1;                    // -1 is CPython's error value: -2
+    return x;
+}
+
+static inline void py27_place(std::vector<int64_t> &tab, size_t mask, const std::vector<uint64_t> &h, int64_t k) {
+    const uint64_t hh = h[k];
+    size_t i = hh & mask;
+    if (tab[i] != -1) {
+        uint64_t perturb = hh, j = i;
+        while (true) {
+            j = (j << 2) + j + perturb + 1;
+            perturb >>= 5;
+            i = j & mask;
+            if (tab[i] == -1) break;
+        }
+    }
+    tab[i] = k;
+}
+
+static void py27_dict_order(const std::vector<uint64_t> &h, std::vector<int64_t> &order) {     // order: insertion order in, iteration order out
+    size_t size = 8, used = 0;
+    std::vector<int64_t> slots(size, -1), grown;
+    for (int64_t k : order) {
+        py27_place(slots, size - 1, h, k);
+        used++;
+        if (used * 3 >= size * 2) {
+            const size_t minused = (used > 50000 ? 2 : 4) * used;
+            size_t newsize = 8;
+            while (newsize <= minused) newsize <<= 1;
+            grown.assign(newsize, -1);
+            for (int64_t k2 : slots) if (k2 != -1) py27_place(grown, newsize - 1, h, k2);
+            slots.swap(grown);
+            size = newsize;
+        }
+    }
+    size_t o = 0;
+    for (int64_t k : slots) if (k != -1) order[o++] = k;
+}
+
+extern "C" int mg_py2_order(const uint8_t *pool, const int64_t *off, int64_t n, int rounds, int64_t *perm) {
+    if (n < 0 || (n > 0 && (!off || !perm)) || rounds < 1) { mg_set_error("mg_py2_order: bad argument"); return MG_EINVAL; }
+    std::vector<uint64_t> h((size_t)n);
+    for (int64_t i = 0; i < n; i++) h[i] = py27_string_hash(pool + off[i], (size_t)(off[i + 1] - off[i]));
+    std::vector<int64_t> order((size_t)n);
+    for (int64_t i = 0; i < n; i++) order[i] = i;
+    for (int r = 0; r < rounds; r++) py27_dict_order(h, order);
+    for (int64_t i = 0; i < n; i++) perm[i] = order[i];
+    return MG_OK;
+}
+
+// the same on string ids of a model (no Python string is built)
+extern "C" int mg_gff_py2_order(mg_gff *m, const int32_t *ids, int64_t n, int rounds, int64_t *perm) {
+    if (!m || n < 0 || (n > 0 && (!ids || !perm)) || rounds < 1) { mg_set_error("mg_gff_py2_order: bad argument"); return MG_EINVAL; }
+    std::vector<uint64_t> h((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        if (ids[i] < 0 || (size_t)ids[i] >= m->in.strs.size()) { mg_set_error("mg_gff_py2_order: bad string id"); return MG_EINVAL; }
+        const Str &t = m->in.strs[ids[i]];
+        h[i] = py27_string_hash((const unsigned char *)t.p, t.len);
+    }
+    std::vector<int64_t> order((size_t)n);
+    for (int64_t i = 0; i < n; i++) order[i] = i;
+    for (int r = 0; r < rounds; r++) py27_dict_order(h, order);
+    for (int64_t i = 0; i < n; i++) perm[i] = order[i];
+    return MG_OK;
+}
+
 // ---- flattener: AnnotationSet.get_fasta(feature) on the integer model ------------------------------------------------------
 // tops[0..n_top): rows of the feature table in the set's iteration order.  contig_of[string id] = contig index of that seqid in
 // the packed genome, -1 = not a contig.  Emits, per top, the records ParentAnnotation.get_fasta would (genome.py:683-719):

@@ -737,11 +737,10 @@ def _native_get_fasta(annotation_set, model, feature, seq_type, longest, genomic
     if rows is None or rows.size == 0:
         return None
     ids = model.column("id")[rows]
-    keys = model.strings(ids)
-    if len(set(keys)) != len(keys):
+    if np.unique(ids).size != ids.size:                  # interned: equal strings <=> equal ids
         return None
-    row_of = dict(zip(keys, rows.tolist()))
-    tops = np.fromiter((row_of[k] for k in _order(keys, deepcopy=True)), dtype=np.int64, count=len(keys))
+    # tops in the order the reference's table dict iterates after its deepcopy, computed on the model's strings
+    tops = np.ascontiguousarray(rows[model.py2_order(ids, deepcopy=True)] if RECORD_ORDER == "py2" else rows, dtype=np.int64)
     seq_ids = np.unique(model.column("seqid"))
     seq_ids = seq_ids[seq_ids >= 0]
     contig_of = np.full(model.n_strings, -1, dtype=np.int32)

@@ -109,6 +109,15 @@ class Model(object):
     def string(self, sid):
         return None if sid < 0 or sid == self.none_id else self.strings([sid])[0]
 
+    def py2_order(self, ids, deepcopy=False):
+        """Indices into `ids` (string ids, unique) in the order a CPython-2.7 dict keyed by those strings iterates them
+        (after a deepcopy: re-inserted once in slot order), computed on the model's own strings (mg_gff_py2_order)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        perm = np.empty(ids.size, dtype=np.int64)
+        check(lib.mg_gff_py2_order(self.handle, ids.ctypes.data_as(ctypes.c_void_p), ids.size, 2 if deepcopy else 1,
+                                   perm.ctypes.data_as(ctypes.c_void_p)))
+        return perm
+
     def find(self, s):
         b = s.encode("latin-1")
         return int(lib.mg_gff_find(self.handle, b, len(b)))

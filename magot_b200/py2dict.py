@@ -44,9 +44,37 @@ def string_hashes(keys):
     return x.tolist()
 
 
+def _native_perm(keys, rounds):
+    """mg_py2_order (csrc/mg_gff.cu) on latin-1 str keys: permutation as a list, or None when the keys are not all str / the
+    library is not loadable (the pure-Python replay below is the same algorithm)."""
+    if len(keys) < 64 or not all(type(k) is str for k in keys):
+        return None
+    try:
+        import ctypes
+        from ._lib import lib
+        enc = "".join(keys).encode("latin-1")
+        if len(enc) != sum(map(len, keys)):
+            return None
+        off = np.zeros(len(keys) + 1, dtype=np.int64)
+        np.cumsum(np.fromiter(map(len, keys), dtype=np.int64, count=len(keys)), out=off[1:])
+        perm = np.empty(len(keys), dtype=np.int64)
+        if lib.mg_py2_order(enc, off.ctypes.data_as(ctypes.c_void_p), len(keys), rounds, perm.ctypes.data_as(ctypes.c_void_p)) != 0:
+            return None
+        return perm.tolist()
+    except Exception:
+        return None
+
+
 def py2_order(keys):
     """Keys (unique, in insertion order) -> the order a CPython 2.7 dict iterates them in."""
     keys = list(keys)
+    perm = _native_perm(keys, 1)
+    if perm is not None:
+        return [keys[i] for i in perm]
+    return _py2_order_python(keys)
+
+
+def _py2_order_python(keys):
     hashes = string_hashes(keys)
     size = 8
     mask = 7
@@ -92,7 +120,11 @@ def py2_order(keys):
 
 def py2_order_after_deepcopy(keys):
     """Order after read_gff's copy.deepcopy (genome.py:415): re-insert in old slot order."""
-    return py2_order(py2_order(keys))
+    keys = list(keys)
+    perm = _native_perm(keys, 2)
+    if perm is not None:
+        return [keys[i] for i in perm]
+    return _py2_order_python(_py2_order_python(keys))
 
 
 def py2_update_order(keys):

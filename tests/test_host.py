@@ -52,12 +52,18 @@ def test_py2_order_matches_oracle_emulator():
     assert py2dict.py2_order_after_deepcopy(keys[:700]) == oracle_py2.py2_order_after_deepcopy(keys[:700])
     hs = py2dict.string_hashes(keys[:50] + ["", "a", "abc"])
     assert hs[-3:] == [0, 12416037344, 1453079729188098211]
+    # the native replay (mg_py2_order, used for >= 64 str keys) and the pure-Python one are the same algorithm
+    assert py2dict._native_perm(keys, 1) is not None
+    assert py2dict._py2_order_python(keys) == oracle_py2.py2_order(keys)
+    assert py2dict.py2_order(keys[:10]) == oracle_py2.py2_order(keys[:10])          # short lists take the Python path
+    assert py2dict.py2_order([b"ab", "cd"] + keys[:80]) == py2dict._py2_order_python([b"ab", "cd"] + keys[:80])   # non-str key: Python path
 
 
 def test_py2_order_large_growth_rule():
     # above 50000 entries CPython 2.7 doubles instead of quadrupling; both emulators must agree there
     keys = ["tx%07d" % i for i in range(70000)]
     assert py2dict.py2_order(keys) == oracle_py2.py2_order(keys)
+    assert py2dict.py2_order_after_deepcopy(keys) == oracle_py2.py2_order_after_deepcopy(keys)
 
 
 def _model_signature_product(aset):
