@@ -121,6 +121,7 @@ struct mg_plan {
     int64_t n_nuc_tile = 0, n_prot_tile = 0;
     int32_t *d_blk1k = nullptr;               // first piece of every 1 KB block of the nucleotide text (+ sentinel), for k_emit_nuc_stream
     int64_t blk1k_cap = 0;                    // entries the table can take (from the host-side upper bound of the text size)
+    bool blk1k_ready = false;                 // filled by the last prepare (only when the streaming K2 variant was selected then)
     int64_t max_seg_per_rec = 0;             // longest record (segments): k_plan_rec walks a record with one thread
     int64_t nuc_upper = 0;                    // host-side upper bound of the nucleotide text size: sum(max(0, end-start+1)) + framing
     int64_t *d_tile_buf = nullptr;

@@ -199,6 +199,10 @@ __global__ void __launch_bounds__(S4_THREADS, S4_MINB) k_emit_nuc_stream(
 
 int mg_launch_nuc_stream(mg_plan *p, uint8_t *out_dev, cudaStream_t st) {
     mg_genome *g = p->g;
+    if (!p->blk1k_ready) {                           // the plan was prepared while another K2 variant was selected
+        mg_set_error("the 1 KB block table of this plan was not built: select the streaming variant (mg_tune(\"emit\", 2)) before mg_plan_prepare");
+        return MG_ESTATE;
+    }
     k_emit_nuc_stream<<<(unsigned)p->n_nuc_tile, S4_THREADS, 0, st>>>(g->d_packed, p->d_piece_off, p->d_piece_src, p->n_piece, p->d_blk1k,
                                                                      p->d_totals, p->nuc_total, g->total_bases, p->d_lit, g->d_exc_pos,
                                                                      g->d_exc_byte, g->n_exc, out_dev);

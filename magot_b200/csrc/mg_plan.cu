@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256, PLAN_MINB) k_plan_pieces(int64_t n_piece,
             }
             // the same at 1 KB granularity (one warp of k_emit_nuc_stream = one 1 KB block): a piece of ~190 bytes holds the first
             // byte of a block once in five times
-            if (len[it] > 0) {
+            if (blk1k_cap > 0 && len[it] > 0) {
                 for (int64_t t = (run + 1023) >> 10; (t << 10) < run + len[it] && t < blk1k_cap; t++) blk1k[t] = (int32_t)(p0 + it);
             }
         }
@@ -514,6 +514,14 @@ extern "C" int mg_plan_create(mg_genome *g, int64_t n_rec, const int64_t *rec_se
     for (int64_t r = 0; r < n_rec; r++) p->max_seg_per_rec = std::max(p->max_seg_per_rec, rec_seg_off[r + 1] - rec_seg_off[r]);
     TRY(dalloc(p, &p->d_scan_tmp, p->scan_tmp_cap, st));
 #undef TRY
+    if (n_rec > 0) {
+        // record -> first piece block: a function of rec_seg_off alone, so it is computed here, once per table, and not in every
+        // prepare (one launch less on the critical path of a step: ~4 us of a 74 us step at 8 GPUs)
+        const int64_t n_block = (p->n_piece + PLAN_TILE - 1) / PLAN_TILE, n_rblock = (n_rec + 255) / 256;
+        k_plan_block_rec<<<(unsigned)n_rblock, 256, 0, st>>>(n_block, n_rec, p->d_rec_seg_off, p->d_blk_r0);
+        MG_COUNT_LAUNCH();
+        if (cudaGetLastError() != cudaSuccess) { mg_set_error("k_plan_block_rec launch failed"); mg_plan_destroy(p); return MG_ECUDA; }
+    }
     *out = p;
     return MG_OK;
 }
@@ -567,14 +575,16 @@ static int plan_launch_scans(mg_plan *p, int prot_flags, cudaStream_t st, bool s
             p->n_nuc_tile, tf_prot, p->n_prot_tile, p->d_blk1k, p->blk1k_cap);
         MG_LAUNCH_CHECK();
         p->prot_ready = true;
+        p->blk1k_ready = true;
         return MG_OK;
     }
-    k_plan_block_rec<<<(unsigned)n_rblock, 256, 0, st>>>(n_block, p->n_rec, p->d_rec_seg_off, p->d_blk_r0);
-    MG_LAUNCH_CHECK();
+    // (d_blk_r0 was filled by mg_plan_create.)  The 1 KB block table is read by the streaming K2 variant only.
+    const bool want_blk1k = mg_emit_mode() == 2;
+    p->blk1k_ready = want_blk1k;
     k_plan_pieces<<<(unsigned)n_block, 256, 0, st>>>(
         p->n_piece, p->n_rec, p->d_rec_seg_off, p->d_blk_r0, p->d_seg_contig, p->d_seg_start, p->d_seg_end, p->d_seg_strand,
         p->d_rec_lit_off, p->d_rec_pre, p->d_rec_suf, g->d_contig_len, g->d_contig_base, g->n_contigs, 2 * g->total_bases,
-        tmp_a, p->d_piece_off, p->d_piece_src, p->d_totals, tf_nuc, p->n_nuc_tile, p->d_blk1k, p->blk1k_cap);
+        tmp_a, p->d_piece_off, p->d_piece_src, p->d_totals, tf_nuc, p->n_nuc_tile, p->d_blk1k, want_blk1k ? p->blk1k_cap : 0);
     MG_LAUNCH_CHECK();
     p->rec_tmp = tmp_b;
     p->rec_tmp_words = n_rblock + 1;
