@@ -80,6 +80,15 @@ def _gff_columns(obj):
 
 
 _GFF3_FORMATS = ("simple gff3", "extended gff3", "exon added gff3")
+
+
+def _gff_format_kind(gff_format):
+    """'gff3' | 'hint' | 'gtf' | None (a format get_gff does not know: the reference then fails on an unbound local)."""
+    if gff_format in _GFF3_FORMATS:
+        return "gff3"
+    if gff_format[:13] == "augustus hint":
+        return "hint"
+    return "gtf" if gff_format == "gtf" else None
 _NOT_EXTENDED = ('ID', 'Parent', 'score', 'strand', 'seqid', 'feature_type', 'phase', 'source')
 
 
@@ -481,22 +490,24 @@ class BaseAnnotation(object):
         """genome.py:616-645 -- one GFF line ("exon added gff3": an exon twin line before every CDS line).
         Returns None without an annotation_set; an unknown format or `gtf` without a parent raise as in the reference
         (UnboundLocalError / TypeError)."""
-        if self.annotation_set is not None:
-            fields_list = _gff_columns(self)
-            if gff_format in _GFF3_FORMATS:
-                defline = _gff3_defline(self, gff_format)
-            elif gff_format[:13] == "augustus hint":
-                gff_format_fields = gff_format.split()
-                fields_list[2] = gff_format_fields[2]
-                defline = "src=" + gff_format_fields[3]
-                if len(gff_format_fields) > 4:
-                    defline = defline + ";pri=" + gff_format_fields[4]
-            elif gff_format == "gtf":
-                defline = 'transcript_id ' + self.parent + ';gene_id ' + self.annotation_set[self.parent].parent
-            fields_list.append(defline)
-            if gff_format == "exon added gff3" and fields_list[2] == "CDS":
-                return '\t'.join(fields_list).replace('\tCDS\t', '\texon\t').replace('ID=', 'ID=ExonOf') + "\n" + '\t'.join(fields_list)
-            return '\t'.join(fields_list)
+        if self.annotation_set is None:
+            return None
+        cols = _gff_columns(self)
+        kind = _gff_format_kind(gff_format)
+        if kind == "gff3":
+            attributes = _gff3_defline(self, gff_format)
+        elif kind == "hint":                              # "augustus hint <type> <src> [<pri>]"
+            words = gff_format.split()
+            cols[2] = words[2]
+            attributes = ";pri=".join(["src=" + words[3]] + words[4:5])
+        elif kind == "gtf":                               # a parentless feature raises TypeError (str + None), as in the reference
+            attributes = 'transcript_id ' + self.parent + ';gene_id ' + self.annotation_set[self.parent].parent
+        else:
+            raise UnboundLocalError("local variable 'defline' referenced before assignment")
+        line = '\t'.join(cols + [attributes])
+        if gff_format == "exon added gff3" and cols[2] == "CDS":
+            return line.replace('\tCDS\t', '\texon\t').replace('ID=', 'ID=ExonOf') + "\n" + line
+        return line
 
     def get_seq(self):
         """genome.py:603-614: contig[start-1:end] (Python slice clamping), reverse-complemented on '-'.
@@ -550,35 +561,30 @@ class ParentAnnotation(object):
         """genome.py:733-778 -- this feature's line (not for `gtf` / `augustus hint`) followed by its children's,
         children sorted by coordinates (a repeated coordinate pair is keyed (start, end + number of children so
         far)); "exon added gff3" moves every CDS line behind the other lines of the feature."""
-        if self.annotation_set is not None:
-            fields_list = _gff_columns(self)
-            parent_line = True
-            if gff_format in _GFF3_FORMATS:
-                defline = _gff3_defline(self, gff_format)
-            elif gff_format[:13] == "augustus hint" or gff_format == 'gtf':
-                parent_line = False
-            if parent_line:
-                fields_list.append(defline)
-                lines_list = ['\t'.join(fields_list)]
-            else:
-                lines_list = []
-            child_dict = {}
-            for child in self.child_list:
-                child_object = self.annotation_set[child]
-                cc = child_object.get_coords()
-                if cc not in child_dict:
-                    child_dict[cc] = child_object.get_gff(gff_format)
-                else:
-                    child_dict[(cc[0], cc[1] + len(child_dict))] = child_object.get_gff(gff_format)
-            for child_index in sorted(child_dict):
-                lines_list.append(child_dict[child_index])
-            if gff_format == "exon added gff3":
-                lines_list = '\n'.join(lines_list).split('\n')
-                for line in lines_list[:]:
-                    if line.split('\t')[2] == "CDS":
-                        lines_list.remove(line)
-                        lines_list.append(line)
-            return '\n'.join(lines_list)
+        if self.annotation_set is None:
+            return None
+        cols = _gff_columns(self)                        # evaluated for every format (a childless parent raises here, as its eval does)
+        kind = _gff_format_kind(gff_format)
+        if kind == "gff3":
+            out = ['\t'.join(cols + [_gff3_defline(self, gff_format)])]
+        elif kind in ("hint", "gtf"):
+            out = []
+        else:
+            raise UnboundLocalError("local variable 'defline' referenced before assignment")
+        by_coords = {}
+        for name in self.child_list:
+            child = self.annotation_set[name]
+            key = child.get_coords()
+            if key in by_coords:
+                key = (key[0], key[1] + len(by_coords))
+            by_coords[key] = child.get_gff(gff_format)
+        out.extend(by_coords[key] for key in sorted(by_coords))
+        if gff_format == "exon added gff3":
+            # the reference removes and re-appends every CDS line while walking a copy of the list: a stable partition
+            physical = '\n'.join(out).split('\n')
+            is_cds = [ln.split('\t')[2] == "CDS" for ln in physical]
+            out = [ln for ln, c in zip(physical, is_cds) if not c] + [ln for ln, c in zip(physical, is_cds) if c]
+        return '\n'.join(out)
 
     def get_fasta(self, seq_type="nucleotide", longest=False, genomic=False, name_from='ID'):
         """genome.py:677-731.  One device pass for this annotation and all its descendants."""
