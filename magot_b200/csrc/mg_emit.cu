@@ -881,14 +881,17 @@ extern "C" int mg_emit_nuc_prot_device(mg_plan *p, uint8_t *nuc_out_dev, uint8_t
 // (config 4, ncu: 368 + 241 + 258 MB read for 183 MB of distinct packed bytes): each launch moves far more than the 126 MB L2
 // holds, so nothing survives from one launch to the next.  Here the tiles of up to three jobs -- nucleotide text of plan A
 // (exon table), nucleotide text of plan B (CDS table), protein text of plan B -- go into ONE grid in an interleaved order:
-// every job advances through its text at the same FRACTIONAL pace, job B a little behind job A and the protein a little
-// behind job B.  Both tables list the same transcripts in the same order, so when a CDS tile runs, the exon tiles of the same
-// transcripts ran a few thousand CTAs earlier and the 64-byte granules it needs are still in L2.
+// every job advances through its text at the same FRACTIONAL pace (optionally job B a little behind job A and the protein a
+// little behind job B: lag).  Both tables list the same transcripts in the same order, so when a CDS tile runs, the exon tiles
+// of the same transcripts run in the same wave of CTAs or ran just before, and the 64-byte granules it needs are in L2.
 //   order of tile t of job j:  key = floor((2t + 1) * 2^30 / (2 n_j)) + lag_j, ties by (job, tile); k_multi_order turns it
 //   into rank -> (job, tile) with closed-form counts (no sort, no search); n_j comes from the text sizes ON THE DEVICE.
 #define MULTI_SH 30
 #ifndef MULTI_LAG_PPM
-#define MULTI_LAG_PPM 60000                          // lag between consecutive jobs, in millionths of a text (tunable: mg_tune("multi_lag"))
+#define MULTI_LAG_PPM 0                              // lag between consecutive jobs, in millionths of a text (mg_tune("multi_lag")).  Measured on
+                                                     // config 4: lag 0 -> 0.353 ms / 424 MB of DRAM reads, 2 % -> 0.357 ms / 469 MB, 6 % -> 0.375 ms / 789 MB
+                                                     // (three launches: 0.378 ms / 868 MB): L2 keeps a line for ~5 % of a launch, and tiles of equal
+                                                     // rank run within one wave of each other anyway
 #endif
 static int g_multi_lag_ppm = MULTI_LAG_PPM;
 void mg_set_multi_lag(int ppm) { g_multi_lag_ppm = ppm; }
